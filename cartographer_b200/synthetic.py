@@ -1,0 +1,165 @@
+"""Seeded synthetic inputs for tests and bench.py.
+
+Pure numpy; no oracle, no CUDA.  Produces the flat records the C ABI consumes:
+probability-grid cells (uint16, row-major ``num_x * y + x``), map limits, and
+scan point clouds (N x 3 float32 in the sensor frame).
+
+World 2D: a 50 m x 50 m procedural floor plan (outer walls, axis-aligned rooms
+with door gaps, square pillars) rasterised at 5 cm; scans are 1081-beam / 270
+degree ray casts with N(0, 1 cm) range noise, beams without a hit clamp to the
+maximum range so N is always 1081.
+"""
+import math
+
+import numpy as np
+
+K_MIN_P = np.float32(0.1)
+K_MAX_P = np.float32(1.0) - K_MIN_P
+K_MIN_COST = np.float32(1.0) - K_MAX_P
+K_MAX_COST = np.float32(1.0) - K_MIN_P
+
+
+def correspondence_cost_to_value(cost):
+    """mapping/probability_values.h:32-44 (BoundedFloatToValue) in float32."""
+    c = np.clip(np.asarray(cost, np.float32), K_MIN_COST, K_MAX_COST)
+    scaled = (c - K_MIN_COST) * (np.float32(32766.0) / (K_MAX_COST - K_MIN_COST))
+    return (np.floor(scaled.astype(np.float64) + 0.5).astype(np.int64) + 1).astype(np.uint16)
+
+
+def probability_to_cell_value(p):
+    return correspondence_cost_to_value(np.float32(1.0) - np.asarray(p, np.float32))
+
+
+class GridSpec:
+    """Plain record of a ProbabilityGrid (cells[y, x]) + MapLimits."""
+
+    def __init__(self, cells, resolution, max_x, max_y):
+        self.cells = np.ascontiguousarray(cells, np.uint16)
+        self.num_y, self.num_x = self.cells.shape
+        self.resolution = float(resolution)
+        self.max_x = float(max_x)
+        self.max_y = float(max_y)
+        self.min_cost = float(K_MIN_COST)
+        self.max_cost = float(K_MAX_COST)
+
+
+def world_to_cell(grid, wx, wy):
+    """mapping/2d/map_limits.h:69-76: index.x <- world y, index.y <- world x."""
+    cx = np.floor((grid.max_y - wy) / grid.resolution).astype(np.int64)
+    cy = np.floor((grid.max_x - wx) / grid.resolution).astype(np.int64)
+    return cx, cy
+
+
+def make_floorplan(seed, size_m=50.0, resolution=0.05, rooms=8, pillars=20):
+    """Boolean occupancy (cells[y, x]) of a procedural floor plan, plus limits.
+
+    Returns (occ, max_x, max_y); world x in (max_x - size, max_x], same for y.
+    """
+    rng = np.random.RandomState(seed)
+    n = int(round(size_m / resolution))
+    occ = np.zeros((n, n), bool)
+    t = 3  # wall thickness in cells
+    occ[:t, :] = occ[-t:, :] = True
+    occ[:, :t] = occ[:, -t:] = True
+    for _ in range(rooms):
+        w = rng.randint(n // 8, n // 3)
+        h = rng.randint(n // 8, n // 3)
+        x0 = rng.randint(t, n - w - t)
+        y0 = rng.randint(t, n - h - t)
+        wall = np.zeros_like(occ)
+        wall[y0:y0 + t, x0:x0 + w] = True
+        wall[y0 + h - t:y0 + h, x0:x0 + w] = True
+        wall[y0:y0 + h, x0:x0 + t] = True
+        wall[y0:y0 + h, x0 + w - t:x0 + w] = True
+        # two door gaps per room
+        for _d in range(2):
+            side = rng.randint(4)
+            g = rng.randint(20, 40)
+            if side < 2:
+                gx = rng.randint(x0 + t, max(x0 + t + 1, x0 + w - g - t))
+                yy = y0 if side == 0 else y0 + h - t
+                wall[yy:yy + t, gx:gx + g] = False
+            else:
+                gy = rng.randint(y0 + t, max(y0 + t + 1, y0 + h - g - t))
+                xx = x0 if side == 2 else x0 + w - t
+                wall[gy:gy + g, xx:xx + t] = False
+        occ |= wall
+    for _ in range(pillars):
+        s = rng.randint(4, 12)
+        x0 = rng.randint(t, n - s - t)
+        y0 = rng.randint(t, n - s - t)
+        occ[y0:y0 + s, x0:x0 + s] = True
+    return occ, size_m / 2.0, size_m / 2.0
+
+
+def occupancy_to_grid(occ, seed, resolution, max_x, max_y, unknown_fraction=0.25):
+    """Wall cells p~U(0.70,0.90); free cells p~U(0.10,0.25); 25% unknown (value 0)."""
+    rng = np.random.RandomState(seed + 7919)
+    p = np.where(occ, rng.uniform(0.70, 0.90, occ.shape), rng.uniform(0.10, 0.25, occ.shape))
+    cells = probability_to_cell_value(p.astype(np.float32))
+    unknown = (rng.uniform(size=occ.shape) < unknown_fraction) & ~occ
+    cells[unknown] = 0
+    return GridSpec(cells, resolution, max_x, max_y)
+
+
+def make_grid2d(seed, size_cells=1000, resolution=0.05):
+    size_m = size_cells * resolution
+    occ, max_x, max_y = make_floorplan(seed, size_m=size_m, resolution=resolution,
+                                       rooms=max(2, int(8 * size_m / 50.0)),
+                                       pillars=max(3, int(20 * size_m / 50.0)))
+    return occupancy_to_grid(occ, seed, resolution, max_x, max_y), occ
+
+
+def crop_grid(grid, occ, x0, y0, nx, ny):
+    """Sub-grid of nx x ny cells starting at cell (x0, y0); limits shifted accordingly."""
+    cells = grid.cells[y0:y0 + ny, x0:x0 + nx]
+    # cell (x0, y0) of the parent becomes (0, 0): max shifts by resolution * (y0, x0)
+    return (GridSpec(cells, grid.resolution, grid.max_x - grid.resolution * y0,
+                     grid.max_y - grid.resolution * x0), occ[y0:y0 + ny, x0:x0 + nx])
+
+
+def random_free_pose(occ, grid, rng, margin_cells=20):
+    ny, nx = occ.shape
+    while True:
+        cx = rng.randint(margin_cells, nx - margin_cells)
+        cy = rng.randint(margin_cells, ny - margin_cells)
+        if not occ[max(0, cy - 4):cy + 5, max(0, cx - 4):cx + 5].any():
+            wx = grid.max_x - (cy + 0.5) * grid.resolution
+            wy = grid.max_y - (cx + 0.5) * grid.resolution
+            return np.array([wx, wy, rng.uniform(-math.pi, math.pi)])
+
+
+def cast_scan(occ, grid, pose, beams=1081, fov_deg=270.0, max_range=30.0, noise=0.01, seed=0):
+    """Ray-cast a planar lidar from `pose` (world x, y, yaw); returns N x 3 float32 in the
+    sensor frame.  Beams with no hit clamp to max_range."""
+    rng = np.random.RandomState(seed)
+    ang = np.deg2rad(np.linspace(-fov_deg / 2.0, fov_deg / 2.0, beams))
+    step = grid.resolution * 0.5
+    steps = np.arange(1, int(max_range / step) + 1) * step                  # (T,)
+    ca, sa = np.cos(ang + pose[2]), np.sin(ang + pose[2])
+    ranges = np.full(beams, max_range)
+    ny, nx = occ.shape
+    alive = np.ones(beams, bool)
+    chunk = 128
+    for t0 in range(0, len(steps), chunk):
+        r = steps[t0:t0 + chunk]                                             # (c,)
+        wx = pose[0] + np.outer(ca, r)
+        wy = pose[1] + np.outer(sa, r)
+        cx, cy = world_to_cell(grid, wx, wy)
+        inside = (cx >= 0) & (cx < nx) & (cy >= 0) & (cy < ny)
+        hit = np.zeros_like(inside)
+        hit[inside] = occ[cy[inside], cx[inside]]
+        hit |= ~inside                                                       # leaving the map ends the ray
+        any_hit = hit.any(axis=1) & alive
+        first = hit.argmax(axis=1)
+        rr = r[first]
+        left_map = ~inside[np.arange(beams), first]
+        ranges[any_hit] = np.where(left_map[any_hit], max_range, rr[any_hit])
+        alive &= ~any_hit
+        if not alive.any():
+            break
+    ranges = np.clip(ranges + rng.normal(0.0, noise, beams), 0.05, max_range)
+    pts = np.zeros((beams, 3), np.float32)
+    pts[:, 0] = (ranges * np.cos(ang)).astype(np.float32)
+    pts[:, 1] = (ranges * np.sin(ang)).astype(np.float32)
+    return pts

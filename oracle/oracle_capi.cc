@@ -1,0 +1,324 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_common.h).
+// Flat C entry points so tests/ and bench.py's cpu_baseline leg can drive the
+// oracle through ctypes.  Not part of the product; libcsm_b200.so never sees it.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "oracle_2d.h"
+
+using namespace oracle;
+
+namespace {
+
+ProbabilityGrid MakeGrid(const uint16_t* cells, int nx, int ny, double res, double max_x,
+                         double max_y, float min_cost, float max_cost) {
+  ProbabilityGrid grid(MapLimits{res, max_x, max_y, CellLimits{nx, ny}}, min_cost, max_cost);
+  std::memcpy(grid.cells.data(), cells, sizeof(uint16_t) * static_cast<size_t>(nx) * ny);
+  return grid;
+}
+
+PointCloud MakeCloud(const float* xyz, int n) {
+  PointCloud cloud(n);
+  for (int i = 0; i < n; ++i) cloud[i] = Vec3f{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+  return cloud;
+}
+
+void FillStats(const MatchStats& s, int64_t* out) {
+  if (!out) return;
+  out[0] = s.candidates_scored;
+  out[1] = s.lowest_resolution_candidates;
+  out[2] = s.nodes_expanded;
+  out[3] = s.num_scans;
+  out[4] = s.best_scan_index;
+  out[5] = s.best_x_offset;
+  out[6] = s.best_y_offset;
+}
+
+struct Fast2DHandle {
+  ProbabilityGrid grid;
+  FastOptions2D options;
+  FastCorrelativeScanMatcher2D matcher;
+  Fast2DHandle(ProbabilityGrid g, FastOptions2D o)
+      : grid(std::move(g)), options(o), matcher(grid, o) {}
+};
+
+struct Frontend2D {
+  SearchParameters sp;
+  std::vector<DiscreteScan2D> scans;
+  std::vector<PointCloud> rotated;
+};
+
+}  // namespace
+
+extern "C" {
+
+void orc_value_to_cost_table(float min_cost, float max_cost, float* out65536) {
+  const std::vector<float> t = PrecomputeValueToBoundedFloat(0, max_cost, min_cost, max_cost);
+  std::memcpy(out65536, t.data(), sizeof(float) * 65536);
+}
+uint16_t orc_probability_to_value(float p) { return ProbabilityToValue(p); }
+uint16_t orc_correspondence_cost_to_value(float c) { return CorrespondenceCostToValue(c); }
+float orc_constant(int which) {
+  switch (which) {
+    case 0: return kMinProbability;
+    case 1: return kMaxProbability;
+    case 2: return kMinCorrespondenceCost;
+    case 3: return kMaxCorrespondenceCost;
+  }
+  return 0.f;
+}
+
+void orc_get_cell_index(double res, double max_x, double max_y, float px, float py, int32_t* out2) {
+  const MapLimits l{res, max_x, max_y, CellLimits{1, 1}};
+  const Array2i c = l.GetCellIndex(px, py);
+  out2[0] = c.x;
+  out2[1] = c.y;
+}
+
+// SearchParameters(linear, angular, cloud, resolution)
+void orc_search_params(double lin, double ang, const float* xyz, int n, double res,
+                       int32_t* num_angular, double* step, int32_t* num_scans,
+                       int32_t* num_linear) {
+  const SearchParameters sp(lin, ang, MakeCloud(xyz, n), res);
+  *num_angular = sp.num_angular_perturbations;
+  *step = sp.angular_perturbation_step_size;
+  *num_scans = sp.num_scans;
+  *num_linear = sp.linear_bounds.empty() ? 0 : sp.linear_bounds[0].max_x;
+}
+
+// Candidate2D(scan, xo, yo, SearchParameters(num_lin, num_ang, step, res)) -> x, y, orientation
+void orc_candidate(int num_lin, int num_ang, double step, double res, int scan, int xo, int yo,
+                   double* out3) {
+  const SearchParameters sp(num_lin, num_ang, step, res);
+  const Candidate2D c(scan, xo, yo, sp);
+  out3[0] = c.x;
+  out3[1] = c.y;
+  out3[2] = c.orientation;
+}
+
+// GenerateRotatedScans with the "for testing" SearchParameters ctor.
+void orc_generate_rotated_scans(const float* xyz, int n, int num_ang, double step,
+                                float* out /* (2*num_ang+1) * n * 3 */) {
+  const SearchParameters sp(0, num_ang, step, 0.);
+  const std::vector<PointCloud> scans = GenerateRotatedScans(MakeCloud(xyz, n), sp);
+  size_t k = 0;
+  for (const PointCloud& s : scans)
+    for (const Vec3f& p : s) {
+      out[k++] = p.x;
+      out[k++] = p.y;
+      out[k++] = p.z;
+    }
+}
+
+void orc_discretize_scans(double res, double max_x, double max_y, int nx, int ny,
+                          const float* scans_xyz, int num_scans, int n, float tx, float ty,
+                          int32_t* out /* S*n*2 */) {
+  const MapLimits l{res, max_x, max_y, CellLimits{nx, ny}};
+  std::vector<PointCloud> scans;
+  for (int s = 0; s < num_scans; ++s) scans.push_back(MakeCloud(scans_xyz + 3 * size_t(s) * n, n));
+  const std::vector<DiscreteScan2D> d = DiscretizeScans(l, scans, tx, ty);
+  size_t k = 0;
+  for (const DiscreteScan2D& s : d)
+    for (const Array2i& c : s) {
+      out[k++] = c.x;
+      out[k++] = c.y;
+    }
+}
+
+// The matcher front-end exactly as MatchWithSearchParameters runs it
+// (fast...2d.cc:236-247): rotate by initial yaw, rotated scans, discretise,
+// ShrinkToFit.  `full` selects the MatchFullSubmap window/centre (:210-225).
+void* orc_frontend2d_create(double res, double max_x, double max_y, int nx, int ny,
+                            const float* xyz, int n, const double* init_pose, int full,
+                            double lin, double ang, int rt_mode) {
+  const MapLimits l{res, max_x, max_y, CellLimits{nx, ny}};
+  const PointCloud cloud = MakeCloud(xyz, n);
+  Rigid2d init{init_pose[0], init_pose[1], init_pose[2]};
+  if (full) {
+    lin = 1e6 * res;
+    ang = M_PI;
+    init = Rigid2d{max_x - 0.5 * res * ny, max_y - 0.5 * res * nx, 0.};
+  }
+  const PointCloud rotated = TransformPointCloudRotZ(cloud, static_cast<float>(init.theta));
+  // RT matcher builds SearchParameters from the rotated cloud (real_time...cc:128-130),
+  // the fast matcher from the unrotated one (fast...cc:202-204).
+  SearchParameters sp(lin, ang, rt_mode ? rotated : cloud, res);
+  std::vector<PointCloud> rs = GenerateRotatedScans(rotated, sp);
+  std::vector<DiscreteScan2D> ds =
+      DiscretizeScans(l, rs, static_cast<float>(init.x), static_cast<float>(init.y));
+  if (!rt_mode) sp.ShrinkToFit(ds, l.cell_limits);
+  return new Frontend2D{std::move(sp), std::move(ds), std::move(rs)};
+}
+int orc_frontend2d_num_scans(void* h) { return static_cast<Frontend2D*>(h)->sp.num_scans; }
+double orc_frontend2d_step(void* h) {
+  return static_cast<Frontend2D*>(h)->sp.angular_perturbation_step_size;
+}
+void orc_frontend2d_get(void* h, int32_t* dscans /* S*n*2 */, int32_t* bounds /* S*4 */,
+                        float* rotated_xyz /* S*n*3 or null */) {
+  Frontend2D* f = static_cast<Frontend2D*>(h);
+  size_t k = 0;
+  for (const DiscreteScan2D& s : f->scans)
+    for (const Array2i& c : s) {
+      dscans[k++] = c.x;
+      dscans[k++] = c.y;
+    }
+  for (int i = 0; i < f->sp.num_scans; ++i) {
+    bounds[4 * i + 0] = f->sp.linear_bounds[i].min_x;
+    bounds[4 * i + 1] = f->sp.linear_bounds[i].max_x;
+    bounds[4 * i + 2] = f->sp.linear_bounds[i].min_y;
+    bounds[4 * i + 3] = f->sp.linear_bounds[i].max_y;
+  }
+  if (rotated_xyz) {
+    k = 0;
+    for (const PointCloud& s : f->rotated)
+      for (const Vec3f& p : s) {
+        rotated_xyz[k++] = p.x;
+        rotated_xyz[k++] = p.y;
+        rotated_xyz[k++] = p.z;
+      }
+  }
+}
+void orc_frontend2d_destroy(void* h) { delete static_cast<Frontend2D*>(h); }
+
+// PrecomputationGrid2D of one width; out has (nx+w-1)*(ny+w-1) bytes.
+void orc_precompute_grid2d(const uint16_t* cells, int nx, int ny, float min_cost, float max_cost,
+                           int width, uint8_t* out) {
+  const ProbabilityGrid grid = MakeGrid(cells, nx, ny, 0.05, 0., 0., min_cost, max_cost);
+  std::vector<float> tmp;
+  const PrecomputationGrid2D pg(grid, grid.limits.cell_limits, width, &tmp);
+  std::memcpy(out, pg.cells().data(), pg.cells().size());
+}
+
+void* orc_fast2d_create(const uint16_t* cells, int nx, int ny, double res, double max_x,
+                        double max_y, float min_cost, float max_cost, double lin, double ang,
+                        int depth) {
+  return new Fast2DHandle(MakeGrid(cells, nx, ny, res, max_x, max_y, min_cost, max_cost),
+                          FastOptions2D{lin, ang, depth});
+}
+void orc_fast2d_destroy(void* h) { delete static_cast<Fast2DHandle*>(h); }
+
+int orc_fast2d_match(void* h, const float* xyz, int n, const double* init_pose, int full,
+                     float min_score, float* score, double* pose_out, int64_t* stats_out) {
+  Fast2DHandle* m = static_cast<Fast2DHandle*>(h);
+  const PointCloud cloud = MakeCloud(xyz, n);
+  MatchStats stats;
+  Rigid2d pose{0, 0, 0};
+  float s = 0.f;
+  bool found;
+  if (full) {
+    found = m->matcher.MatchFullSubmap(cloud, min_score, &s, &pose, &stats);
+  } else {
+    found = m->matcher.Match(Rigid2d{init_pose[0], init_pose[1], init_pose[2]}, cloud,
+                             min_score, &s, &pose, &stats);
+  }
+  if (found) {
+    *score = s;
+    pose_out[0] = pose.x;
+    pose_out[1] = pose.y;
+    pose_out[2] = pose.theta;
+  }
+  FillStats(stats, stats_out);
+  return found ? 1 : 0;
+}
+
+// ScoreCandidates at one stack level, unsorted, plus the raw integer sums.
+void orc_fast2d_score_candidates(void* h, int level, const int32_t* dscans, int num_scans, int n,
+                                 const int32_t* cand /* C*3: scan, xo, yo */, int num_cand,
+                                 float* scores, int32_t* sums) {
+  Fast2DHandle* m = static_cast<Fast2DHandle*>(h);
+  const PrecomputationGrid2D& pg = m->matcher.stack().Get(level);
+  for (int c = 0; c < num_cand; ++c) {
+    const int32_t* d = dscans + 2 * size_t(cand[3 * c]) * n;
+    int sum = 0;
+    for (int p = 0; p < n; ++p)
+      sum += pg.GetValue(Array2i{d[2 * p] + cand[3 * c + 1], d[2 * p + 1] + cand[3 * c + 2]});
+    if (sums) sums[c] = sum;
+    scores[c] = pg.ToScore(sum / static_cast<float>(n));
+  }
+  (void)num_scans;
+}
+
+void orc_fast2d_level(void* h, int level, uint8_t* out, int32_t* wide_nx, int32_t* wide_ny) {
+  Fast2DHandle* m = static_cast<Fast2DHandle*>(h);
+  const PrecomputationGrid2D& pg = m->matcher.stack().Get(level);
+  *wide_nx = pg.wide_limits().num_x_cells;
+  *wide_ny = pg.wide_limits().num_y_cells;
+  if (out) std::memcpy(out, pg.cells().data(), pg.cells().size());
+}
+
+double orc_rt2d_match(const uint16_t* cells, int nx, int ny, double res, double max_x,
+                      double max_y, const float* xyz, int n, const double* init_pose, double lin,
+                      double ang, double w_t, double w_r, double* pose_out, int64_t* stats_out) {
+  const ProbabilityGrid grid =
+      MakeGrid(cells, nx, ny, res, max_x, max_y, kMinCorrespondenceCost, kMaxCorrespondenceCost);
+  const RealTimeCorrelativeScanMatcher2D matcher(RealTimeOptions{lin, ang, w_t, w_r});
+  MatchStats stats;
+  Rigid2d pose{0, 0, 0};
+  const double score = matcher.Match(Rigid2d{init_pose[0], init_pose[1], init_pose[2]},
+                                     MakeCloud(xyz, n), grid, &pose, &stats);
+  pose_out[0] = pose.x;
+  pose_out[1] = pose.y;
+  pose_out[2] = pose.theta;
+  FillStats(stats, stats_out);
+  return score;
+}
+
+// RT ScoreCandidates over an explicit candidate list (test hook,
+// real_time_correlative_scan_matcher_2d_test.cc:125-198).
+void orc_rt2d_score_candidates(const uint16_t* cells, int nx, int ny, double res, double max_x,
+                               double max_y, const int32_t* dscans, int n, int num_lin,
+                               int num_ang, double step, double w_t, double w_r,
+                               const int32_t* cand, int num_cand, float* scores) {
+  const ProbabilityGrid grid =
+      MakeGrid(cells, nx, ny, res, max_x, max_y, kMinCorrespondenceCost, kMaxCorrespondenceCost);
+  const SearchParameters sp(num_lin, num_ang, step, res);
+  std::vector<DiscreteScan2D> ds(sp.num_scans);
+  for (int s = 0; s < sp.num_scans; ++s)
+    for (int p = 0; p < n; ++p)
+      ds[s].push_back(Array2i{dscans[2 * (size_t(s) * n + p)], dscans[2 * (size_t(s) * n + p) + 1]});
+  std::vector<Candidate2D> cs;
+  for (int c = 0; c < num_cand; ++c)
+    cs.emplace_back(cand[3 * c], cand[3 * c + 1], cand[3 * c + 2], sp);
+  const RealTimeCorrelativeScanMatcher2D matcher(RealTimeOptions{0., 0., w_t, w_r});
+  matcher.ScoreCandidates(grid, ds, sp, &cs);
+  for (int c = 0; c < num_cand; ++c) scores[c] = cs[c].score;
+}
+
+// CPU baseline: run `num_jobs` fast matches on `threads` worker threads
+// (one matcher per job's stack handle, jobs pulled from an atomic counter —
+// the oracle-side stand-in for ThreadPool, constraints/constraint_builder_2d.cc:102-111).
+// jobs: per job {stack index, cloud index}; returns wall seconds.
+double orc_fast2d_batch(void** matchers, const int32_t* job_matcher, const int32_t* job_cloud,
+                        const double* job_init_pose /* J*3 */, int num_jobs,
+                        const float* const* clouds_xyz, const int32_t* cloud_n, int full,
+                        float min_score, int threads, int32_t* found, float* scores,
+                        double* poses /* J*3 */, int64_t* cand_scored /* J */) {
+  std::atomic<int> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int j = next.fetch_add(1);
+      if (j >= num_jobs) return;
+      int64_t st[8] = {0};
+      float s = 0.f;
+      double p[3] = {0, 0, 0};
+      const int ci = job_cloud[j];
+      found[j] = orc_fast2d_match(matchers[job_matcher[j]], clouds_xyz[ci], cloud_n[ci],
+                                  job_init_pose + 3 * j, full, min_score, &s, p, st);
+      scores[j] = s;
+      poses[3 * j] = p[0];
+      poses[3 * j + 1] = p[1];
+      poses[3 * j + 2] = p[2];
+      cand_scored[j] = st[0];
+    }
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+  for (std::thread& t : pool) t.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // extern "C"
