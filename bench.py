@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the correlative scan-matching hot path.
+
+Metric (BASELINE.json): candidate poses scored / s (+ loop-closure constraints / s).
+Workload at every N: BASELINE config[1] — 2D FastCorrelativeScanMatcher
+MatchFullSubmap, 1081-beam synthetic scans vs a 1000x1000 @5 cm ProbabilityGrid,
+depth-7 PrecomputationGridStack.  A step = MATCHES_PER_STEP full-submap matches of
+distinct scans against the rank's submap (one csm_match2d_batch call); at N > 1
+every rank owns its own submap + scans (weak scaling, the ConstraintBuilder queue
+sharded by submap) and the winning constraints are all-gathered over NCCL once per
+step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`value`  : device-resident inputs (clouds + stack in HBM before the timed region).
+`e2e`    : the same matches through csm_match2d with HOST clouds (H2D + D2H inside).
+`--impl reference`: the CPU oracle (restated reference path; the real reference does
+not build here) on the host cores, same metric / workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cartographer_b200 import synthetic  # noqa: E402
+
+BYTES_PER_CANDIDATE = 1081 * (8 + 1) + 16  # N*(8+1)+16 @ N=1081
+MATCHES_PER_STEP = 4
+MIN_SCORE = 0.6          # pose_graph.lua:28 global_localization_min_score
+DEPTH = 7                # pose_graph.lua:27
+LIN, ANG = 7.0, math.radians(30.0)
+WORKLOAD = "fast2d_MatchFullSubmap_1081beams_1000x1000_5cm_depth7"
+
+
+def make_world(seed, num_scans):
+    grid, occ = synthetic.make_grid2d(seed, 1000)
+    rng = np.random.RandomState(seed * 1000 + 17)
+    scans = []
+    for i in range(num_scans):
+        pose = synthetic.random_free_pose(occ, grid, rng)
+        scans.append(synthetic.cast_scan(occ, grid, pose, seed=seed * 100000 + i))
+    return grid, scans
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                  "--format=csv,noheader,nounits", "-lms", "100"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.proc = p
+        for line in p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+            if self.stop_flag:
+                break
+        p.terminate()
+
+    def summary(self):
+        self.stop_flag = True
+        time.sleep(0.15)
+        if getattr(self, "proc", None):
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def cpu_reference_step(oracle, og_matcher, scans, threads):
+    """One bounded CPU sample: `threads` full-submap matches, one per worker thread."""
+    jobs = list(range(len(scans)))
+    secs, found, scores, poses, cs = oracle.fast2d_batch(
+        [og_matcher], [0] * len(jobs), jobs, np.zeros((len(jobs), 3)), scans, True, MIN_SCORE,
+        threads)
+    return secs, int(cs.sum()), len(jobs), int(found.sum())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as oracle
+    oracle.build()
+    threads = max(1, min(os.cpu_count() or 1, 64))
+    per_step = threads  # one full-submap match per host thread per step (bounded sample)
+    grid, scans = make_world(0, per_step)
+    og = oracle.Grid2D(grid.cells, grid.resolution, grid.max_x, grid.max_y)
+    t0 = time.perf_counter()
+    om = oracle.FastCorrelativeScanMatcher2D(og, LIN, ANG, DEPTH)
+    build_s = time.perf_counter() - t0
+    tot_s, tot_c, tot_m = 0.0, 0, 0
+    for it in range(args.warmup + args.steps):
+        secs, cands, matches, _ = cpu_reference_step(oracle, om, scans, threads)
+        if it >= args.warmup:
+            tot_s += secs
+            tot_c += cands
+            tot_m += matches
+    value = tot_c / tot_s
+    line = {
+        "impl": "reference", "metric": "candidate_poses_scored_per_sec", "value": value,
+        "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "matches_per_step": per_step,
+                   "min_score": MIN_SCORE, "oracle_stack_build_s": build_s},
+        "constraints_per_sec": tot_m / tot_s,
+        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": threads,
+                         "kind": "port",
+                         "sample": "%d MatchFullSubmap per step, one per host thread, "
+                                   "oracle/ (C++ restatement, -O3 -DNDEBUG, no -march)" % per_step},
+        "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from cartographer_b200 import scan_matching as sm
+    from cartographer_b200._lib import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    total_steps = args.warmup + args.steps
+    num_scans = total_steps * MATCHES_PER_STEP
+    grid, scans = make_world(rank, num_scans + MATCHES_PER_STEP)
+    opts = sm.FastCorrelativeScanMatcherOptions2D(LIN, ANG, DEPTH)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    matcher = sm.FastCorrelativeScanMatcher2D(grid, opts, device=local_rank)
+    stack_build_ms = 1e3 * (time.perf_counter() - t0)
+    clouds = [sm.DeviceCloud(s, device=local_rank) for s in scans]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def jobs_for(step):
+        jobs = np.zeros(MATCHES_PER_STEP, sm.JOB2D_DTYPE)
+        for b in range(MATCHES_PER_STEP):
+            jobs[b]["stack_index"] = 0
+            jobs[b]["cloud_index"] = step * MATCHES_PER_STEP + b
+            jobs[b]["full_submap"] = 1
+            jobs[b]["min_score"] = MIN_SCORE
+        return jobs
+
+    gathered = None
+    if dist is not None:
+        gathered = torch.empty(world * MATCHES_PER_STEP * sm.RESULT2D_DTYPE.itemsize,
+                               dtype=torch.uint8, device=dev)
+
+    def allgather_results(res):
+        """The path's only collective: every rank ends up with all constraints."""
+        if dist is None:
+            return res
+        mine = torch.from_numpy(res.view(np.uint8).reshape(-1).copy()).to(dev, non_blocking=False)
+        dist.all_gather_into_tensor(gathered, mine)
+        return gathered
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg (value) -------------------------------------------
+    sampler = ClockSampler(local_rank)
+    launches0 = sm.kernel_launch_count()
+    step_s, cand, found = [], 0, 0
+    dev_ms = 0.0
+    for it in range(total_steps):
+        flush.zero_()
+        barrier()
+        if it == args.warmup:
+            sampler.start()
+            launches0 = sm.kernel_launch_count()
+        t0 = time.perf_counter()
+        res, st = sm.match_batch([matcher], clouds, jobs_for(it), LIN, ANG)
+        allgather_results(res)
+        barrier()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            step_s.append(dt)
+            cand += st["candidates_scored"]
+            found += int(res["found"].sum())
+            dev_ms += st["device_ms"]
+    launches = sm.kernel_launch_count() - launches0
+    clocks = sampler.summary() if sampler.is_alive() or sampler.rows else \
+        {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    elapsed = float(sum(step_s))
+    t = torch.tensor([elapsed, float(cand), float(found)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed, cand_all, found_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        cand_all, found_all = float(cand), float(found)
+    matches_all = world * args.steps * MATCHES_PER_STEP
+    value = cand_all / elapsed
+
+    # ---- end-to-end leg (host clouds through csm_match2d) ------------------------
+    e2e_s, e2e_c = [], 0
+    for it in range(total_steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        res = np.zeros(MATCHES_PER_STEP, sm.RESULT2D_DTYPE)
+        c_step = 0
+        for b in range(MATCHES_PER_STEP):
+            f, s, p = matcher.MatchFullSubmap(scans[it * MATCHES_PER_STEP + b], MIN_SCORE)
+            res[b]["found"] = int(f)
+            c_step += matcher.last_stats["candidates_scored"]
+        allgather_results(res)
+        barrier()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            e2e_s.append(dt)
+            e2e_c += c_step
+    te = torch.tensor([float(sum(e2e_s)), float(e2e_c)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        a = te.clone()
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = te.clone()
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_value = float(b[1]) / float(a[0])
+    else:
+        e2e_value = float(te[1]) / float(te[0])
+    h2d = MATCHES_PER_STEP * 1081 * 12
+    d2h = MATCHES_PER_STEP * sm.RESULT2D_DTYPE.itemsize
+
+    # ---- roofline of the dominant kernel (CUDA events on the engine's stream) ----
+    import ctypes as C
+    roofline = None
+    if rank == 0:
+        lib().csm_profile_enable(1)
+        sm.match_batch([matcher], clouds, jobs_for(args.warmup), LIN, ANG)
+        buf = C.create_string_buffer(8192)
+        lib().csm_profile_read(buf, 8192)
+        lib().csm_profile_enable(0)
+        kernels = {}
+        for ln in buf.value.decode().strip().splitlines():
+            nm, n_l, ms, units = ln.split()
+            kernels[nm] = {"launches": int(n_l), "ms": float(ms), "units": float(units)}
+        tot_ms = sum(k["ms"] for k in kernels.values())
+        top = max(kernels, key=lambda k: kernels[k]["ms"])
+        k = kernels[top]
+        peak, how = measured_peak_gbs()
+        ach = k["units"] * BYTES_PER_CANDIDATE / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak,
+                    "peak_source": how, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "launches": k["launches"],
+                    "avg_launch_ms": k["ms"] / max(1, k["launches"]),
+                    "share_of_step": k["ms"] / tot_ms if tot_ms else None,
+                    "bytes_per_candidate": BYTES_PER_CANDIDATE,
+                    "kernels": {n: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                                    "candidates": v["units"]} for n, v in kernels.items()}}
+
+    # ---- CPU baseline (oracle on the host cores, bounded sample) -----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle as oracle
+        oracle.build()
+        threads = max(1, min(os.cpu_count() or 1, 64))
+        og = oracle.Grid2D(grid.cells, grid.resolution, grid.max_x, grid.max_y)
+        om = oracle.FastCorrelativeScanMatcher2D(og, LIN, ANG, DEPTH)
+        secs, c_cpu, m_cpu, _ = cpu_reference_step(oracle, om, scans[:threads] if
+                                                   len(scans) >= threads else
+                                                   (scans * threads)[:threads], threads)
+        cpu = {"value": c_cpu / secs, "unit": "candidates/s", "cores": threads, "kind": "port",
+               "constraints_per_sec": m_cpu / secs,
+               "sample": "%d MatchFullSubmap (one per host thread) of the same workload, "
+                         "%.1f s wall" % (m_cpu, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": "candidate_poses_scored_per_sec", "value": value, "unit": "candidates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "matches_per_step_per_gpu": MATCHES_PER_STEP,
+                       "min_score": MIN_SCORE, "l2": "flushed between steps (256 MB write)",
+                       "stack_build_ms": stack_build_ms, "found": found_all,
+                       "parallelism": "submap-sharded x%d" % world},
+            "constraints_per_sec": matches_all / elapsed,
+            "device_ms_per_step": dev_ms / max(1, args.steps),
+            "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+// Shared plumbing of libcsm_b200.so: error reporting, per-device context
+// (stream + growable device workspace + pinned staging), launch counting.
+#ifndef CSM_COMMON_CUH_
+#define CSM_COMMON_CUH_
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/csm_abi.h"
+
+namespace csm {
+
+void SetError(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define CSM_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ::csm::SetError("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,            \
+                      cudaGetErrorString(_e));                                      \
+      return CSM_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define CSM_REQUIRE(cond, msg)                                                      \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      ::csm::SetError("%s:%d: invalid argument: %s (%s)", __FILE__, __LINE__, msg,  \
+                      #cond);                                                       \
+      return CSM_E_INVALID;                                                         \
+    }                                                                               \
+  } while (0)
+
+#define CSM_TRY(expr)                     \
+  do {                                    \
+    csm_status _s = (expr);               \
+    if (_s != CSM_OK) return _s;          \
+  } while (0)
+
+#define CSM_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    ::csm::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
+    CSM_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+// A device buffer that only ever grows; reused across calls so the steady state
+// performs no cudaMalloc.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  csm_status Reserve(size_t bytes) {
+    if (bytes <= cap) return CSM_OK;
+    if (p) CSM_CUDA(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CSM_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return CSM_OK;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  csm_status Reserve(size_t bytes) {
+    if (bytes <= cap) return CSM_OK;
+    if (p) CSM_CUDA(cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CSM_CUDA(cudaMallocHost(&p, want));
+    cap = want;
+    return CSM_OK;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+// One per CUDA device, created on first use.  `mu` serialises engine calls on
+// the device (handle-level locking).
+struct Ctx {
+  int device = -1;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;
+  std::map<std::string, DevBuf> dev;      // named workspaces
+  std::map<std::string, PinnedBuf> pin;
+  DevBuf& D(const char* name) { return dev[name]; }
+  PinnedBuf& P(const char* name) { return pin[name]; }
+};
+
+csm_status GetCtx(int device, Ctx** out);
+
+// Optional per-kernel timing (csm_profile_enable): CUDA events on the engine's
+// own stream around every launch of a named kernel; bench.py reads the totals
+// to compute the roofline numbers of the dominant kernel.
+extern std::atomic<int> g_profile_on;
+void ProfBegin(Ctx* ctx);
+void ProfStop(Ctx* ctx);                                   // records the end event
+void ProfCommit(Ctx* ctx, const char* name, double units);  // waits for it and accumulates
+inline void ProfEnd(Ctx* ctx, const char* name, double units) {
+  ProfStop(ctx);
+  ProfCommit(ctx, name, units);
+}
+
+}  // namespace csm
+
+#endif  // CSM_COMMON_CUH_

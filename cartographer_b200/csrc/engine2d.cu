@@ -1,0 +1,1496 @@
+// FastCorrelativeScanMatcher2D on B200: precomputation-grid stack build,
+// scan discretisation, candidate scoring and a batched, device-resident
+// branch-and-bound.  Reference: cartographer/mapping/internal/2d/scan_matching/
+// {correlative_scan_matcher_2d,fast_correlative_scan_matcher_2d}.{h,cc}.
+//
+// Exactness rules: every float/double expression whose
+// value reaches an output is written with explicit round-to-nearest intrinsics
+// (__fmul_rn ...) so ptxas can never contract it into an FMA — the reference
+// build has no FMA (cmake/functions.cmake:100-101).  Transcendentals are
+// evaluated on the host with libm, like the reference.
+#include "engine2d.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <functional>
+
+namespace csm {
+
+// ---------------------------------------------------------------------------
+// Small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned FloatToOrdered(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float OrderedToFloat(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+static inline unsigned HostFloatToOrdered(float f) {
+  unsigned u;
+  std::memcpy(&u, &f, 4);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float HostOrderedToFloat(unsigned u) {
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+// PrecomputationGrid2D::ToScore(sum / float(N))   (fast...2d.h:74-76, .cc:328-329)
+__device__ __forceinline__ float ToScore(const StackDev& st, int sum, int n) {
+  const float mean = __fdiv_rn(__int2float_rn(sum), __int2float_rn(n));
+  return __fadd_rn(st.min_score, __fmul_rn(mean, st.k255));
+}
+
+// PrecomputationGrid2D::GetValue (fast...2d.h:56-71) on the row-major level.
+__device__ __forceinline__ int GetValue(const uint8_t* __restrict__ g, int wx, int wy, int lx,
+                                        int ly) {
+  if (static_cast<unsigned>(lx) >= static_cast<unsigned>(wx) ||
+      static_cast<unsigned>(ly) >= static_cast<unsigned>(wy))
+    return 0;
+  return __ldg(g + static_cast<size_t>(ly) * wx + lx);
+}
+
+__device__ __forceinline__ int WarpSum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// K1: precomputation grid stack
+// ---------------------------------------------------------------------------
+// Level 0: cells -> uint8 through the 64 Ki LUT
+//   lut[v] = ComputeCellValue(1.f - |table[v]|)   (fast...2d.cc:110-111,163-169)
+__global__ void k_stack_level0(const uint16_t* __restrict__ cells,
+                               const uint8_t* __restrict__ lut, uint8_t* __restrict__ out,
+                               int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = lut[cells[i]];
+}
+
+// Level h (window w = 2^h) from level h-1 (window w/2): a w x w window is the
+// union of four (w/2) x (w/2) windows; max is exact and quantisation is
+// monotone, so max-of-uint8 equals the reference's quantised float max
+// (fast...2d.cc:108-160).  Coordinates are wide-grid local indices.
+__global__ void k_stack_double(const uint8_t* __restrict__ prev, int pwx, int pwy,
+                               uint8_t* __restrict__ out, int wx, int wy, int half) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= wx || y >= wy) return;
+  auto at = [&](int px, int py) -> int {
+    return (px >= 0 && py >= 0 && px < pwx && py < pwy) ? prev[static_cast<size_t>(py) * pwx + px]
+                                                        : 0;
+  };
+  int v = max(max(at(x - half, y - half), at(x, y - half)), max(at(x - half, y), at(x, y)));
+  out[static_cast<size_t>(y) * wx + x] = static_cast<uint8_t>(v);
+}
+
+// Decimated copy of one level (see StackDev::dec).
+__global__ void k_stack_decimate(const uint8_t* __restrict__ lvl, int wx, int wy, int h,
+                                 uint8_t* __restrict__ dec, int id, int jd, int id_stride) {
+  const int s = 1 << h;
+  const size_t total = static_cast<size_t>(s) * s * jd * id_stride;
+  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int I = t % id_stride;
+    size_t r = t / id_stride;
+    int J = r % jd;
+    r /= jd;
+    int ax = r % s;
+    int ay = r / s;
+    int x = s * I + ax, y = s * J + ay;
+    uint8_t v = 0;
+    if (I < id && x < wx && y < wy) v = lvl[static_cast<size_t>(y) * wx + x];
+    dec[t] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2: GenerateRotatedScans + DiscretizeScans + ShrinkToFit
+// ---------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 CrossRn(const V3& a, const V3& b) {
+  return V3{__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)),
+            __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+            __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x))};
+}
+// Eigen QuaternionBase::_transformVector followed by "+ translation(0)"
+// (transform/rigid_transform.h:192-196, sensor/point_cloud.cc:56-64).
+__device__ __forceinline__ V3 RotateRn(float qw, const V3& qv, const V3& v) {
+  V3 uv = CrossRn(qv, v);
+  uv.x = __fadd_rn(uv.x, uv.x);
+  uv.y = __fadd_rn(uv.y, uv.y);
+  uv.z = __fadd_rn(uv.z, uv.z);
+  const V3 c = CrossRn(qv, uv);
+  V3 r{__fadd_rn(__fadd_rn(v.x, __fmul_rn(qw, uv.x)), c.x),
+       __fadd_rn(__fadd_rn(v.y, __fmul_rn(qw, uv.y)), c.y),
+       __fadd_rn(__fadd_rn(v.z, __fmul_rn(qw, uv.z)), c.z)};
+  r.x = __fadd_rn(r.x, 0.f);
+  r.y = __fadd_rn(r.y, 0.f);
+  r.z = __fadd_rn(r.z, 0.f);
+  return r;
+}
+
+// One CTA per (job, scan).  Writes the scan's cell indices and its LinearBounds
+// after ShrinkToFit (correlative_scan_matcher_2d.cc:73-127), plus the number of
+// lowest-resolution candidates per axis (fast...2d.cc:281-292).
+__global__ void __launch_bounds__(128)
+k_discretize(const JobDev* __restrict__ jobs, const int* __restrict__ scan_job,
+             int2* __restrict__ dscan, ScanInfo* __restrict__ info, int shrink,
+             unsigned long long* __restrict__ counters) {
+  const int sg = blockIdx.x;
+  const int j = scan_job[sg];
+  const JobDev jb = jobs[j];
+  const StackDev& st = *jb.stack;
+  const int k = sg - jb.scan_base;
+  const float2 cs = jb.trig[k];
+  // Quaternionf(AngleAxisf(a, UnitZ)): w = cos(ha), vec = sin(ha) * (0, 0, 1)
+  const V3 qk{__fmul_rn(cs.y, 0.f), __fmul_rn(cs.y, 0.f), __fmul_rn(cs.y, 1.f)};
+  const V3 q0{jb.q0x, jb.q0y, jb.q0z};
+  int2* out = dscan + jb.dscan_off + static_cast<long long>(k) * jb.n;
+  int min_ix = INT_MAX, max_ix = INT_MIN, min_iy = INT_MAX, max_iy = INT_MIN;
+  for (int p = threadIdx.x; p < jb.n; p += blockDim.x) {
+    const V3 v{jb.xyz[3 * p], jb.xyz[3 * p + 1], jb.xyz[3 * p + 2]};
+    const V3 r0 = RotateRn(jb.q0w, q0, v);   // rotated_point_cloud   (fast...2d.cc:236-239)
+    const V3 r1 = RotateRn(cs.x, qk, r0);    // GenerateRotatedScans  (corr...2d.cc:93-109)
+    // Affine2f(Translation2f) * v = (1*x + 0*y) + t                    (corr...2d.cc:120-121)
+    const float px = __fadd_rn(__fadd_rn(__fmul_rn(1.f, r1.x), __fmul_rn(0.f, r1.y)), jb.tx);
+    const float py = __fadd_rn(__fadd_rn(__fmul_rn(0.f, r1.x), __fmul_rn(1.f, r1.y)), jb.ty);
+    // MapLimits::GetCellIndex in double                               (2d/map_limits.h:69-76)
+    const double fx = __dsub_rn(__ddiv_rn(__dsub_rn(st.max_y, static_cast<double>(py)),
+                                          st.resolution), 0.5);
+    const double fy = __dsub_rn(__ddiv_rn(__dsub_rn(st.max_x, static_cast<double>(px)),
+                                          st.resolution), 0.5);
+    const int ix = static_cast<int>(llround(fx));
+    const int iy = static_cast<int>(llround(fy));
+    out[p] = make_int2(ix, iy);
+    min_ix = min(min_ix, ix);
+    max_ix = max(max_ix, ix);
+    min_iy = min(min_iy, iy);
+    max_iy = max(max_iy, iy);
+  }
+  __shared__ int red[4][4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    min_ix = min(min_ix, __shfl_xor_sync(0xffffffffu, min_ix, o));
+    max_ix = max(max_ix, __shfl_xor_sync(0xffffffffu, max_ix, o));
+    min_iy = min(min_iy, __shfl_xor_sync(0xffffffffu, min_iy, o));
+    max_iy = max(max_iy, __shfl_xor_sync(0xffffffffu, max_iy, o));
+  }
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    red[warp][0] = min_ix;
+    red[warp][1] = max_ix;
+    red[warp][2] = min_iy;
+    red[warp][3] = max_iy;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; ++w) {
+      red[0][0] = min(red[0][0], red[w][0]);
+      red[0][1] = max(red[0][1], red[w][1]);
+      red[0][2] = min(red[0][2], red[w][2]);
+      red[0][3] = max(red[0][3], red[w][3]);
+    }
+    ScanInfo si;
+    si.job = j;
+    si.min_x = -jb.lin;
+    si.max_x = jb.lin;
+    si.min_y = -jb.lin;
+    si.max_y = jb.lin;
+    if (shrink) {
+      // min_bound = min(0, min(-xy)); max_bound = max(0, max(limits - 1 - xy))
+      const int min_bx = min(0, -red[0][1]), max_bx = max(0, st.nx - 1 - red[0][0]);
+      const int min_by = min(0, -red[0][3]), max_by = max(0, st.ny - 1 - red[0][2]);
+      si.min_x = max(si.min_x, min_bx);
+      si.max_x = min(si.max_x, max_bx);
+      si.min_y = max(si.min_y, min_by);
+      si.max_y = min(si.max_y, max_by);
+    }
+    const int step = 1 << (st.depth - 1);
+    si.nxc = (si.max_x - si.min_x + step) / step;
+    si.nyc = (si.max_y - si.min_y + step) / step;
+    si.pad = 0;
+    info[sg] = si;
+    const unsigned long long slots = static_cast<unsigned long long>(si.nxc) * si.nyc;
+    atomicAdd(&counters[0], slots);  // every lowest-resolution candidate gets scored
+    atomicAdd(&counters[3], slots);
+  }
+}
+
+csm_status LaunchDiscretize2D(cudaStream_t stream, const JobDev* jobs, const int* scan_job,
+                              int total_scans, int2* dscan, ScanInfo* info, int shrink,
+                              unsigned long long* counters) {
+  k_discretize<<<total_scans, 128, 0, stream>>>(jobs, scan_job, dscan, info, shrink, counters);
+  CSM_LAUNCH_CHECK();
+  return CSM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K3: candidate scoring
+// ---------------------------------------------------------------------------
+// Lowest-resolution pass, gather form: one warp per (scan, slot); slot = i*nyc+j
+// follows the reference's generation order (x outer, y inner; fast...2d.cc:296-309).
+__global__ void __launch_bounds__(256)
+k_score_top_gather(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+                   const int2* __restrict__ dscan, int* __restrict__ top_sum,
+                   const long long* __restrict__ scan_slot_base, int total_scans,
+                   long long total_slots) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (w >= total_slots) return;
+  // scan = last index with scan_slot_base[scan] <= w
+  int lo = 0, hi = total_scans - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (scan_slot_base[mid] <= w) lo = mid; else hi = mid - 1;
+  }
+  const int sg = lo;
+  const int slot = static_cast<int>(w - scan_slot_base[sg]);
+  const ScanInfo si = info[sg];
+  if (slot >= si.nxc * si.nyc) return;
+  const JobDev& jb = jobs[si.job];
+  const StackDev& st = *jb.stack;
+  const int h = st.depth - 1;
+  const int w1 = (1 << h) - 1;
+  const uint8_t* __restrict__ g = st.level[h];
+  const int wx = st.wx[h], wy = st.wy[h];
+  const int2* __restrict__ pts = dscan + jb.dscan_off +
+                                 static_cast<long long>(sg - jb.scan_base) * jb.n;
+  const int i = slot / si.nyc, jy = slot - i * si.nyc;
+  const int ox = si.min_x + (i << h) + w1, oy = si.min_y + (jy << h) + w1;
+  int sum = 0;
+  for (int p = lane; p < jb.n; p += 32) {
+    const int2 c = pts[p];
+    sum += GetValue(g, wx, wy, c.x + ox, c.y + oy);
+  }
+  sum = WarpSum(sum);
+  if (lane == 0) top_sum[scan_slot_base[sg] + slot] = sum;
+}
+
+// Lowest-resolution pass, dense form: one CTA per (scan, tile of candidates).
+// Thread t owns candidates (i, j0..) of the scan's lattice; for a point p the
+// cells touched by all candidates of the lattice are one contiguous block of the
+// decimated level (StackDev::dec), so consecutive lanes read consecutive bytes.
+// Point descriptors are staged in shared memory once per chunk and broadcast.
+constexpr int kDenseThreads = 256;
+constexpr int kDenseCandPerThread = 8;
+constexpr int kDenseChunk = 256;
+__global__ void __launch_bounds__(kDenseThreads)
+k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+                  const int2* __restrict__ dscan, int* __restrict__ top_sum,
+                  const long long* __restrict__ scan_slot_base, int total_scans) {
+  __shared__ int s_base[kDenseChunk];   // tile base + qy * id_stride + qx
+  __shared__ short2 s_q[kDenseChunk];   // (qx, qy)
+  for (int sg = blockIdx.x; sg < total_scans; sg += gridDim.x) {
+    const ScanInfo si = info[sg];
+    const JobDev& jb = jobs[si.job];
+    const StackDev& st = *jb.stack;
+    const int h = st.depth - 1;
+    const int s = 1 << h;
+    const int id = st.id[h], jd = st.jd[h], ids = st.id_stride[h];
+    const uint8_t* __restrict__ dec = st.dec[h];
+    const int slots = si.nxc * si.nyc;
+    const int2* __restrict__ pts = dscan + jb.dscan_off +
+                                   static_cast<long long>(sg - jb.scan_base) * jb.n;
+    for (int tile0 = 0; tile0 < slots; tile0 += kDenseThreads * kDenseCandPerThread) {
+      // candidate c = tile0 + threadIdx.x + r * kDenseThreads, laid out j-fastest
+      // in slot order; for coalescing we want i-fastest across lanes, so map
+      // lattice index q = c -> (jy = q / nxc, i = q % nxc) and store to slot i*nyc+jy.
+      int acc[kDenseCandPerThread];
+      int ci[kDenseCandPerThread], cj[kDenseCandPerThread];
+#pragma unroll
+      for (int r = 0; r < kDenseCandPerThread; ++r) {
+        acc[r] = 0;
+        const int q = tile0 + threadIdx.x + r * kDenseThreads;
+        cj[r] = q / si.nxc;
+        ci[r] = q - cj[r] * si.nxc;
+        if (q >= slots) { ci[r] = -(1 << 20); cj[r] = -(1 << 20); }
+      }
+      for (int p0 = 0; p0 < jb.n; p0 += kDenseChunk) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kDenseChunk; t += kDenseThreads) {
+          const int p = p0 + t;
+          int base = 0;
+          short2 q = make_short2(-30000, -30000);
+          if (p < jb.n) {
+            const int2 c = pts[p];
+            const int bx = c.x + si.min_x + s - 1, by = c.y + si.min_y + s - 1;
+            const int qx = bx >> h, qy = by >> h;            // floor division
+            const int ax = bx & (s - 1), ay = by & (s - 1);
+            if (qx > -30000 && qx < 30000 && qy > -30000 && qy < 30000) {
+              base = ((ay * s + ax) * jd) * ids;
+              q = make_short2(static_cast<short>(qx), static_cast<short>(qy));
+            }
+          }
+          s_base[t] = base;
+          s_q[t] = q;
+        }
+        __syncthreads();
+        const int cnt = min(kDenseChunk, jb.n - p0);
+        for (int t = 0; t < cnt; ++t) {
+          const int base = s_base[t];
+          const short2 q = s_q[t];
+#pragma unroll
+          for (int r = 0; r < kDenseCandPerThread; ++r) {
+            const int I = q.x + ci[r], J = q.y + cj[r];
+            if (static_cast<unsigned>(I) < static_cast<unsigned>(id) &&
+                static_cast<unsigned>(J) < static_cast<unsigned>(jd))
+              acc[r] += __ldg(dec + base + J * ids + I);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kDenseCandPerThread; ++r) {
+        const int q = tile0 + threadIdx.x + r * kDenseThreads;
+        if (q < slots) top_sum[scan_slot_base[sg] + ci[r] * si.nyc + cj[r]] = acc[r];
+      }
+    }
+  }
+}
+
+// Generic list scoring (test hook + tie resolution): one warp per candidate.
+struct ListCand { int scan; int xo, yo, level; };
+__global__ void __launch_bounds__(256)
+k_score_list(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+             const int2* __restrict__ dscan, const ListCand* __restrict__ cands, int count,
+             int* __restrict__ sums, float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= count) return;
+  const ListCand c = cands[warp];
+  const JobDev& jb = jobs[info[c.scan].job];
+  const StackDev& st = *jb.stack;
+  const int w1 = (1 << c.level) - 1;
+  const uint8_t* __restrict__ g = st.level[c.level];
+  const int wx = st.wx[c.level], wy = st.wy[c.level];
+  const int2* __restrict__ pts = dscan + jb.dscan_off +
+                                 static_cast<long long>(c.scan - jb.scan_base) * jb.n;
+  int sum = 0;
+  for (int p = lane; p < jb.n; p += 32) {
+    const int2 q = pts[p];
+    sum += GetValue(g, wx, wy, q.x + c.xo + w1, q.y + c.yo + w1);
+  }
+  sum = WarpSum(sum);
+  if (lane == 0) {
+    if (sums) sums[warp] = sum;
+    if (scores) scores[warp] = ToScore(st, sum, jb.n);
+  }
+}
+
+// Scores the (up to) four children of `parent` at level h-1 with one warp.
+// Children are generated in the reference's order: x offset {0, half} outer,
+// y offset {0, half} inner, each clipped against the scan's max bound
+// (fast...2d.cc:352-367).  Returns the child count; sums[c] valid for c < count.
+__device__ __forceinline__ int ScoreChildren(const StackDev& st, const ScanInfo& si,
+                                             const int2* __restrict__ pts, int n, int xo,
+                                             int yo, int h, int lane, int sums[4], int cx[4],
+                                             int cy[4]) {
+  const int half = 1 << (h - 1);
+  const int nxk = (xo + half > si.max_x) ? 1 : 2;
+  const int nyk = (yo + half > si.max_y) ? 1 : 2;
+  const int lv = h - 1;
+  const int w1 = (1 << lv) - 1;
+  const uint8_t* __restrict__ g = st.level[lv];
+  const int wx = st.wx[lv], wy = st.wy[lv];
+  int s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+  const int bx = xo + w1, by = yo + w1;
+  for (int p = lane; p < n; p += 32) {
+    const int2 q = pts[p];
+    const int lx = q.x + bx, ly = q.y + by;
+    s00 += GetValue(g, wx, wy, lx, ly);
+    if (nyk == 2) s01 += GetValue(g, wx, wy, lx, ly + half);
+    if (nxk == 2) {
+      s10 += GetValue(g, wx, wy, lx + half, ly);
+      if (nyk == 2) s11 += GetValue(g, wx, wy, lx + half, ly + half);
+    }
+  }
+  s00 = WarpSum(s00);
+  s01 = WarpSum(s01);
+  s10 = WarpSum(s10);
+  s11 = WarpSum(s11);
+  int c = 0;
+  sums[c] = s00; cx[c] = xo; cy[c] = yo; ++c;
+  if (nyk == 2) { sums[c] = s01; cx[c] = xo; cy[c] = yo + half; ++c; }
+  if (nxk == 2) {
+    sums[c] = s10; cx[c] = xo + half; cy[c] = yo; ++c;
+    if (nyk == 2) { sums[c] = s11; cx[c] = xo + half; cy[c] = yo + half; ++c; }
+  }
+  return c;
+}
+
+// Greedy dives: one warp per scan starts at the scan's best lowest-resolution
+// candidate and follows the best child down to a leaf.  Every leaf score is a
+// valid lower bound of the job's optimum; the maximum over all scans seeds the
+// branch-and-bound (the reference's DFS gets the same bound from its first dive,
+// fast...2d.cc:335-378, only later).
+__global__ void __launch_bounds__(256)
+k_dive(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+       const int2* __restrict__ dscan, const int* __restrict__ top_sum,
+       const long long* __restrict__ scan_slot_base, int total_scans,
+       unsigned* __restrict__ lb, unsigned long long* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const int sg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (sg >= total_scans) return;
+  const ScanInfo si = info[sg];
+  const JobDev& jb = jobs[si.job];
+  const StackDev& st = *jb.stack;
+  const int slots = si.nxc * si.nyc;
+  const int* __restrict__ ts = top_sum + scan_slot_base[sg];
+  int best = -1, best_slot = 0;
+  for (int s = lane; s < slots; s += 32) {
+    const int v = ts[s];
+    if (v > best) { best = v; best_slot = s; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int os = __shfl_xor_sync(0xffffffffu, best_slot, o);
+    if (ov > best || (ov == best && os < best_slot)) { best = ov; best_slot = os; }
+  }
+  if (!(ToScore(st, best, jb.n) > jb.min_score)) return;
+  int h = st.depth - 1;
+  const int i = best_slot / si.nyc, jy = best_slot - i * si.nyc;
+  int xo = si.min_x + (i << h), yo = si.min_y + (jy << h);
+  const int2* __restrict__ pts = dscan + jb.dscan_off +
+                                 static_cast<long long>(sg - jb.scan_base) * jb.n;
+  int leaf_sum = best;
+  unsigned long long scored = 0;
+  while (h > 0) {
+    int sums[4], cx[4], cy[4];
+    const int c = ScoreChildren(st, si, pts, jb.n, xo, yo, h, lane, sums, cx, cy);
+    scored += c;
+    int b = 0;
+    for (int t = 1; t < c; ++t)
+      if (sums[t] > sums[b]) b = t;
+    xo = cx[b];
+    yo = cy[b];
+    leaf_sum = sums[b];
+    --h;
+  }
+  if (lane == 0) {
+    const float score = ToScore(st, leaf_sum, jb.n);
+    if (score > jb.min_score) atomicMax(&lb[si.job], FloatToOrdered(score));
+    atomicAdd(&counters[0], scored);
+    atomicAdd(&counters[2], 1ull);
+  }
+}
+
+// Pushes every lowest-resolution candidate that can still contain the optimum
+// (score > min_score and score >= current bound) onto the top-level queue.
+__global__ void __launch_bounds__(256)
+k_filter_top(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+             const int* __restrict__ top_sum, const long long* __restrict__ scan_slot_base,
+             int total_scans, const unsigned* __restrict__ lb, Node* __restrict__ queue,
+             int* __restrict__ qcount, int qcap, int* __restrict__ overflow) {
+  for (int sg = blockIdx.x; sg < total_scans; sg += gridDim.x) {
+    const ScanInfo si = info[sg];
+    const JobDev& jb = jobs[si.job];
+    const StackDev& st = *jb.stack;
+    const int h = st.depth - 1;
+    const int slots = si.nxc * si.nyc;
+    const float bound = OrderedToFloat(lb[si.job]);
+    const int* __restrict__ ts = top_sum + scan_slot_base[sg];
+    for (int s0 = 0; s0 < slots; s0 += blockDim.x) {
+      const int s = s0 + threadIdx.x;
+      bool keep = false;
+      float score = 0.f;
+      if (s < slots) {
+        score = ToScore(st, ts[s], jb.n);
+        keep = score > jb.min_score && score >= bound;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(qcount, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (keep) {
+          const int idx = base + __popc(m & ((1u << lane) - 1));
+          if (idx < qcap) {
+            const int i = s / si.nyc, jy = s - i * si.nyc;
+            queue[idx] = Node{sg, si.min_x + (i << h), si.min_y + (jy << h), score};
+          } else {
+            *overflow = 1;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Branch step: one warp per parent node of level h.  Scores its children at
+// level h-1, then either pushes the survivors to the next queue (h-1 >= 1) or,
+// at h-1 == 0, raises the job's bound and records the leaf.
+__global__ void __launch_bounds__(256)
+k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+         const int2* __restrict__ dscan, const Node* __restrict__ parents, int count, int h,
+         unsigned* __restrict__ lb, Node* __restrict__ next, int* __restrict__ next_count,
+         int next_cap, Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
+         int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= count) return;
+  const Node nd = parents[warp];
+  const ScanInfo si = info[nd.scan];
+  const JobDev& jb = jobs[si.job];
+  const StackDev& st = *jb.stack;
+  // bound may have risen since the node was queued
+  if (!(nd.score >= OrderedToFloat(lb[si.job]))) return;
+  const int2* __restrict__ pts = dscan + jb.dscan_off +
+                                 static_cast<long long>(nd.scan - jb.scan_base) * jb.n;
+  int sums[4], cx[4], cy[4];
+  const int c = ScoreChildren(st, si, pts, jb.n, nd.xo, nd.yo, h, lane, sums, cx, cy);
+  if (lane != 0) return;
+  atomicAdd(&counters[0], (unsigned long long)c);
+  atomicAdd(&counters[1], 1ull);
+  float sc[4];
+  for (int t = 0; t < c; ++t) sc[t] = ToScore(st, sums[t], jb.n);
+  if (h - 1 == 0) {
+    for (int t = 0; t < c; ++t) {
+      if (!(sc[t] > jb.min_score)) continue;
+      const unsigned o = FloatToOrdered(sc[t]);
+      const unsigned old = atomicMax(&lb[si.job], o);
+      if (o >= old) {
+        const int idx = atomicAdd(leaf_count, 1);
+        if (idx < leaf_cap) leaves[idx] = Node{nd.scan, cx[t], cy[t], sc[t]};
+        else *overflow = 1;
+      }
+    }
+  } else {
+    const float bound = OrderedToFloat(lb[si.job]);
+    int keep = 0;
+    for (int t = 0; t < c; ++t)
+      if (sc[t] > jb.min_score && sc[t] >= bound) ++keep;
+    if (keep) {
+      int idx = atomicAdd(next_count, keep);
+      for (int t = 0; t < c; ++t) {
+        if (sc[t] > jb.min_score && sc[t] >= bound) {
+          if (idx < next_cap) next[idx] = Node{nd.scan, cx[t], cy[t], sc[t]};
+          else *overflow = 1;
+          ++idx;
+        }
+      }
+    }
+  }
+}
+
+// Keeps the leaves whose score equals their job's final optimum.
+__global__ void k_compact_leaves(const ScanInfo* __restrict__ info, const Node* __restrict__ in,
+                                 int count, const unsigned* __restrict__ lb,
+                                 Node* __restrict__ out, int* __restrict__ out_count, int cap,
+                                 int* __restrict__ overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const Node nd = in[i];
+  if (FloatToOrdered(nd.score) >= lb[info[nd.scan].job]) {
+    const int idx = atomicAdd(out_count, 1);
+    if (idx < cap) out[idx] = nd;
+    else *overflow = 1;
+  }
+}
+
+}  // namespace csm
+
+// ===========================================================================
+// Host side
+// ===========================================================================
+using namespace csm;
+
+namespace {
+
+// mapping/value_conversion_tables.cc:29-51 and fast...2d.cc:97-98,110-111,163-169:
+// lut[v] = lround(((1 - |cost(v)|) - min_score) * (255 / (max_score - min_score)))
+void BuildLut(float min_cost, float max_cost, uint8_t* lut, float* min_score, float* max_score) {
+  const float lo = 1.f - max_cost;  // min_score_
+  const float hi = 1.f - min_cost;  // max_score_
+  *min_score = lo;
+  *max_score = hi;
+  const float kScale = (max_cost - min_cost) / 32766.f;
+  for (int v = 0; v < 65536; ++v) {
+    const uint16_t value = static_cast<uint16_t>(v) & static_cast<uint16_t>(~(1u << 15));
+    float cost;
+    if (value == 0) cost = max_cost;  // unknown -> max_correspondence_cost (grid_2d.cc:69-71)
+    else cost = value * kScale + (min_cost - kScale);
+    const float probability = 1.f - std::abs(cost);
+    const long q = std::lround((probability - lo) * (255.f / (hi - lo)));
+    lut[v] = static_cast<uint8_t>(q < 0 ? 0 : (q > 255 ? 255 : q));
+  }
+}
+
+int DivUp(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+}  // namespace
+
+extern "C" {
+
+csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, double resolution,
+                              double max_x, double max_y, float min_cost, float max_cost,
+                              int32_t depth, int32_t device, csm_stack2d** out) {
+  CSM_REQUIRE(out != nullptr && cells != nullptr, "null pointer");
+  CSM_REQUIRE(nx >= 1 && ny >= 1, "cell limits must be >= 1");  // fast...2d.cc:100-102
+  CSM_REQUIRE(depth >= 1 && depth <= kMaxDepth, "branch_and_bound_depth out of range");  // :174
+  CSM_REQUIRE(resolution > 0., "resolution must be > 0");
+  CSM_REQUIRE(min_cost < max_cost, "min cost must be < max cost");  // grid_2d.cc:73
+  CSM_REQUIRE(static_cast<long long>(nx) + (1 << (depth - 1)) < 32000 &&
+              static_cast<long long>(ny) + (1 << (depth - 1)) < 32000, "grid too large");
+  Ctx* ctx;
+  CSM_TRY(GetCtx(device, &ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CSM_CUDA(cudaSetDevice(device));
+  std::unique_ptr<csm_stack2d> st(new csm_stack2d);
+  st->ctx = ctx;
+  st->min_cost = min_cost;
+  st->max_cost = max_cost;
+  StackDev& h = st->h;
+  std::memset(&h, 0, sizeof(h));
+  h.nx = nx;
+  h.ny = ny;
+  h.depth = depth;
+  h.resolution = resolution;
+  h.max_x = max_x;
+  h.max_y = max_y;
+  std::vector<uint8_t> lut(65536);
+  BuildLut(min_cost, max_cost, lut.data(), &h.min_score, &h.max_score);
+  h.k255 = (h.max_score - h.min_score) / 255.f;
+  size_t total = 0;
+  for (int l = 0; l < depth; ++l) {
+    const int w = 1 << l;
+    h.wx[l] = nx + w - 1;
+    h.wy[l] = ny + w - 1;
+    st->level_off[l] = total;
+    total += (static_cast<size_t>(h.wx[l]) * h.wy[l] + 255) / 256 * 256;
+  }
+  CSM_CUDA(cudaMalloc(&st->d_levels, total));
+  for (int l = 0; l < depth; ++l) h.level[l] = st->d_levels + st->level_off[l];
+  // decimated copy of the top level only (the dense lowest-resolution pass)
+  const int top = depth - 1;
+  {
+    const int s = 1 << top;
+    h.id[top] = (h.wx[top] + s - 1) / s;
+    h.jd[top] = (h.wy[top] + s - 1) / s;
+    h.id_stride[top] = (h.id[top] + 3) / 4 * 4 + 4;
+    const size_t bytes = static_cast<size_t>(s) * s * h.jd[top] * h.id_stride[top];
+    CSM_CUDA(cudaMalloc(&st->d_dec, bytes + 32));
+    CSM_CUDA(cudaMemsetAsync(st->d_dec, 0, bytes + 32, ctx->stream));
+    h.dec[top] = st->d_dec + 16;
+  }
+  // upload cells + LUT into scratch
+  DevBuf& d_cells = ctx->D("stack_cells");
+  DevBuf& d_lut = ctx->D("stack_lut");
+  const size_t ncell = static_cast<size_t>(nx) * ny;
+  CSM_TRY(d_cells.Reserve(ncell * sizeof(uint16_t)));
+  CSM_TRY(d_lut.Reserve(65536));
+  CSM_CUDA(cudaMemcpyAsync(d_cells.p, cells, ncell * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  CSM_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 65536, cudaMemcpyHostToDevice, ctx->stream));
+  k_stack_level0<<<DivUp(ncell, 256), 256, 0, ctx->stream>>>(
+      d_cells.as<uint16_t>(), d_lut.as<uint8_t>(), st->d_levels + st->level_off[0],
+      static_cast<int>(ncell));
+  CSM_LAUNCH_CHECK();
+  for (int l = 1; l < depth; ++l) {
+    dim3 block(32, 8), grid(DivUp(h.wx[l], 32), DivUp(h.wy[l], 8));
+    k_stack_double<<<grid, block, 0, ctx->stream>>>(st->d_levels + st->level_off[l - 1],
+                                                    h.wx[l - 1], h.wy[l - 1],
+                                                    st->d_levels + st->level_off[l], h.wx[l],
+                                                    h.wy[l], 1 << (l - 1));
+    CSM_LAUNCH_CHECK();
+  }
+  k_stack_decimate<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+      h.level[top], h.wx[top], h.wy[top], top, st->d_dec + 16, h.id[top], h.jd[top],
+      h.id_stride[top]);
+  CSM_LAUNCH_CHECK();
+  CSM_CUDA(cudaMalloc(&st->d, sizeof(StackDev)));
+  CSM_CUDA(cudaMemcpyAsync(st->d, &h, sizeof(StackDev), cudaMemcpyHostToDevice, ctx->stream));
+  CSM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = st.release();
+  return CSM_OK;
+}
+
+csm_status csm_stack2d_destroy(csm_stack2d* stack) {
+  if (!stack) return CSM_OK;
+  std::lock_guard<std::mutex> lock(stack->ctx->mu);
+  cudaSetDevice(stack->ctx->device);
+  cudaStreamSynchronize(stack->ctx->stream);
+  cudaFree(stack->d_levels);
+  cudaFree(stack->d_dec);
+  cudaFree(stack->d);
+  delete stack;
+  return CSM_OK;
+}
+
+csm_status csm_stack2d_read_level(const csm_stack2d* stack, int32_t level, uint8_t* out,
+                                  int32_t* wide_num_x, int32_t* wide_num_y) {
+  CSM_REQUIRE(stack != nullptr, "null stack");
+  CSM_REQUIRE(level >= 0 && level < stack->h.depth, "level out of range");
+  if (wide_num_x) *wide_num_x = stack->h.wx[level];
+  if (wide_num_y) *wide_num_y = stack->h.wy[level];
+  if (out) {
+    std::lock_guard<std::mutex> lock(stack->ctx->mu);
+    CSM_CUDA(cudaSetDevice(stack->ctx->device));
+    CSM_CUDA(cudaMemcpy(out, stack->h.level[level],
+                        static_cast<size_t>(stack->h.wx[level]) * stack->h.wy[level],
+                        cudaMemcpyDeviceToHost));
+  }
+  return CSM_OK;
+}
+
+csm_status csm_cloud_create(const float* xyz, int32_t n, int32_t device, csm_cloud** out) {
+  CSM_REQUIRE(out != nullptr && xyz != nullptr, "null pointer");
+  CSM_REQUIRE(n >= 1, "empty point cloud");
+  Ctx* ctx;
+  CSM_TRY(GetCtx(device, &ctx));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CSM_CUDA(cudaSetDevice(device));
+  std::unique_ptr<csm_cloud> c(new csm_cloud);
+  c->ctx = ctx;
+  c->n = n;
+  c->h_xyz.assign(xyz, xyz + 3 * static_cast<size_t>(n));
+  float m = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float x = xyz[3 * i], y = xyz[3 * i + 1];
+    const float range = std::sqrt(x * x + y * y);  // head<2>().norm()
+    m = std::max(range, m);
+  }
+  c->max_norm = m;
+  CSM_CUDA(cudaMalloc(&c->d_xyz, sizeof(float) * 3 * n));
+  CSM_CUDA(cudaMemcpyAsync(c->d_xyz, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice,
+                           ctx->stream));
+  CSM_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = c.release();
+  return CSM_OK;
+}
+
+csm_status csm_cloud_destroy(csm_cloud* cloud) {
+  if (!cloud) return CSM_OK;
+  std::lock_guard<std::mutex> lock(cloud->ctx->mu);
+  cudaSetDevice(cloud->ctx->device);
+  cudaStreamSynchronize(cloud->ctx->stream);
+  cudaFree(cloud->d_xyz);
+  delete cloud;
+  return CSM_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Batched matcher
+// ---------------------------------------------------------------------------
+namespace {
+
+// SearchParameters(linear, angular, cloud, resolution)   (corr...2d.cc:27-55)
+struct HostSearch {
+  int num_angular;
+  int num_scans;
+  int lin;
+  double step;
+};
+HostSearch MakeSearch(double linear_window, double angular_window, float cloud_max_norm,
+                      double resolution) {
+  float max_scan_range = 3.f * resolution;
+  max_scan_range = std::max(cloud_max_norm, max_scan_range);
+  const double kSafetyMargin = 1. - 1e-3;
+  HostSearch s;
+  s.step = kSafetyMargin *
+           std::acos(1. - (resolution * resolution) / (2. * (max_scan_range * max_scan_range)));
+  s.num_angular = static_cast<int>(std::ceil(angular_window / s.step));
+  s.num_scans = 2 * s.num_angular + 1;
+  s.lin = static_cast<int>(std::ceil(linear_window / resolution));
+  return s;
+}
+
+struct TrigKey {
+  const csm_cloud* cloud;
+  double resolution, angular;
+  bool operator<(const TrigKey& o) const {
+    if (cloud != o.cloud) return cloud < o.cloud;
+    if (resolution != o.resolution) return resolution < o.resolution;
+    return angular < o.angular;
+  }
+};
+
+struct BatchPlan {
+  std::vector<JobDev> jobs;
+  std::vector<HostSearch> search;
+  std::vector<double> init_x, init_y, init_theta;
+  std::vector<int> scan_job;
+  std::vector<long long> scan_slot_base;
+  long long total_scans = 0, total_points = 0, total_slots = 0;
+};
+
+struct TieLeaf { int scan, xo, yo; };
+
+}  // namespace
+
+// Runs a batch of independent matches.  `with_search` == false stops after
+// discretisation (test hook csm_discretize2d).
+static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num_stacks,
+                             const csm_cloud* const* clouds, int num_clouds,
+                             const csm_job2d* jobs, int num_jobs, double linear_window,
+                             double angular_window, csm_result2d* results, csm_stats* total,
+                             bool discretize_only, int32_t* out_dscan, int32_t* out_bounds) {
+  CSM_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  BatchPlan plan;
+  plan.jobs.resize(num_jobs);
+  plan.search.resize(num_jobs);
+  plan.init_x.resize(num_jobs);
+  plan.init_y.resize(num_jobs);
+  plan.init_theta.resize(num_jobs);
+
+  // ---- host: SearchParameters + rotation tables (libm, like the reference) ----
+  std::map<TrigKey, long long> trig_index;  // -> offset (in float2) into trig table
+  std::vector<float> trig;                  // (cos, sin) pairs
+  std::vector<long long> trig_off;
+  for (int j = 0; j < num_jobs; ++j) {
+    const csm_job2d& jb = jobs[j];
+    CSM_REQUIRE(jb.stack_index >= 0 && jb.stack_index < num_stacks, "stack index");
+    CSM_REQUIRE(jb.cloud_index >= 0 && jb.cloud_index < num_clouds, "cloud index");
+    const csm_stack2d* st = stacks[jb.stack_index];
+    const csm_cloud* cl = clouds[jb.cloud_index];
+    CSM_REQUIRE(st && cl && st->ctx == ctx && cl->ctx == ctx, "handles must share one device");
+    const StackDev& h = st->h;
+    double lin = linear_window, ang = angular_window;
+    double ix = jb.initial_pose[0], iy = jb.initial_pose[1], ith = jb.initial_pose[2];
+    if (jb.full_submap) {  // fast...2d.cc:210-225
+      lin = 1e6 * h.resolution;
+      ang = M_PI;
+      ix = h.max_x - 0.5 * h.resolution * h.ny;
+      iy = h.max_y - 0.5 * h.resolution * h.nx;
+      ith = 0.;
+    }
+    const HostSearch sp = MakeSearch(lin, ang, cl->max_norm, h.resolution);
+    CSM_REQUIRE(sp.num_scans > 0 && sp.num_scans < (1 << 22), "angular window / step");
+    plan.search[j] = sp;
+    plan.init_x[j] = ix;
+    plan.init_y[j] = iy;
+    plan.init_theta[j] = ith;
+    const TrigKey key{cl, h.resolution, ang};
+    auto it = trig_index.find(key);
+    if (it == trig_index.end()) {
+      const long long off = static_cast<long long>(trig.size() / 2);
+      // GenerateRotatedScans: delta_theta accumulates in double, is cast to float
+      // for AngleAxisf, Quaternionf takes cos/sin of the float half angle.
+      double delta_theta = -sp.num_angular * sp.step;
+      for (int k = 0; k < sp.num_scans; ++k, delta_theta += sp.step) {
+        const float ha = 0.5f * static_cast<float>(delta_theta);
+        trig.push_back(std::cos(ha));
+        trig.push_back(std::sin(ha));
+      }
+      it = trig_index.emplace(key, off).first;
+    }
+    JobDev& d = plan.jobs[j];
+    d.stack = st->d;
+    d.xyz = cl->d_xyz;
+    d.trig = nullptr;  // set once the table is uploaded
+    trig_off.push_back(it->second);
+    d.n = cl->n;
+    d.num_scans = sp.num_scans;
+    d.scan_base = static_cast<int>(plan.total_scans);
+    d.lin = sp.lin;
+    {
+      const float ha = 0.5f * static_cast<float>(ith);
+      const float sn = std::sin(ha);
+      d.q0w = std::cos(ha);
+      d.q0x = sn * 0.f;
+      d.q0y = sn * 0.f;
+      d.q0z = sn * 1.f;
+    }
+    d.tx = static_cast<float>(ix);
+    d.ty = static_cast<float>(iy);
+    d.min_score = jb.min_score;
+    // upper bound of lowest-resolution candidates per axis after ShrinkToFit:
+    // window <= min(2*lin, cells - 1 + scan extent)
+    const int step = 1 << (h.depth - 1);
+    const long long extent = 2LL * static_cast<long long>(std::ceil(cl->max_norm / h.resolution)) + 4;
+    const long long span_x = std::min<long long>(2LL * sp.lin, h.nx - 1 + extent);
+    const long long span_y = std::min<long long>(2LL * sp.lin, h.ny - 1 + extent);
+    const long long cx = (span_x + step) / step, cy = (span_y + step) / step;
+    d.cap_y = static_cast<int>(cy);
+    d.cap = static_cast<int>(cx * cy);
+    d.dscan_off = plan.total_points;
+    d.top_off = plan.total_slots;
+    plan.total_scans += sp.num_scans;
+    plan.total_points += static_cast<long long>(sp.num_scans) * cl->n;
+    plan.total_slots += static_cast<long long>(sp.num_scans) * d.cap;
+    CSM_REQUIRE(plan.total_scans < (1LL << 30), "too many scans in one batch");
+  }
+  plan.scan_job.resize(plan.total_scans);
+  plan.scan_slot_base.resize(plan.total_scans);
+  for (int j = 0; j < num_jobs; ++j) {
+    const JobDev& d = plan.jobs[j];
+    for (int k = 0; k < d.num_scans; ++k) {
+      plan.scan_job[d.scan_base + k] = j;
+      plan.scan_slot_base[d.scan_base + k] = d.top_off + static_cast<long long>(k) * d.cap;
+    }
+  }
+
+  // ---- device buffers ----
+  DevBuf& d_trig = ctx->D("trig");
+  DevBuf& d_jobs = ctx->D("jobs");
+  DevBuf& d_scan_job = ctx->D("scan_job");
+  DevBuf& d_slot_base = ctx->D("slot_base");
+  DevBuf& d_info = ctx->D("info");
+  DevBuf& d_dscan = ctx->D("dscan");
+  DevBuf& d_top = ctx->D("top_sum");
+  DevBuf& d_lb = ctx->D("lb");
+  DevBuf& d_ctr = ctx->D("counters");
+  CSM_TRY(d_trig.Reserve(trig.size() * sizeof(float)));
+  CSM_TRY(d_jobs.Reserve(sizeof(JobDev) * num_jobs));
+  CSM_TRY(d_scan_job.Reserve(sizeof(int) * plan.total_scans));
+  CSM_TRY(d_slot_base.Reserve(sizeof(long long) * plan.total_scans));
+  CSM_TRY(d_info.Reserve(sizeof(ScanInfo) * plan.total_scans));
+  CSM_TRY(d_dscan.Reserve(sizeof(int2) * plan.total_points));
+  CSM_TRY(d_lb.Reserve(sizeof(unsigned) * num_jobs));
+  CSM_TRY(d_ctr.Reserve(sizeof(unsigned long long) * 8 + sizeof(int) * 32));
+  for (int j = 0; j < num_jobs; ++j) plan.jobs[j].trig = d_trig.as<float2>() + trig_off[j];
+
+  CSM_CUDA(cudaEventRecord(ctx->ev0, s));
+  CSM_CUDA(cudaMemcpyAsync(d_trig.p, trig.data(), trig.size() * sizeof(float),
+                           cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemcpyAsync(d_jobs.p, plan.jobs.data(), sizeof(JobDev) * num_jobs,
+                           cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemcpyAsync(d_scan_job.p, plan.scan_job.data(), sizeof(int) * plan.total_scans,
+                           cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemcpyAsync(d_slot_base.p, plan.scan_slot_base.data(),
+                           sizeof(long long) * plan.total_scans, cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 8 + sizeof(int) * 32, s));
+  unsigned long long* ctr = d_ctr.as<unsigned long long>();
+  int* ictr = reinterpret_cast<int*>(ctr + 8);  // [0..15] queue counts, [16] leaf, [17] best, [20] overflow
+
+  const int total_scans = static_cast<int>(plan.total_scans);
+  ProfBegin(ctx);
+  k_discretize<<<total_scans, 128, 0, s>>>(d_jobs.as<JobDev>(), d_scan_job.as<int>(),
+                                           d_dscan.as<int2>(), d_info.as<ScanInfo>(), 1, ctr);
+  CSM_LAUNCH_CHECK();
+  ProfEnd(ctx, "k_discretize", static_cast<double>(plan.total_points));
+
+  std::vector<ScanInfo> h_info;
+  if (discretize_only) {
+    h_info.resize(total_scans);
+    CSM_CUDA(cudaMemcpyAsync(h_info.data(), d_info.p, sizeof(ScanInfo) * total_scans,
+                             cudaMemcpyDeviceToHost, s));
+    if (out_dscan)
+      CSM_CUDA(cudaMemcpyAsync(out_dscan, d_dscan.p, sizeof(int2) * plan.total_points,
+                               cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaStreamSynchronize(s));
+    if (out_bounds)
+      for (int i = 0; i < total_scans; ++i) {
+        out_bounds[4 * i + 0] = h_info[i].min_x;
+        out_bounds[4 * i + 1] = h_info[i].max_x;
+        out_bounds[4 * i + 2] = h_info[i].min_y;
+        out_bounds[4 * i + 3] = h_info[i].max_y;
+      }
+    return CSM_OK;
+  }
+
+  // ---- lowest-resolution pass ----
+  CSM_TRY(d_top.Reserve(sizeof(int) * plan.total_slots));
+  {
+    std::vector<unsigned> lb0(num_jobs);
+    for (int j = 0; j < num_jobs; ++j) lb0[j] = HostFloatToOrdered(jobs[j].min_score);
+    CSM_CUDA(cudaMemcpyAsync(d_lb.p, lb0.data(), sizeof(unsigned) * num_jobs,
+                             cudaMemcpyHostToDevice, s));
+    CSM_CUDA(cudaStreamSynchronize(s));  // lb0 is a local
+  }
+  // Wide lattices (MatchFullSubmap) take the dense decimated-grid kernel; narrow
+  // ones (local windows: a few dozen candidates per scan) the gather kernel.
+  static const char* force = getenv("CSM_TOP_KERNEL");  // "gather" | "dense" (debug)
+  int max_cap = 0;
+  for (const JobDev& d : plan.jobs) max_cap = std::max(max_cap, d.cap);
+  bool use_gather_top = max_cap < 128;
+  if (force && !strcmp(force, "gather")) use_gather_top = true;
+  if (force && !strcmp(force, "dense")) use_gather_top = false;
+  ProfBegin(ctx);
+  if (use_gather_top) {
+    k_score_top_gather<<<DivUp(plan.total_slots * 32, 256), 256, 0, s>>>(
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),
+        d_slot_base.as<long long>(), total_scans, plan.total_slots);
+  } else {
+    k_score_top_dense<<<std::min(total_scans, ctx->sm_count * 64), kDenseThreads, 0, s>>>(
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),
+        d_slot_base.as<long long>(), total_scans);
+  }
+  CSM_LAUNCH_CHECK();
+  if (g_profile_on.load()) {
+    unsigned long long c3 = 0;
+    ProfStop(ctx);
+    CSM_CUDA(cudaStreamSynchronize(s));
+    CSM_CUDA(cudaMemcpy(&c3, ctr + 3, sizeof(c3), cudaMemcpyDeviceToHost));
+    ProfCommit(ctx, use_gather_top ? "k_score_top_gather" : "k_score_top_dense",
+               static_cast<double>(c3));
+  }
+
+  // ---- greedy dives seed the per-job bound ----
+  unsigned long long prof_c0 = 0;
+  auto prof_scored = [&]() -> double {  // candidates scored since the last call
+    unsigned long long c0 = 0;
+    cudaStreamSynchronize(s);
+    cudaMemcpy(&c0, ctr, sizeof(c0), cudaMemcpyDeviceToHost);
+    const double d = static_cast<double>(c0 - prof_c0);
+    prof_c0 = c0;
+    return d;
+  };
+  if (g_profile_on.load()) prof_scored();
+  ProfBegin(ctx);
+  k_dive<<<DivUp(static_cast<long long>(total_scans) * 32, 256), 256, 0, s>>>(
+      d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),
+      d_slot_base.as<long long>(), total_scans, d_lb.as<unsigned>(), ctr);
+  CSM_LAUNCH_CHECK();
+  if (g_profile_on.load()) {
+    ProfStop(ctx);
+    ProfCommit(ctx, "k_dive", prof_scored());
+  }
+
+  // ---- branch and bound: per-level queues, deepest level first ----
+  int depth_max = 0;
+  for (int j = 0; j < num_jobs; ++j)
+    depth_max = std::max(depth_max, stacks[jobs[j].stack_index]->h.depth);
+  for (int j = 0; j < num_jobs; ++j)
+    CSM_REQUIRE(stacks[jobs[j].stack_index]->h.depth == depth_max,
+                "all stacks of one batch must share branch_and_bound_depth");
+  const int hmax = depth_max - 1;
+  const int kChunk = 1 << 20;
+  const int kQueueCap = 4 * kChunk;
+  const int kLeafCap = 1 << 22;
+  const long long top_cap_ll = std::min<long long>(plan.total_slots, 1LL << 30);
+  const int top_cap = static_cast<int>(top_cap_ll);
+  DevBuf& d_qtop = ctx->D("queue_top");
+  DevBuf& d_q = ctx->D("queues");
+  DevBuf& d_leaves = ctx->D("leaves");
+  DevBuf& d_best = ctx->D("best_leaves");
+  CSM_TRY(d_qtop.Reserve(sizeof(Node) * static_cast<size_t>(top_cap)));
+  CSM_TRY(d_q.Reserve(sizeof(Node) * static_cast<size_t>(kQueueCap) * std::max(1, hmax)));
+  CSM_TRY(d_leaves.Reserve(sizeof(Node) * static_cast<size_t>(kLeafCap)));
+  CSM_TRY(d_best.Reserve(sizeof(Node) * static_cast<size_t>(kLeafCap)));
+  auto queue_ptr = [&](int h) -> Node* {
+    return h == hmax ? d_qtop.as<Node>() : d_q.as<Node>() + static_cast<size_t>(kQueueCap) * h;
+  };
+  auto queue_cap = [&](int h) { return h == hmax ? top_cap : kQueueCap; };
+  int* overflow = ictr + 20;
+  int* leaf_count = ictr + 16;
+  int* best_count = ictr + 17;
+
+  std::vector<int> qn(hmax + 1, 0);
+  int h_leaf = 0, h_over = 0;
+  PinnedBuf& pin = ctx->P("readback");
+  CSM_TRY(pin.Reserve(sizeof(int) * 32));
+  int* hp = pin.as<int>();
+
+  if (hmax == 0) {
+    // depth 1: the lowest resolution IS the leaf level (fast...2d.cc:339-343).
+    // Treat every top candidate as a leaf via the filter + a copy to `leaves`.
+  }
+  k_filter_top<<<std::min(total_scans, ctx->sm_count * 16), 256, 0, s>>>(
+      d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_top.as<int>(), d_slot_base.as<long long>(),
+      total_scans, d_lb.as<unsigned>(), queue_ptr(hmax), ictr + hmax, queue_cap(hmax), overflow);
+  CSM_LAUNCH_CHECK();
+  CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
+  CSM_CUDA(cudaStreamSynchronize(s));
+  qn[hmax] = hp[hmax];
+  if (hp[20]) { SetError("top-level queue overflow"); return CSM_E_CAPACITY; }
+
+  if (hmax == 0) {
+    // every queued node is already a leaf
+    CSM_CUDA(cudaMemcpyAsync(d_leaves.p, queue_ptr(0), sizeof(Node) * qn[0],
+                             cudaMemcpyDeviceToDevice, s));
+    CSM_CUDA(cudaMemcpyAsync(leaf_count, &qn[0], sizeof(int), cudaMemcpyHostToDevice, s));
+    CSM_CUDA(cudaStreamSynchronize(s));
+    h_leaf = qn[0];
+    // bound = max score: computed by a tiny expand-less pass below (compact uses lb),
+    // so raise lb on the host side from the leaves
+    std::vector<Node> tmp(qn[0]);
+    CSM_CUDA(cudaMemcpy(tmp.data(), d_leaves.p, sizeof(Node) * qn[0], cudaMemcpyDeviceToHost));
+    std::vector<unsigned> lbh(num_jobs);
+    CSM_CUDA(cudaMemcpy(lbh.data(), d_lb.p, sizeof(unsigned) * num_jobs, cudaMemcpyDeviceToHost));
+    std::vector<int> sj(plan.scan_job);
+    for (const Node& nd : tmp)
+      lbh[sj[nd.scan]] = std::max(lbh[sj[nd.scan]], HostFloatToOrdered(nd.score));
+    CSM_CUDA(cudaMemcpy(d_lb.p, lbh.data(), sizeof(unsigned) * num_jobs, cudaMemcpyHostToDevice));
+    qn[0] = 0;
+  }
+
+  for (;;) {
+    int h = -1;
+    for (int l = 1; l <= hmax; ++l)
+      if (qn[l] > 0) { h = l; break; }
+    if (h < 0) break;
+    const int chunk = std::min(qn[h], kChunk);
+    const int start = qn[h] - chunk;
+    if (h - 1 >= 1) CSM_CUDA(cudaMemsetAsync(ictr + (h - 1), 0, sizeof(int), s));
+    ProfBegin(ctx);
+    k_expand<<<DivUp(static_cast<long long>(chunk) * 32, 256), 256, 0, s>>>(
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), queue_ptr(h) + start,
+        chunk, h, d_lb.as<unsigned>(), h - 1 >= 1 ? queue_ptr(h - 1) : nullptr,
+        ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap, d_leaves.as<Node>(), leaf_count, kLeafCap,
+        overflow, ctr);
+    CSM_LAUNCH_CHECK();
+    if (g_profile_on.load()) {
+      ProfStop(ctx);
+      ProfCommit(ctx, "k_expand", prof_scored());
+    }
+    qn[h] -= chunk;
+    CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaStreamSynchronize(s));
+    if (h - 1 >= 1) qn[h - 1] = hp[h - 1];
+    h_leaf = hp[16];
+    h_over = hp[20];
+    if (h_over) { SetError("branch-and-bound queue overflow"); return CSM_E_CAPACITY; }
+    if (h_leaf > kLeafCap / 2) {
+      // drop leaves that are already below their job's bound
+      CSM_CUDA(cudaMemsetAsync(best_count, 0, sizeof(int), s));
+      k_compact_leaves<<<DivUp(h_leaf, 256), 256, 0, s>>>(
+          d_info.as<ScanInfo>(), d_leaves.as<Node>(), h_leaf, d_lb.as<unsigned>(),
+          d_best.as<Node>(), best_count, kLeafCap, overflow);
+      CSM_LAUNCH_CHECK();
+      CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
+      CSM_CUDA(cudaStreamSynchronize(s));
+      h_leaf = hp[17];
+      if (h_leaf > kLeafCap / 2) { SetError("too many tied leaves"); return CSM_E_CAPACITY; }
+      CSM_CUDA(cudaMemcpyAsync(d_leaves.p, d_best.p, sizeof(Node) * h_leaf,
+                               cudaMemcpyDeviceToDevice, s));
+      CSM_CUDA(cudaMemcpyAsync(leaf_count, &hp[17], sizeof(int), cudaMemcpyHostToDevice, s));
+      CSM_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+
+  // ---- collect the optimal leaves of every job ----
+  CSM_CUDA(cudaMemsetAsync(best_count, 0, sizeof(int), s));
+  if (h_leaf > 0) {
+    k_compact_leaves<<<DivUp(h_leaf, 256), 256, 0, s>>>(
+        d_info.as<ScanInfo>(), d_leaves.as<Node>(), h_leaf, d_lb.as<unsigned>(),
+        d_best.as<Node>(), best_count, kLeafCap, overflow);
+    CSM_LAUNCH_CHECK();
+  }
+  CSM_CUDA(cudaEventRecord(ctx->ev1, s));
+  CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
+  CSM_CUDA(cudaStreamSynchronize(s));
+  const int n_best = hp[17];
+  std::vector<Node> best(n_best);
+  std::vector<unsigned> lbh(num_jobs);
+  unsigned long long hctr[8];
+  if (n_best)
+    CSM_CUDA(cudaMemcpyAsync(best.data(), d_best.p, sizeof(Node) * n_best,
+                             cudaMemcpyDeviceToHost, s));
+  CSM_CUDA(cudaMemcpyAsync(lbh.data(), d_lb.p, sizeof(unsigned) * num_jobs,
+                           cudaMemcpyDeviceToHost, s));
+  CSM_CUDA(cudaMemcpyAsync(hctr, ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
+  CSM_CUDA(cudaStreamSynchronize(s));
+
+  // group optimal leaves by job
+  std::vector<std::vector<TieLeaf>> per_job(num_jobs);
+  for (const Node& nd : best) per_job[plan.scan_job[nd.scan]].push_back(TieLeaf{nd.scan, nd.xo, nd.yo});
+
+  // ---- tie resolution: the reference returns the first optimal leaf in DFS order ----
+  int host_resolves = 0;
+  long long lowest_total = 0;
+  bool need_info = false;
+  for (int j = 0; j < num_jobs; ++j)
+    if (per_job[j].size() > 1) need_info = true;
+  if (need_info) {
+    h_info.resize(total_scans);
+    CSM_CUDA(cudaMemcpy(h_info.data(), d_info.p, sizeof(ScanInfo) * total_scans,
+                        cudaMemcpyDeviceToHost));
+  }
+  lowest_total = static_cast<long long>(hctr[3]);
+  for (int j = 0; j < num_jobs; ++j) {
+    std::vector<TieLeaf>& ties = per_job[j];
+    if (ties.size() <= 1) continue;
+    const int T = static_cast<int>(ties.size());
+    // ancestor scores at levels 1..hmax
+    std::vector<ListCand> lc;
+    lc.reserve(static_cast<size_t>(T) * hmax);
+    for (const TieLeaf& t : ties) {
+      const ScanInfo& si = h_info[t.scan];
+      for (int l = 1; l <= hmax; ++l) {
+        const int ax = si.min_x + (((t.xo - si.min_x) >> l) << l);
+        const int ay = si.min_y + (((t.yo - si.min_y) >> l) << l);
+        lc.push_back(ListCand{t.scan, ax, ay, l});
+      }
+    }
+    std::vector<float> anc(lc.size());
+    if (!lc.empty()) {
+      DevBuf& d_lc = ctx->D("tie_cands");
+      DevBuf& d_ls = ctx->D("tie_scores");
+      CSM_TRY(d_lc.Reserve(sizeof(ListCand) * lc.size()));
+      CSM_TRY(d_ls.Reserve(sizeof(float) * lc.size()));
+      CSM_CUDA(cudaMemcpyAsync(d_lc.p, lc.data(), sizeof(ListCand) * lc.size(),
+                               cudaMemcpyHostToDevice, s));
+      k_score_list<<<DivUp(static_cast<long long>(lc.size()) * 32, 256), 256, 0, s>>>(
+          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_lc.as<ListCand>(),
+          static_cast<int>(lc.size()), nullptr, d_ls.as<float>());
+      CSM_LAUNCH_CHECK();
+      CSM_CUDA(cudaMemcpyAsync(anc.data(), d_ls.p, sizeof(float) * lc.size(),
+                               cudaMemcpyDeviceToHost, s));
+      CSM_CUDA(cudaStreamSynchronize(s));
+    }
+    // lazily computed rank of every lowest-resolution candidate of this job in
+    // the reference's std::sort order (fast...2d.cc:331-332)
+    std::vector<int> top_rank;
+    std::vector<long long> scan_first;  // first generation index of each scan
+    auto ensure_top_rank = [&]() -> csm_status {
+      if (!top_rank.empty()) return CSM_OK;
+      ++host_resolves;
+      const JobDev& jd = plan.jobs[j];
+      std::vector<int> sums(static_cast<size_t>(jd.num_scans) * jd.cap);
+      CSM_CUDA(cudaMemcpy(sums.data(), d_top.as<int>() + jd.top_off, sizeof(int) * sums.size(),
+                          cudaMemcpyDeviceToHost));
+      const StackDev& sh = stacks[jobs[j].stack_index]->h;
+      struct Item { float score; int gen; };
+      std::vector<Item> items;
+      scan_first.assign(jd.num_scans, 0);
+      for (int k = 0; k < jd.num_scans; ++k) {
+        const ScanInfo& si = h_info[jd.scan_base + k];
+        scan_first[k] = static_cast<long long>(items.size());
+        for (int q = 0; q < si.nxc * si.nyc; ++q) {
+          const float mean = static_cast<float>(sums[static_cast<size_t>(k) * jd.cap + q]) /
+                             static_cast<float>(jd.n);
+          items.push_back(Item{sh.min_score + mean * sh.k255, static_cast<int>(items.size())});
+        }
+      }
+      std::sort(items.begin(), items.end(),
+                [](const Item& a, const Item& b) { return a.score > b.score; });
+      top_rank.resize(items.size());
+      for (size_t r = 0; r < items.size(); ++r) top_rank[items[r].gen] = static_cast<int>(r);
+      return CSM_OK;
+    };
+    // returns true if leaf a precedes leaf b in the reference's DFS order
+    csm_status err = CSM_OK;
+    auto before = [&](int a, int b) -> bool {
+      const TieLeaf& A = ties[a];
+      const TieLeaf& B = ties[b];
+      const ScanInfo& sa = h_info[A.scan];
+      const ScanInfo& sb = h_info[B.scan];
+      for (int l = hmax; l >= 0; --l) {
+        const int ax = (A.xo - sa.min_x) >> l, ay = (A.yo - sa.min_y) >> l;
+        const int bx = (B.xo - sb.min_x) >> l, by = (B.yo - sb.min_y) >> l;
+        if (A.scan == B.scan && ax == bx && ay == by) continue;  // same ancestor
+        const float fa = l == 0 ? 0.f : anc[static_cast<size_t>(a) * hmax + (l - 1)];
+        const float fb = l == 0 ? 0.f : anc[static_cast<size_t>(b) * hmax + (l - 1)];
+        if (l > 0 && fa != fb) return fa > fb;
+        if (l == hmax) {
+          // equal lowest-resolution scores: replay the reference's std::sort
+          if (ensure_top_rank() != CSM_OK) { err = CSM_E_CUDA; return false; }
+          const JobDev& jd = plan.jobs[j];
+          const long long ga = scan_first[A.scan - jd.scan_base] + static_cast<long long>(ax) * sa.nyc + ay;
+          const long long gb = scan_first[B.scan - jd.scan_base] + static_cast<long long>(bx) * sb.nyc + by;
+          return top_rank[ga] < top_rank[gb];
+        }
+        // siblings: stable insertion sort keeps generation order (x outer, y inner)
+        if ((ax & 1) != (bx & 1)) return (ax & 1) < (bx & 1);
+        return (ay & 1) < (by & 1);
+      }
+      return false;
+    };
+    int w = 0;
+    for (int t = 1; t < T; ++t)
+      if (before(t, w)) w = t;
+    if (err != CSM_OK) return err;
+    std::swap(ties[0], ties[w]);
+  }
+
+  // ---- results ----
+  for (int j = 0; j < num_jobs; ++j) {
+    csm_result2d& r = results[j];
+    const float best_score = HostOrderedToFloat(lbh[j]);
+    r.found = 0;
+    r.leaves_tied = static_cast<int32_t>(per_job[j].size());
+    if (!per_job[j].empty() && best_score > jobs[j].min_score) {
+      const TieLeaf& t = per_job[j][0];
+      const JobDev& jd = plan.jobs[j];
+      const HostSearch& sp = plan.search[j];
+      const double res = stacks[jobs[j].stack_index]->h.resolution;
+      const int scan_index = t.scan - jd.scan_base;
+      // Candidate2D (corr...2d.h:77-86): x = -y_off * res, y = -x_off * res
+      const double cx = -t.yo * res, cy = -t.xo * res;
+      const double orientation = (scan_index - sp.num_angular) * sp.step;
+      r.found = 1;
+      r.score = best_score;
+      r.pose_estimate[0] = plan.init_x[j] + cx;
+      r.pose_estimate[1] = plan.init_y[j] + cy;
+      r.pose_estimate[2] = plan.init_theta[j] + orientation;
+      r.best_scan_index = scan_index;
+      r.best_x_offset = t.xo;
+      r.best_y_offset = t.yo;
+    }
+  }
+  if (total) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    total->candidates_scored += static_cast<int64_t>(hctr[0]);
+    total->nodes_expanded += static_cast<int64_t>(hctr[1]);
+    total->lowest_resolution_candidates += lowest_total;
+    total->host_tie_resolves += host_resolves;
+    total->device_ms += ms;
+    if (num_jobs == 1) {
+      total->num_scans = plan.search[0].num_scans;
+      total->leaves_tied = results[0].leaves_tied;
+      total->best_scan_index = results[0].best_scan_index;
+      total->best_x_offset = results[0].best_x_offset;
+      total->best_y_offset = results[0].best_y_offset;
+    }
+  }
+  return CSM_OK;
+}
+
+extern "C" {
+
+csm_status csm_match2d_batch(const csm_stack2d* const* stacks, int32_t num_stacks,
+                             const csm_cloud* const* clouds, int32_t num_clouds,
+                             const csm_job2d* jobs, int32_t num_jobs, double linear_window,
+                             double angular_window, csm_result2d* results, csm_stats* total) {
+  CSM_REQUIRE(stacks && clouds && jobs && results, "null pointer");
+  CSM_REQUIRE(num_jobs >= 1 && num_stacks >= 1 && num_clouds >= 1, "empty batch");
+  CSM_REQUIRE(stacks[0] != nullptr, "null stack");
+  Ctx* ctx = stacks[0]->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (total) std::memset(total, 0, sizeof(*total));
+  // Split into sub-batches so the discrete-scan buffer stays below ~8 GB.
+  const long long kMaxPoints = 1LL << 30;
+  int j0 = 0;
+  while (j0 < num_jobs) {
+    long long pts = 0;
+    int j1 = j0;
+    while (j1 < num_jobs) {
+      const csm_job2d& jb = jobs[j1];
+      CSM_REQUIRE(jb.stack_index >= 0 && jb.stack_index < num_stacks, "stack index");
+      CSM_REQUIRE(jb.cloud_index >= 0 && jb.cloud_index < num_clouds, "cloud index");
+      const csm_stack2d* st = stacks[jb.stack_index];
+      const csm_cloud* cl = clouds[jb.cloud_index];
+      CSM_REQUIRE(st && cl, "null handle");
+      const double ang = jb.full_submap ? M_PI : angular_window;
+      const double lin = jb.full_submap ? 1e6 * st->h.resolution : linear_window;
+      const HostSearch sp = MakeSearch(lin, ang, cl->max_norm, st->h.resolution);
+      const long long add = static_cast<long long>(sp.num_scans) * cl->n;
+      if (j1 > j0 && pts + add > kMaxPoints) break;
+      pts += add;
+      ++j1;
+    }
+    CSM_TRY(RunBatch2D(ctx, stacks, num_stacks, clouds, num_clouds, jobs + j0, j1 - j0,
+                       linear_window, angular_window, results + j0, total, false, nullptr,
+                       nullptr));
+    j0 = j1;
+  }
+  return CSM_OK;
+}
+
+csm_status csm_match2d(const csm_stack2d* stack, const float* xyz, int32_t n,
+                       const double initial_pose[3], int32_t full_submap, double linear_window,
+                       double angular_window, float min_score, int32_t* found, float* score,
+                       double pose_estimate[3], csm_stats* stats) {
+  CSM_REQUIRE(stack && xyz && found && score && pose_estimate, "null pointer");  // :232-233
+  CSM_REQUIRE(full_submap || initial_pose, "null initial pose");
+  csm_cloud* cloud = nullptr;
+  CSM_TRY(csm_cloud_create(xyz, n, stack->ctx->device, &cloud));
+  csm_job2d job;
+  std::memset(&job, 0, sizeof(job));
+  job.full_submap = full_submap;
+  if (initial_pose) std::memcpy(job.initial_pose, initial_pose, sizeof(double) * 3);
+  job.min_score = min_score;
+  csm_result2d res;
+  std::memset(&res, 0, sizeof(res));
+  const csm_cloud* cl = cloud;
+  const csm_status st = csm_match2d_batch(&stack, 1, &cl, 1, &job, 1, linear_window,
+                                          angular_window, &res, stats);
+  csm_cloud_destroy(cloud);
+  if (st != CSM_OK) return st;
+  *found = res.found;
+  if (res.found) {
+    *score = res.score;
+    std::memcpy(pose_estimate, res.pose_estimate, sizeof(double) * 3);
+  }
+  return CSM_OK;
+}
+
+csm_status csm_discretize2d(const csm_stack2d* stack, const float* xyz, int32_t n,
+                            const double initial_pose[3], int32_t full_submap,
+                            double linear_window, double angular_window, int32_t* num_scans,
+                            int32_t* discrete_scans, int32_t* bounds) {
+  CSM_REQUIRE(stack && xyz && num_scans, "null pointer");
+  csm_cloud* cloud = nullptr;
+  CSM_TRY(csm_cloud_create(xyz, n, stack->ctx->device, &cloud));
+  const double ang = full_submap ? M_PI : angular_window;
+  const double lin = full_submap ? 1e6 * stack->h.resolution : linear_window;
+  *num_scans = MakeSearch(lin, ang, cloud->max_norm, stack->h.resolution).num_scans;
+  csm_status st = CSM_OK;
+  if (discrete_scans || bounds) {
+    csm_job2d job;
+    std::memset(&job, 0, sizeof(job));
+    job.full_submap = full_submap;
+    if (initial_pose) std::memcpy(job.initial_pose, initial_pose, sizeof(double) * 3);
+    const csm_cloud* cl = cloud;
+    std::lock_guard<std::mutex> lock(stack->ctx->mu);
+    st = RunBatch2D(stack->ctx, &stack, 1, &cl, 1, &job, 1, linear_window, angular_window,
+                    nullptr, nullptr, true, discrete_scans, bounds);
+  }
+  csm_cloud_destroy(cloud);
+  return st;
+}
+
+csm_status csm_score_candidates2d(const csm_stack2d* stack, int32_t level,
+                                  const int32_t* discrete_scans, int32_t num_scans,
+                                  int32_t n, const int32_t* candidates, int32_t num_candidates,
+                                  float* scores, int32_t* sums) {
+  CSM_REQUIRE(stack && discrete_scans && candidates && scores, "null pointer");
+  CSM_REQUIRE(level >= 0 && level < stack->h.depth, "level out of range");
+  CSM_REQUIRE(num_scans >= 1 && n >= 1 && num_candidates >= 0, "sizes");
+  if (num_candidates == 0) return CSM_OK;
+  Ctx* ctx = stack->ctx;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CSM_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // one synthetic job whose discrete scans are supplied by the caller
+  JobDev jd;
+  std::memset(&jd, 0, sizeof(jd));
+  jd.stack = stack->d;
+  jd.n = n;
+  jd.num_scans = num_scans;
+  std::vector<ScanInfo> info(num_scans);
+  for (int k = 0; k < num_scans; ++k) {
+    std::memset(&info[k], 0, sizeof(ScanInfo));
+    info[k].job = 0;
+  }
+  std::vector<ListCand> lc(num_candidates);
+  for (int c = 0; c < num_candidates; ++c) {
+    CSM_REQUIRE(candidates[3 * c] >= 0 && candidates[3 * c] < num_scans, "scan_index");
+    lc[c] = ListCand{candidates[3 * c], candidates[3 * c + 1], candidates[3 * c + 2], level};
+  }
+  DevBuf& d_jobs = ctx->D("hook_jobs");
+  DevBuf& d_info = ctx->D("hook_info");
+  DevBuf& d_dscan = ctx->D("hook_dscan");
+  DevBuf& d_lc = ctx->D("hook_cands");
+  DevBuf& d_sc = ctx->D("hook_scores");
+  DevBuf& d_su = ctx->D("hook_sums");
+  const size_t npts = static_cast<size_t>(num_scans) * n;
+  CSM_TRY(d_jobs.Reserve(sizeof(JobDev)));
+  CSM_TRY(d_info.Reserve(sizeof(ScanInfo) * num_scans));
+  CSM_TRY(d_dscan.Reserve(sizeof(int2) * npts));
+  CSM_TRY(d_lc.Reserve(sizeof(ListCand) * num_candidates));
+  CSM_TRY(d_sc.Reserve(sizeof(float) * num_candidates));
+  CSM_TRY(d_su.Reserve(sizeof(int) * num_candidates));
+  CSM_CUDA(cudaMemcpyAsync(d_jobs.p, &jd, sizeof(jd), cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemcpyAsync(d_info.p, info.data(), sizeof(ScanInfo) * num_scans,
+                           cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemcpyAsync(d_dscan.p, discrete_scans, sizeof(int2) * npts,
+                           cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemcpyAsync(d_lc.p, lc.data(), sizeof(ListCand) * num_candidates,
+                           cudaMemcpyHostToDevice, s));
+  k_score_list<<<DivUp(static_cast<long long>(num_candidates) * 32, 256), 256, 0, s>>>(
+      d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_lc.as<ListCand>(),
+      num_candidates, d_su.as<int>(), d_sc.as<float>());
+  CSM_LAUNCH_CHECK();
+  CSM_CUDA(cudaMemcpyAsync(scores, d_sc.p, sizeof(float) * num_candidates,
+                           cudaMemcpyDeviceToHost, s));
+  if (sums)
+    CSM_CUDA(cudaMemcpyAsync(sums, d_su.p, sizeof(int) * num_candidates, cudaMemcpyDeviceToHost,
+                             s));
+  CSM_CUDA(cudaStreamSynchronize(s));
+  return CSM_OK;
+}
+
+}  // extern "C"

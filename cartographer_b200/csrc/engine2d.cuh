@@ -1,0 +1,84 @@
+// Device-side records of the 2D fast correlative scan matcher.
+#ifndef CSM_ENGINE2D_CUH_
+#define CSM_ENGINE2D_CUH_
+
+#include "common.cuh"
+
+namespace csm {
+
+constexpr int kMaxDepth = 12;
+
+// PrecomputationGridStack2D on the device.  Level h has width w = 2^h, wide
+// limits (nx + w - 1, ny + w - 1), offset (-w+1, -w+1) and is stored row-major
+// (x + y * wx), exactly the reference's PrecomputationGrid2D::cells_
+// (fast_correlative_scan_matcher_2d.h:56-71).
+struct StackDev {
+  const uint8_t* level[kMaxDepth];
+  // Decimated ("phase-major") copy of every level for the dense top pass:
+  //   dec[h][((ay * s + ax) * jd + J) * id_stride + I] = level[h][(s*J + ay) * wx + s*I + ax]
+  // with s = 2^h, zero where the source index falls outside the wide grid.
+  const uint8_t* dec[kMaxDepth];
+  int wx[kMaxDepth], wy[kMaxDepth];
+  int id[kMaxDepth], jd[kMaxDepth], id_stride[kMaxDepth];
+  int nx, ny, depth;
+  double resolution, max_x, max_y;
+  float min_score, max_score, k255;  // k255 = (max_score - min_score) / 255.f
+};
+
+struct JobDev {
+  const StackDev* stack;
+  const float* xyz;      // cloud, n x 3
+  const float2* trig;    // per scan: (cos(ha), sin(ha)) of the rotation quaternion
+  int n;
+  int num_scans;
+  int scan_base;         // global index of this job's scan 0
+  int lin;               // num_linear_perturbations (pre-shrink window)
+  int cap;               // top-level slots reserved per scan
+  int cap_y;             // max candidates along y (slot = i * nyc + j uses the scan's own nyc)
+  float q0w, q0x, q0y, q0z;  // initial rotation as Quaternionf(AngleAxisf(yaw, UnitZ))
+  float tx, ty;          // initial translation (float casts)
+  float min_score;
+  long long dscan_off;   // first int2 of this job in the discrete-scan buffer
+  long long top_off;     // first slot of this job in the top-level sum buffer
+};
+
+struct ScanInfo {
+  int job;
+  int min_x, max_x, min_y, max_y;  // LinearBounds after ShrinkToFit
+  int nxc, nyc;                    // lowest-resolution candidates per axis
+  int pad;
+};
+
+struct Node {  // 16 B
+  int scan;    // global scan index
+  int xo, yo;  // x/y_index_offset
+  float score;
+};
+
+// Launches K2 (rotate + discretise + optional ShrinkToFit) for `total_scans`
+// scans on `stream`; defined in engine2d.cu, shared with the real-time matcher.
+csm_status LaunchDiscretize2D(cudaStream_t stream, const JobDev* jobs, const int* scan_job,
+                              int total_scans, int2* dscan, ScanInfo* info, int shrink,
+                              unsigned long long* counters);
+
+}  // namespace csm
+
+struct csm_stack2d {
+  csm::Ctx* ctx = nullptr;
+  csm::StackDev h;             // host copy of the descriptor (device pointers inside)
+  csm::StackDev* d = nullptr;  // device copy
+  uint8_t* d_levels = nullptr;
+  uint8_t* d_dec = nullptr;
+  size_t level_off[csm::kMaxDepth];
+  float min_cost = 0.f, max_cost = 0.f;
+};
+
+struct csm_cloud {
+  csm::Ctx* ctx = nullptr;
+  int n = 0;
+  float* d_xyz = nullptr;
+  float max_norm = 0.f;  // max_i sqrt(x*x + y*y) in float (correlative_scan_matcher_2d.cc:35-38)
+  std::vector<float> h_xyz;
+};
+
+#endif  // CSM_ENGINE2D_CUH_

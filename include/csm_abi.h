@@ -1,0 +1,180 @@
+/* csm_abi.h — C ABI of the B200 correlative scan-matching engine (libcsm_b200.so).
+ *
+ * This is the drop-in boundary: the entry points a maintainer of
+ * cartographer-project/cartographer binds behind the existing C++ classes
+ *   cartographer::mapping::scan_matching::FastCorrelativeScanMatcher2D
+ *   cartographer::mapping::scan_matching::RealTimeCorrelativeScanMatcher2D
+ *   cartographer::mapping::scan_matching::FastCorrelativeScanMatcher3D
+ *   cartographer::mapping::constraints::ConstraintBuilder2D / 3D
+ * (see INTEGRATION.md for the adapter code).  Plain pointers and sizes only;
+ * no C++ / torch / CUDA types cross the boundary.
+ *
+ * Conventions
+ *  - every function returns a csm_status (0 == CSM_OK); nothing aborts or
+ *    throws across the ABI (the reference CHECK-aborts on programmer errors,
+ *    e.g. fast_correlative_scan_matcher_2d.cc:232-233; here they become
+ *    CSM_E_INVALID);  csm_last_error_string() describes the last failure of
+ *    the calling thread.
+ *  - "no pose above min_score" is NOT an error: *found == 0 and the outputs
+ *    are left untouched (fast_correlative_scan_matcher_2d.cc:253-261).
+ *  - opaque handles own device memory; the caller owns every host buffer and
+ *    may free it as soon as the call returns.
+ *  - all entry points are thread-safe (per-device serialisation inside);
+ *    Match* may be called concurrently on one stack, as the reference's pool
+ *    threads do (constraints/constraint_builder_2d.cc:102-111).
+ *  - there is no CPU fallback: without a usable CUDA device every call
+ *    returns CSM_E_CUDA.
+ *
+ * File:line citations are relative to /root/reference/cartographer/ .
+ */
+#ifndef CSM_ABI_H_
+#define CSM_ABI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t csm_status;
+enum {
+  CSM_OK = 0,
+  CSM_E_INVALID = 1,      /* bad argument (reference: glog CHECK) */
+  CSM_E_CUDA = 2,         /* CUDA runtime / no device */
+  CSM_E_CAPACITY = 3,     /* internal capacity exceeded (e.g. > 2^20 exactly tied optima) */
+  CSM_E_INTERNAL = 4
+};
+
+/* Per-call counters.  `candidates_scored` counts one per candidate whose score
+ * the engine computed (all levels) — the unit of BASELINE.json's metric. */
+typedef struct csm_stats {
+  int64_t candidates_scored;
+  int64_t lowest_resolution_candidates; /* == reference's top-level list size */
+  int64_t nodes_expanded;               /* B&B parents whose children were scored */
+  int64_t leaves_tied;                  /* leaves sharing the best score (1 == unique) */
+  int32_t num_scans;                    /* SearchParameters::num_scans */
+  int32_t best_scan_index;              /* winning Candidate2D identity (integers) */
+  int32_t best_x_offset;
+  int32_t best_y_offset;
+  int32_t host_tie_resolves;            /* top-level std::sort replays */
+  int32_t reserved;
+  float device_ms;                      /* CUDA-event time of the device work of this call */
+  float reserved_f;
+} csm_stats;
+
+/* ---- device / context ---------------------------------------------------- */
+csm_status csm_device_count(int32_t* count);
+const char* csm_last_error_string(void);
+/* Number of kernel launches issued by this process so far (bench `gpu_launches`). */
+int64_t csm_kernel_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline block: CUDA events on the
+ * engine's stream around every kernel launch (adds a sync per launch; off by
+ * default).  csm_profile_read writes "<kernel> <launches> <total_ms> <units>"
+ * lines, units = scored candidates (or cells) the launches processed. */
+csm_status csm_profile_enable(int32_t on);
+csm_status csm_profile_read(char* buf, int32_t capacity);
+
+/* ---- 2D precomputation grid stack ---------------------------------------- */
+/* Replaces FastCorrelativeScanMatcher2D's ctor
+ * (internal/2d/scan_matching/fast_correlative_scan_matcher_2d.cc:188-194), i.e.
+ * PrecomputationGridStack2D (:171-186) over a Grid2D.  `cells` is
+ * Grid2D::correspondence_cost_cells() (uint16, flat index num_x*y + x,
+ * 2d/grid_2d.h:113-116); min/max_cost are Grid2D::Get{Min,Max}CorrespondenceCost().
+ * Like the reference ctor it copies what it needs; `cells` is not retained. */
+typedef struct csm_stack2d csm_stack2d;
+csm_status csm_stack2d_create(const uint16_t* cells, int32_t num_x_cells, int32_t num_y_cells,
+                              double resolution, double max_x, double max_y,
+                              float min_correspondence_cost, float max_correspondence_cost,
+                              int32_t branch_and_bound_depth, int32_t device,
+                              csm_stack2d** out);
+csm_status csm_stack2d_destroy(csm_stack2d* stack);
+/* Test hook: PrecomputationGrid2D::cells_ of one level, row-major
+ * (x + y * wide_num_x), fast_correlative_scan_matcher_2d.h:56-71,92.
+ * `out` may be NULL to query the dimensions only. */
+csm_status csm_stack2d_read_level(const csm_stack2d* stack, int32_t level, uint8_t* out,
+                                  int32_t* wide_num_x, int32_t* wide_num_y);
+
+/* ---- device-resident scan (sensor::PointCloud) --------------------------- */
+/* A PointCloud (sensor/point_cloud.h:33-92: N x {x,y,z} float32) copied to the
+ * device once so that many matches can borrow it (ConstraintBuilder matches one
+ * node scan against many submaps). */
+typedef struct csm_cloud csm_cloud;
+csm_status csm_cloud_create(const float* xyz, int32_t num_points, int32_t device,
+                            csm_cloud** out);
+csm_status csm_cloud_destroy(csm_cloud* cloud);
+
+/* ---- FastCorrelativeScanMatcher2D::Match / MatchFullSubmap ---------------- */
+/* fast_correlative_scan_matcher_2d.cc:198-262.  full_submap != 0 ignores
+ * initial_pose and the two windows (MatchFullSubmap, :210-225).
+ * initial_pose / pose_estimate = {x, y, yaw} of a transform::Rigid2d. */
+csm_status csm_match2d(const csm_stack2d* stack, const float* xyz, int32_t num_points,
+                       const double initial_pose[3], int32_t full_submap,
+                       double linear_search_window, double angular_search_window,
+                       float min_score, int32_t* found, float* score,
+                       double pose_estimate[3], csm_stats* stats /* may be NULL */);
+
+/* One (submap, node) search of ConstraintBuilder2D::ComputeConstraint
+ * (constraints/constraint_builder_2d.cc:188-277, the part before Ceres). */
+typedef struct csm_job2d {
+  int32_t stack_index;   /* into stacks[] */
+  int32_t cloud_index;   /* into clouds[] */
+  int32_t full_submap;   /* MaybeAddGlobalConstraint (:114-137) vs MaybeAddConstraint */
+  int32_t reserved;
+  double initial_pose[3];
+  float min_score;       /* options.min_score() / global_localization_min_score() */
+  float reserved_f;
+} csm_job2d;
+
+typedef struct csm_result2d {
+  int32_t found;
+  float score;
+  double pose_estimate[3];
+  int32_t best_scan_index, best_x_offset, best_y_offset;
+  int32_t leaves_tied;
+} csm_result2d;
+
+/* Batched form: every job is an independent FastCorrelativeScanMatcher2D match;
+ * all stacks and clouds must live on the same device.  Results are written in
+ * job order.  This is the entry ConstraintBuilder2D's queue drains into. */
+csm_status csm_match2d_batch(const csm_stack2d* const* stacks, int32_t num_stacks,
+                             const csm_cloud* const* clouds, int32_t num_clouds,
+                             const csm_job2d* jobs, int32_t num_jobs,
+                             double linear_search_window, double angular_search_window,
+                             csm_result2d* results, csm_stats* total /* may be NULL */);
+
+/* ---- test hooks ("visible for testing" in the reference) ------------------ */
+/* FastCorrelativeScanMatcher2D::ScoreCandidates (fast...2d.cc:314-333) without
+ * the sort: candidates are {scan_index, x_index_offset, y_index_offset} triples,
+ * discrete_scans is num_scans x num_points x {x, y} int32 (DiscreteScan2D,
+ * correlative_scan_matcher_2d.h:32).  sums may be NULL. */
+csm_status csm_score_candidates2d(const csm_stack2d* stack, int32_t level,
+                                  const int32_t* discrete_scans, int32_t num_scans,
+                                  int32_t num_points, const int32_t* candidates,
+                                  int32_t num_candidates, float* scores, int32_t* sums);
+/* GenerateRotatedScans + DiscretizeScans + ShrinkToFit exactly as
+ * MatchWithSearchParameters runs them (fast...2d.cc:236-247).  Call with
+ * discrete_scans == NULL to get *num_scans first.  bounds is num_scans x
+ * {min_x, max_x, min_y, max_y} (SearchParameters::LinearBounds). */
+csm_status csm_discretize2d(const csm_stack2d* stack, const float* xyz, int32_t num_points,
+                            const double initial_pose[3], int32_t full_submap,
+                            double linear_search_window, double angular_search_window,
+                            int32_t* num_scans, int32_t* discrete_scans, int32_t* bounds);
+
+/* ---- RealTimeCorrelativeScanMatcher2D::Match ------------------------------ */
+/* real_time_correlative_scan_matcher_2d.cc:117-149 on a ProbabilityGrid (the
+ * grid is passed per call, as in the reference signature).  Returns the best
+ * score (the reference's return value) in *score. */
+csm_status csm_rt_match2d(const uint16_t* cells, int32_t num_x_cells, int32_t num_y_cells,
+                          double resolution, double max_x, double max_y, const float* xyz,
+                          int32_t num_points, const double initial_pose[3],
+                          double linear_search_window, double angular_search_window,
+                          double translation_delta_cost_weight,
+                          double rotation_delta_cost_weight, int32_t device, double* score,
+                          double pose_estimate[3], csm_stats* stats /* may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CSM_ABI_H_ */

@@ -10,6 +10,10 @@
 
 namespace oracle {
 
+// oracle-only instrumentation; thread-local so that one matcher can be shared by
+// the CPU-baseline worker threads like the reference's pool threads share theirs.
+static thread_local MatchStats* stats_ = nullptr;
+
 ProbabilityGrid::ProbabilityGrid(const MapLimits& l, float min_cost, float max_cost)
     : limits(l),
       min_correspondence_cost(min_cost),

@@ -214,7 +214,6 @@ class FastCorrelativeScanMatcher2D {  // fast...2d.h:112-164, .cc:188-378
   const FastOptions2D options_;
   MapLimits limits_;
   std::unique_ptr<PrecomputationGridStack2D> stack_;
-  mutable MatchStats* stats_ = nullptr;  // oracle-only instrumentation
 };
 
 struct RealTimeOptions {  // proto/scan_matching/real_time_correlative_scan_matcher_options.proto

@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and
+exports every symbol include/csm_abi.h declares; struct layouts match; argument
+validation returns status codes (never aborts).  No compute calls (no GPU here).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def csm():
+    from cartographer_b200 import _lib
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    return _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "csm_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(csm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(csm):
+    lib = csm.lib()
+    names = _declared_symbols()
+    assert len(names) >= 13
+    for n in names:
+        assert hasattr(lib, n), "libcsm_b200.so does not export %s" % n
+
+
+def test_struct_layouts(csm):
+    assert C.sizeof(csm.CsmStats) == 64
+    assert C.sizeof(csm.CsmJob2D) == 48
+    assert C.sizeof(csm.CsmResult2D) == 48
+    assert csm.JOB2D_DTYPE.itemsize == 48 and csm.RESULT2D_DTYPE.itemsize == 48
+
+
+def test_invalid_arguments_return_status(csm):
+    lib = csm.lib()
+    out = C.c_void_p()
+    cells = np.zeros((4, 4), np.uint16)
+    # depth 0 is a CHECK failure in the reference (fast...2d.cc:174); here a status code
+    st = lib.csm_stack2d_create(cells.ctypes.data_as(C.POINTER(C.c_uint16)), 4, 4,
+                                C.c_double(0.05), C.c_double(0.1), C.c_double(0.1),
+                                C.c_float(0.1), C.c_float(0.9), 0, 0, C.byref(out))
+    assert st == 1
+    assert b"branch_and_bound_depth" in lib.csm_last_error_string()
+    st = lib.csm_stack2d_create(None, 4, 4, C.c_double(0.05), C.c_double(0.1), C.c_double(0.1),
+                                C.c_float(0.1), C.c_float(0.9), 3, 0, C.byref(out))
+    assert st == 1
+
+
+def test_no_cpu_fallback_without_gpu(csm):
+    """Without a CUDA device the product path must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = csm.lib()
+    out = C.c_void_p()
+    cells = np.zeros((4, 4), np.uint16)
+    st = lib.csm_stack2d_create(cells.ctypes.data_as(C.POINTER(C.c_uint16)), 4, 4,
+                                C.c_double(0.05), C.c_double(0.1), C.c_double(0.1),
+                                C.c_float(0.1), C.c_float(0.9), 3, 0, C.byref(out))
+    assert st == 2, "expected CSM_E_CUDA"
+    from cartographer_b200 import scan_matching as sm
+    from cartographer_b200 import synthetic
+    grid = synthetic.GridSpec(cells, 0.05, 0.1, 0.1)
+    with pytest.raises(csm.CsmError):
+        sm.FastCorrelativeScanMatcher2D(grid, sm.FastCorrelativeScanMatcherOptions2D(1.0, 0.5, 3))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under cartographer_b200/ may touch it."""
+    pkg = os.path.join(ROOT, "cartographer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "pyoracle" not in text and "liboracle" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
