@@ -90,23 +90,30 @@ __global__ void k_stack_double(const uint8_t* __restrict__ prev, int pwx, int pw
   out[static_cast<size_t>(y) * wx + x] = static_cast<uint8_t>(v);
 }
 
-// Decimated copy of one level (see StackDev::dec).
-__global__ void k_stack_decimate(const uint8_t* __restrict__ lvl, int wx, int wy, int h,
-                                 uint8_t* __restrict__ dec, int id, int jd, int id_stride) {
+// Four byte-shifted copies of the decimated lowest-resolution level
+// (see StackDev::dec4).
+__global__ void k_stack_decimate4(const uint8_t* __restrict__ lvl, int wx, int wy, int h,
+                                  uint8_t* __restrict__ dec4, int lpad, int id, int jd,
+                                  int ids) {
   const int s = 1 << h;
-  const size_t total = static_cast<size_t>(s) * s * jd * id_stride;
-  for (size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; t < total;
-       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    int I = t % id_stride;
-    size_t r = t / id_stride;
-    int J = r % jd;
-    r /= jd;
-    int ax = r % s;
-    int ay = r / s;
-    int x = s * I + ax, y = s * J + ay;
+  const long long total = static_cast<long long>(s) * s * jd * ids;
+  const long long n = 4LL * lpad;
+  for (long long u = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; u < n;
+       u += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(u / lpad);
+    const long long t = u % lpad - 16 + k;  // index into D
     uint8_t v = 0;
-    if (I < id && x < wx && y < wy) v = lvl[static_cast<size_t>(y) * wx + x];
-    dec[t] = v;
+    if (t >= 0 && t < total) {
+      const int I = static_cast<int>(t % ids);
+      long long r = t / ids;
+      const int J = static_cast<int>(r % jd);
+      r /= jd;
+      const int ax = static_cast<int>(r % s);
+      const int ay = static_cast<int>(r / s);
+      const int x = s * I + ax, y = s * J + ay;
+      if (I < id && x < wx && y < wy) v = lvl[static_cast<size_t>(y) * wx + x];
+    }
+    dec4[u] = v;
   }
 }
 
@@ -273,82 +280,102 @@ k_score_top_gather(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__
   if (lane == 0) top_sum[scan_slot_base[sg] + slot] = sum;
 }
 
-// Lowest-resolution pass, dense form: one CTA per (scan, tile of candidates).
-// Thread t owns candidates (i, j0..) of the scan's lattice; for a point p the
-// cells touched by all candidates of the lattice are one contiguous block of the
-// decimated level (StackDev::dec), so consecutive lanes read consecutive bytes.
-// Point descriptors are staged in shared memory once per chunk and broadcast.
-constexpr int kDenseThreads = 256;
-constexpr int kDenseCandPerThread = 8;
-constexpr int kDenseChunk = 256;
+// Lowest-resolution pass, dense form: one CTA per scan.  The candidates of one
+// rotated scan form a lattice of stride s = 2^h, so for a scan point p the cells
+// they read are one contiguous block of the decimated level (StackDev::dec4).
+// A thread owns kQuads "quads" = 4 x-consecutive candidates of one lattice row
+// and fetches their 4 cells with ONE aligned 32-bit load from the byte-shifted
+// copy that matches the address' alignment; the four byte lanes are accumulated
+// SIMD-in-register (2 x u16 per register, flushed every 256 points).  Point
+// descriptors (tile base + lattice origin) are computed once per CTA into shared
+// memory and broadcast to all threads.
+constexpr int kDenseThreads = 128;
+constexpr int kDenseChunk = 256;  // <= 257 so the packed u16 sums cannot overflow
+template <int kQuads>
 __global__ void __launch_bounds__(kDenseThreads)
 k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
                   const int2* __restrict__ dscan, int* __restrict__ top_sum,
                   const long long* __restrict__ scan_slot_base, int total_scans) {
-  __shared__ int s_base[kDenseChunk];   // tile base + qy * id_stride + qx
-  __shared__ short2 s_q[kDenseChunk];   // (qx, qy)
+  __shared__ int4 s_pt[kDenseChunk];  // {D index of lattice origin, qx, qy, 0}
   for (int sg = blockIdx.x; sg < total_scans; sg += gridDim.x) {
     const ScanInfo si = info[sg];
     const JobDev& jb = jobs[si.job];
     const StackDev& st = *jb.stack;
     const int h = st.depth - 1;
     const int s = 1 << h;
-    const int id = st.id[h], jd = st.jd[h], ids = st.id_stride[h];
-    const uint8_t* __restrict__ dec = st.dec[h];
-    const int slots = si.nxc * si.nyc;
+    const int id = st.dec_id, jd = st.dec_jd, ids = st.dec_ids;
+    const unsigned lpad1 = static_cast<unsigned>(st.dec_lpad) - 1u;
+    const uint8_t* __restrict__ dec = st.dec4 + 16;
+    const int qr = (si.nxc + 3) >> 2;       // quads per lattice row
+    const int quads = qr * si.nyc;
     const int2* __restrict__ pts = dscan + jb.dscan_off +
                                    static_cast<long long>(sg - jb.scan_base) * jb.n;
-    for (int tile0 = 0; tile0 < slots; tile0 += kDenseThreads * kDenseCandPerThread) {
-      // candidate c = tile0 + threadIdx.x + r * kDenseThreads, laid out j-fastest
-      // in slot order; for coalescing we want i-fastest across lanes, so map
-      // lattice index q = c -> (jy = q / nxc, i = q % nxc) and store to slot i*nyc+jy.
-      int acc[kDenseCandPerThread];
-      int ci[kDenseCandPerThread], cj[kDenseCandPerThread];
+    int* __restrict__ out = top_sum + scan_slot_base[sg];
+    for (int u0 = 0; u0 < quads; u0 += kDenseThreads * kQuads) {
+      int jy[kQuads], i0[kQuads], toff[kQuads];
+      unsigned sum[kQuads][4];
 #pragma unroll
-      for (int r = 0; r < kDenseCandPerThread; ++r) {
-        acc[r] = 0;
-        const int q = tile0 + threadIdx.x + r * kDenseThreads;
-        cj[r] = q / si.nxc;
-        ci[r] = q - cj[r] * si.nxc;
-        if (q >= slots) { ci[r] = -(1 << 20); cj[r] = -(1 << 20); }
+      for (int r = 0; r < kQuads; ++r) {
+        const int u = u0 + threadIdx.x + r * kDenseThreads;
+        jy[r] = u / qr;
+        i0[r] = (u - jy[r] * qr) << 2;
+        if (u >= quads) jy[r] = 1 << 20;    // never in range
+        toff[r] = jy[r] * ids + i0[r];
+        sum[r][0] = sum[r][1] = sum[r][2] = sum[r][3] = 0u;
       }
       for (int p0 = 0; p0 < jb.n; p0 += kDenseChunk) {
         __syncthreads();
         for (int t = threadIdx.x; t < kDenseChunk; t += kDenseThreads) {
           const int p = p0 + t;
-          int base = 0;
-          short2 q = make_short2(-30000, -30000);
+          int4 d = make_int4(0, -(1 << 24), -(1 << 24), 0);
           if (p < jb.n) {
             const int2 c = pts[p];
             const int bx = c.x + si.min_x + s - 1, by = c.y + si.min_y + s - 1;
-            const int qx = bx >> h, qy = by >> h;            // floor division
+            const int qx = bx >> h, qy = by >> h;          // floor division
             const int ax = bx & (s - 1), ay = by & (s - 1);
-            if (qx > -30000 && qx < 30000 && qy > -30000 && qy < 30000) {
-              base = ((ay * s + ax) * jd) * ids;
-              q = make_short2(static_cast<short>(qx), static_cast<short>(qy));
-            }
+            if (qx > -(1 << 20) && qx < (1 << 20) && qy > -(1 << 20) && qy < (1 << 20))
+              d = make_int4(((ay * s + ax) * jd + qy) * ids + qx, qx, qy, 0);
           }
-          s_base[t] = base;
-          s_q[t] = q;
+          s_pt[t] = d;
         }
         __syncthreads();
         const int cnt = min(kDenseChunk, jb.n - p0);
-        for (int t = 0; t < cnt; ++t) {
-          const int base = s_base[t];
-          const short2 q = s_q[t];
+        unsigned a02[kQuads], a13[kQuads];
 #pragma unroll
-          for (int r = 0; r < kDenseCandPerThread; ++r) {
-            const int I = q.x + ci[r], J = q.y + cj[r];
-            if (static_cast<unsigned>(I) < static_cast<unsigned>(id) &&
-                static_cast<unsigned>(J) < static_cast<unsigned>(jd))
-              acc[r] += __ldg(dec + base + J * ids + I);
+        for (int r = 0; r < kQuads; ++r) a02[r] = a13[r] = 0u;
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+          const int4 d = s_pt[t];
+#pragma unroll
+          for (int r = 0; r < kQuads; ++r) {
+            const int J = d.z + jy[r];
+            const int c3 = d.y + i0[r] + 3;   // column of the quad's last byte
+            if (static_cast<unsigned>(J) < static_cast<unsigned>(jd) &&
+                static_cast<unsigned>(c3) < static_cast<unsigned>(id + 3)) {
+              const int a = d.x + toff[r];    // D index of the quad's first byte (>= -3)
+              const unsigned k = static_cast<unsigned>(a) & 3u;
+              const unsigned w = __ldg(reinterpret_cast<const unsigned*>(
+                  dec + static_cast<long long>(a) + static_cast<long long>(k * lpad1)));
+              a02[r] += __byte_perm(w, 0u, 0x4240);  // bytes 0 and 2 in u16 lanes
+              a13[r] += __byte_perm(w, 0u, 0x4341);  // bytes 1 and 3
+            }
           }
+        }
+#pragma unroll
+        for (int r = 0; r < kQuads; ++r) {
+          sum[r][0] += a02[r] & 0xffffu;
+          sum[r][2] += a02[r] >> 16;
+          sum[r][1] += a13[r] & 0xffffu;
+          sum[r][3] += a13[r] >> 16;
         }
       }
 #pragma unroll
-      for (int r = 0; r < kDenseCandPerThread; ++r) {
-        const int q = tile0 + threadIdx.x + r * kDenseThreads;
-        if (q < slots) top_sum[scan_slot_base[sg] + ci[r] * si.nyc + cj[r]] = acc[r];
+      for (int r = 0; r < kQuads; ++r) {
+        if (jy[r] < si.nyc) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (i0[r] + e < si.nxc) out[(i0[r] + e) * si.nyc + jy[r]] = static_cast<int>(sum[r][e]);
+        }
       }
     }
   }
@@ -668,17 +695,18 @@ csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, dou
   }
   CSM_CUDA(cudaMalloc(&st->d_levels, total));
   for (int l = 0; l < depth; ++l) h.level[l] = st->d_levels + st->level_off[l];
-  // decimated copy of the top level only (the dense lowest-resolution pass)
+  // decimated, 4x byte-shifted copy of the top level (the dense lowest-resolution pass)
   const int top = depth - 1;
   {
     const int s = 1 << top;
-    h.id[top] = (h.wx[top] + s - 1) / s;
-    h.jd[top] = (h.wy[top] + s - 1) / s;
-    h.id_stride[top] = (h.id[top] + 3) / 4 * 4 + 4;
-    const size_t bytes = static_cast<size_t>(s) * s * h.jd[top] * h.id_stride[top];
-    CSM_CUDA(cudaMalloc(&st->d_dec, bytes + 32));
-    CSM_CUDA(cudaMemsetAsync(st->d_dec, 0, bytes + 32, ctx->stream));
-    h.dec[top] = st->d_dec + 16;
+    h.dec_id = (h.wx[top] + s - 1) / s;
+    h.dec_jd = (h.wy[top] + s - 1) / s;
+    h.dec_ids = (h.dec_id + 3) / 4 * 4 + 4;
+    const long long bytes = static_cast<long long>(s) * s * h.dec_jd * h.dec_ids;
+    CSM_REQUIRE(bytes < (1LL << 29), "decimated level too large");
+    h.dec_lpad = static_cast<int>((bytes + 32 + 15) / 16 * 16);
+    CSM_CUDA(cudaMalloc(&st->d_dec, 4 * static_cast<size_t>(h.dec_lpad)));
+    h.dec4 = st->d_dec;
   }
   // upload cells + LUT into scratch
   DevBuf& d_cells = ctx->D("stack_cells");
@@ -701,9 +729,9 @@ csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, dou
                                                     h.wy[l], 1 << (l - 1));
     CSM_LAUNCH_CHECK();
   }
-  k_stack_decimate<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-      h.level[top], h.wx[top], h.wy[top], top, st->d_dec + 16, h.id[top], h.jd[top],
-      h.id_stride[top]);
+  k_stack_decimate4<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+      h.level[top], h.wx[top], h.wy[top], top, st->d_dec, h.dec_lpad, h.dec_id, h.dec_jd,
+      h.dec_ids);
   CSM_LAUNCH_CHECK();
   CSM_CUDA(cudaMalloc(&st->d, sizeof(StackDev)));
   CSM_CUDA(cudaMemcpyAsync(st->d, &h, sizeof(StackDev), cudaMemcpyHostToDevice, ctx->stream));
@@ -1001,8 +1029,12 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   // Wide lattices (MatchFullSubmap) take the dense decimated-grid kernel; narrow
   // ones (local windows: a few dozen candidates per scan) the gather kernel.
   static const char* force = getenv("CSM_TOP_KERNEL");  // "gather" | "dense" (debug)
-  int max_cap = 0;
-  for (const JobDev& d : plan.jobs) max_cap = std::max(max_cap, d.cap);
+  int max_cap = 0, max_cap_x = 0, max_cap_y = 0;
+  for (const JobDev& d : plan.jobs) {
+    max_cap = std::max(max_cap, d.cap);
+    max_cap_y = std::max(max_cap_y, d.cap_y);
+    max_cap_x = std::max(max_cap_x, d.cap / std::max(1, d.cap_y));
+  }
   bool use_gather_top = max_cap < 128;
   if (force && !strcmp(force, "gather")) use_gather_top = true;
   if (force && !strcmp(force, "dense")) use_gather_top = false;
@@ -1012,9 +1044,16 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
         d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),
         d_slot_base.as<long long>(), total_scans, plan.total_slots);
   } else {
-    k_score_top_dense<<<std::min(total_scans, ctx->sm_count * 64), kDenseThreads, 0, s>>>(
-        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),
-        d_slot_base.as<long long>(), total_scans);
+    const int max_quads = (max_cap_x + 3) / 4 * max_cap_y;
+    const int grid = std::min(total_scans, ctx->sm_count * 128);
+#define CSM_DENSE(Q)                                                                       \
+    k_score_top_dense<Q><<<grid, kDenseThreads, 0, s>>>(                                   \
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),   \
+        d_slot_base.as<long long>(), total_scans)
+    if (max_quads <= kDenseThreads) CSM_DENSE(1);
+    else if (max_quads <= 2 * kDenseThreads) CSM_DENSE(2);
+    else CSM_DENSE(4);
+#undef CSM_DENSE
   }
   CSM_LAUNCH_CHECK();
   if (g_profile_on.load()) {

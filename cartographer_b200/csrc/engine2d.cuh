@@ -14,12 +14,18 @@ constexpr int kMaxDepth = 12;
 // (fast_correlative_scan_matcher_2d.h:56-71).
 struct StackDev {
   const uint8_t* level[kMaxDepth];
-  // Decimated ("phase-major") copy of every level for the dense top pass:
-  //   dec[h][((ay * s + ax) * jd + J) * id_stride + I] = level[h][(s*J + ay) * wx + s*I + ax]
-  // with s = 2^h, zero where the source index falls outside the wide grid.
-  const uint8_t* dec[kMaxDepth];
+  // Decimated ("phase-major") layout of the lowest-resolution level h = depth-1
+  // for the dense top pass.  With s = 2^h the flat array
+  //   D[((ay * s + ax) * jd + J) * ids + I] = level[h][(s*J + ay) * wx + s*I + ax]
+  // (zero outside the wide grid; every row is followed by >= 4 zero bytes) puts
+  // the cells that the candidates of one scan lattice need for one scan point
+  // into consecutive bytes.  dec4 holds FOUR copies of D, copy k shifted left by
+  // k bytes (copy_k[t] = D[t + k]), each dec_lpad bytes long with index 0 at byte
+  // 16, so that any 4 consecutive bytes of D can be fetched with one aligned
+  // 32-bit load: word(a) = *(u32*)(dec4 + (a & 3) * dec_lpad + 16 + (a & ~3)).
+  const uint8_t* dec4;
+  int dec_lpad, dec_id, dec_jd, dec_ids;
   int wx[kMaxDepth], wy[kMaxDepth];
-  int id[kMaxDepth], jd[kMaxDepth], id_stride[kMaxDepth];
   int nx, ny, depth;
   double resolution, max_x, max_y;
   float min_score, max_score, k255;  // k255 = (max_score - min_score) / 255.f
