@@ -1,0 +1,306 @@
+"""Host-side mirror of cartographer::mapping::constraints::ConstraintBuilder2D
+(cartographer/mapping/internal/constraints/constraint_builder_2d.{h,cc}) for the
+fast-correlative-scan-matching part of the queue.
+
+Same public surface and gating as the reference —
+  MaybeAddConstraint / MaybeAddGlobalConstraint / NotifyEndOfNode / WhenDone /
+  GetNumFinishedNodes / DeleteScanMatcher
+— but instead of one thread-pool task per (submap, node) pair the queued pairs are
+drained as ONE batched device call (csm_match2d_batch) when WhenDone is invoked.
+With torch.distributed initialised the queue is sharded submap-major across ranks
+(rank r owns the submaps whose first-use order index % world == r; stacks are
+only built on their owner) and the fixed-size constraint records are exchanged
+with a single all_gather; every rank then reports the same Result in queue order.
+
+Constraints are pinned PRE-Ceres: `pose` is ComputeSubmapPose(submap)^-1 *
+pose_estimate of the fast matcher (constraint_builder_2d.cc:251-258 without the
+CeresScanMatcher2D refinement at :245-249, which is third-party and out of scope,
+SURVEY.md §8c/§8f).
+"""
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+RECORD_DTYPE = np.dtype([("submap_trajectory", "<i4"), ("submap_index", "<i4"),
+                         ("node_trajectory", "<i4"), ("node_index", "<i4"),
+                         ("found", "<u4"), ("score", "<f4"), ("pose", "<f8", (3,)),
+                         ("pad", "<u4", (4,))], align=True)
+assert RECORD_DTYPE.itemsize == 64
+
+
+@dataclass
+class ConstraintBuilderOptions:
+    """constraints/proto/constraint_builder_options.proto (the fields on the path);
+    defaults from configuration_files/pose_graph.lua:18-36."""
+    sampling_ratio: float = 0.3
+    max_constraint_distance: float = 15.0
+    min_score: float = 0.55
+    global_localization_min_score: float = 0.6
+    loop_closure_translation_weight: float = 1.1e4
+    loop_closure_rotation_weight: float = 1e5
+    linear_search_window: float = 7.0
+    angular_search_window: float = math.radians(30.0)
+    branch_and_bound_depth: int = 7
+
+
+@dataclass
+class Submap2D:
+    """What the builder needs of a Submap2D: its grid and local pose (x, y, yaw)."""
+    grid: object
+    local_pose: tuple = (0.0, 0.0, 0.0)
+
+
+@dataclass
+class Constraint:
+    """PoseGraphInterface::Constraint (mapping/pose_graph_interface.h:36-53)."""
+    submap_id: tuple
+    node_id: tuple
+    zbar_ij: tuple            # (x, y, yaw) of submap i <- node j
+    translation_weight: float
+    rotation_weight: float
+    tag: str = "INTER_SUBMAP"
+    score: float = 0.0
+
+
+class FixedRatioSampler:
+    """common/fixed_ratio_sampler.cc:23-39."""
+
+    def __init__(self, ratio):
+        if not 0.0 <= ratio <= 1.0:
+            raise ValueError("ratio must be in [0, 1]")
+        self.ratio = ratio
+        self.num_pulses = 0
+        self.num_samples = 0
+
+    def Pulse(self):
+        self.num_pulses += 1
+        if self.num_samples / self.num_pulses < self.ratio:
+            self.num_samples += 1
+            return True
+        return False
+
+
+def _compose(a, b):
+    """transform::Rigid2d operator* (transform/rigid_transform.h:93-99)."""
+    c, s = math.cos(a[2]), math.sin(a[2])
+    return (c * b[0] - s * b[1] + a[0], s * b[0] + c * b[1] + a[1], a[2] + b[2])
+
+
+def _inverse(a):
+    """Rigid2::inverse (transform/rigid_transform.h:76-80)."""
+    c, s = math.cos(-a[2]), math.sin(-a[2])
+    return (-(c * a[0] - s * a[1]), -(s * a[0] + c * a[1]), -a[2])
+
+
+@dataclass
+class _Job:
+    submap_id: tuple
+    node_id: tuple
+    cloud_key: int
+    initial_pose: tuple
+    full: bool
+    min_score: float
+
+
+class CudaExecutor:
+    """Drains a list of jobs through csm_match2d_batch on one device.  Keeps one
+    device stack per submap (DispatchScanMatcherConstruction,
+    constraint_builder_2d.cc:165-186) and one device cloud per node scan."""
+
+    def __init__(self, options, device=0):
+        from . import scan_matching as sm
+        self.sm = sm
+        self.options = options
+        self.device = device
+        self.matchers = {}
+        self.clouds = {}
+        self.stats = {"candidates_scored": 0, "device_ms": 0.0, "searched": 0}
+
+    def ensure_matcher(self, submap_id, grid):
+        if submap_id not in self.matchers:
+            o = self.options
+            self.matchers[submap_id] = self.sm.FastCorrelativeScanMatcher2D(
+                grid, self.sm.FastCorrelativeScanMatcherOptions2D(
+                    o.linear_search_window, o.angular_search_window, o.branch_and_bound_depth),
+                device=self.device)
+
+    def delete_matcher(self, submap_id):
+        m = self.matchers.pop(submap_id, None)
+        if m is not None:
+            m.close()
+
+    def run(self, jobs, submaps, clouds):
+        """-> list of (found, score, pose_estimate) in job order."""
+        if not jobs:
+            return []
+        sm = self.sm
+        sub_ids = sorted({j.submap_id for j in jobs})
+        for sid in sub_ids:
+            self.ensure_matcher(sid, submaps[sid].grid)
+        cloud_keys = sorted({j.cloud_key for j in jobs})
+        for k in cloud_keys:
+            if k not in self.clouds:
+                self.clouds[k] = sm.DeviceCloud(clouds[k], device=self.device)
+        sidx = {s: i for i, s in enumerate(sub_ids)}
+        cidx = {k: i for i, k in enumerate(cloud_keys)}
+        arr = np.zeros(len(jobs), sm.JOB2D_DTYPE)
+        for i, j in enumerate(jobs):
+            arr[i]["stack_index"] = sidx[j.submap_id]
+            arr[i]["cloud_index"] = cidx[j.cloud_key]
+            arr[i]["full_submap"] = int(j.full)
+            arr[i]["initial_pose"] = j.initial_pose
+            arr[i]["min_score"] = j.min_score
+        res, st = sm.match_batch([self.matchers[s] for s in sub_ids],
+                                 [self.clouds[k] for k in cloud_keys], arr,
+                                 self.options.linear_search_window,
+                                 self.options.angular_search_window)
+        self.stats["candidates_scored"] += st["candidates_scored"]
+        self.stats["device_ms"] += st["device_ms"]
+        self.stats["searched"] += len(jobs)
+        return [(bool(r["found"]), float(r["score"]), tuple(r["pose_estimate"])) for r in res]
+
+    def release_clouds(self):
+        for c in self.clouds.values():
+            c.close()
+        self.clouds = {}
+
+
+class ConstraintBuilder2D:
+    """constraint_builder_2d.h:60-107.  `executor.run(jobs, submaps, clouds)` does the
+    matching (CudaExecutor in production); `process_group` (torch.distributed) turns
+    on submap-major sharding + the single all_gather of constraint records."""
+
+    def __init__(self, options, executor=None, process_group=None, device=0):
+        self.options = options
+        self.executor = executor if executor is not None else CudaExecutor(options, device)
+        self.pg = process_group
+        self.device = device
+        self._jobs = []
+        self._submaps = {}
+        self._clouds = {}
+        self._submap_order = {}
+        self._samplers = {}
+        self._when_done = None
+        self.num_started_nodes = 0
+        self.num_finished_nodes = 0
+        self.last_records = None
+
+    # -- queue --------------------------------------------------------------------
+    def _register(self, submap_id, submap, constant_data):
+        self._submaps[submap_id] = submap
+        self._submap_order.setdefault(submap_id, len(self._submap_order))
+        key = id(constant_data)
+        self._clouds[key] = constant_data
+        return key
+
+    def MaybeAddConstraint(self, submap_id, submap, node_id, constant_data,
+                           initial_relative_pose):
+        """constraint_builder_2d.cc:77-112.  constant_data is the node's
+        filtered_gravity_aligned_point_cloud (N x 3 float32)."""
+        if math.hypot(initial_relative_pose[0], initial_relative_pose[1]) > \
+                self.options.max_constraint_distance:
+            return
+        sampler = self._samplers.setdefault(submap_id,
+                                            FixedRatioSampler(self.options.sampling_ratio))
+        if not sampler.Pulse():
+            return
+        key = self._register(submap_id, submap, constant_data)
+        initial_pose = _compose(tuple(submap.local_pose), tuple(initial_relative_pose))  # :196-197
+        self._jobs.append(_Job(submap_id, node_id, key, initial_pose, False,
+                               self.options.min_score))
+
+    def MaybeAddGlobalConstraint(self, submap_id, submap, node_id, constant_data):
+        """constraint_builder_2d.cc:114-137."""
+        key = self._register(submap_id, submap, constant_data)
+        self._jobs.append(_Job(submap_id, node_id, key, (0.0, 0.0, 0.0), True,
+                               self.options.global_localization_min_score))
+
+    def NotifyEndOfNode(self):
+        """constraint_builder_2d.cc:139-151 (the node finishes when WhenDone drains)."""
+        self.num_started_nodes += 1
+
+    def GetNumFinishedNodes(self):
+        return self.num_finished_nodes
+
+    def DeleteScanMatcher(self, submap_id):
+        """constraint_builder_2d.cc:307-316."""
+        if hasattr(self.executor, "delete_matcher"):
+            self.executor.delete_matcher(submap_id)
+        self._samplers.pop(submap_id, None)
+
+    # -- drain ---------------------------------------------------------------------
+    def _world(self):
+        if self.pg is None:
+            return 0, 1
+        import torch.distributed as dist
+        return dist.get_rank(self.pg), dist.get_world_size(self.pg)
+
+    def WhenDone(self, callback):
+        """constraint_builder_2d.cc:153-163 + RunWhenDoneCallback :279-300: runs the
+        queue, then calls callback(Result) with the found constraints in queue order."""
+        if self._when_done is not None:
+            raise RuntimeError("WhenDone called twice")  # CHECK(when_done_ == nullptr)
+        self._when_done = callback
+        rank, world = self._world()
+        jobs = self._jobs
+        owner = [self._submap_order[j.submap_id] % world for j in jobs]
+        mine = [i for i, o in enumerate(owner) if o == rank]
+        out = self.executor.run([jobs[i] for i in mine], self._submaps, self._clouds)
+        local = np.zeros(len(mine), RECORD_DTYPE)
+        for rec, i, (found, score, pose) in zip(local, mine, out):
+            j = jobs[i]
+            rec["submap_trajectory"], rec["submap_index"] = j.submap_id
+            rec["node_trajectory"], rec["node_index"] = j.node_id
+            rec["found"] = int(found)
+            if found:
+                rec["score"] = score
+                # constraint_transform = ComputeSubmapPose(submap)^-1 * pose_estimate (:251-252)
+                rec["pose"] = _compose(_inverse(tuple(self._submaps[j.submap_id].local_pose)), pose)
+        records = self._allgather(local, mine, len(jobs), rank, world)
+        self.last_records = records
+        result = []
+        for rec in records:
+            if rec["found"]:
+                result.append(Constraint(
+                    (int(rec["submap_trajectory"]), int(rec["submap_index"])),
+                    (int(rec["node_trajectory"]), int(rec["node_index"])),
+                    tuple(float(v) for v in rec["pose"]),
+                    self.options.loop_closure_translation_weight,
+                    self.options.loop_closure_rotation_weight, "INTER_SUBMAP",
+                    float(rec["score"])))
+        self._jobs = []
+        self._clouds = {}
+        if hasattr(self.executor, "release_clouds"):
+            self.executor.release_clouds()
+        self.num_finished_nodes = self.num_started_nodes
+        cb, self._when_done = self._when_done, None
+        cb(result)
+        return result
+
+    def _allgather(self, local, mine, total, rank, world):
+        """The path's single collective: fixed-size records, padded to the largest
+        shard, gathered to every rank and re-ordered into queue order."""
+        if world == 1:
+            return local
+        import torch
+        import torch.distributed as dist
+        counts = [sum(1 for j in self._jobs if self._submap_order[j.submap_id] % world == r)
+                  for r in range(world)]
+        cap = max(1, max(counts))
+        backend = dist.get_backend(self.pg)
+        dev = torch.device("cuda", self.device) if backend == "nccl" else torch.device("cpu")
+        send = np.zeros(cap, RECORD_DTYPE)
+        send[:len(local)] = local
+        t_send = torch.from_numpy(send.view(np.uint8).reshape(-1).copy()).to(dev)
+        t_recv = torch.empty(world * cap * RECORD_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(t_recv, t_send, group=self.pg)
+        allrec = np.frombuffer(t_recv.cpu().numpy().tobytes(), dtype=RECORD_DTYPE).reshape(
+            world, cap)
+        out = np.zeros(total, RECORD_DTYPE)
+        cursor = [0] * world
+        for i, j in enumerate(self._jobs):
+            r = self._submap_order[j.submap_id] % world
+            out[i] = allrec[r, cursor[r]]
+            cursor[r] += 1
+        return out

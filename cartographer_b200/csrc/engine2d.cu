@@ -410,45 +410,47 @@ k_score_list(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
   }
 }
 
-// Scores the (up to) four children of `parent` at level h-1 with one warp.
-// Children are generated in the reference's order: x offset {0, half} outer,
-// y offset {0, half} inner, each clipped against the scan's max bound
-// (fast...2d.cc:352-367).  Returns the child count; sums[c] valid for c < count.
-__device__ __forceinline__ int ScoreChildren(const StackDev& st, const ScanInfo& si,
-                                             const int2* __restrict__ pts, int n, int xo,
-                                             int yo, int h, int lane, int sums[4], int cx[4],
-                                             int cy[4]) {
+// Scores the (up to) four children of a node at level h-1 with one warp.
+// Slot t = 2*ix + iy (ix, iy in {0,1}) is the child at offset (ix*half, iy*half);
+// increasing t is the reference's generation order (x offset outer, y offset
+// inner), and a slot is valid unless it is clipped by the scan's max bound
+// (fast...2d.cc:352-367).  Four scan points per lane are in flight per iteration
+// so that 4 point loads + up to 16 cell gathers overlap (the loop is
+// latency-bound otherwise).  Returns the valid mask; sums[t] is 0 if invalid.
+__device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const ScanInfo& si,
+                                                  const int2* __restrict__ pts, int n, int xo,
+                                                  int yo, int h, int lane, int sums[4]) {
   const int half = 1 << (h - 1);
-  const int nxk = (xo + half > si.max_x) ? 1 : 2;
-  const int nyk = (yo + half > si.max_y) ? 1 : 2;
+  const bool x2 = !(xo + half > si.max_x);
+  const bool y2 = !(yo + half > si.max_y);
   const int lv = h - 1;
   const int w1 = (1 << lv) - 1;
   const uint8_t* __restrict__ g = st.level[lv];
   const int wx = st.wx[lv], wy = st.wy[lv];
   int s00 = 0, s01 = 0, s10 = 0, s11 = 0;
   const int bx = xo + w1, by = yo + w1;
-  for (int p = lane; p < n; p += 32) {
-    const int2 q = pts[p];
-    const int lx = q.x + bx, ly = q.y + by;
-    s00 += GetValue(g, wx, wy, lx, ly);
-    if (nyk == 2) s01 += GetValue(g, wx, wy, lx, ly + half);
-    if (nxk == 2) {
-      s10 += GetValue(g, wx, wy, lx + half, ly);
-      if (nyk == 2) s11 += GetValue(g, wx, wy, lx + half, ly + half);
+  constexpr int kU = 4;
+  for (int p = lane; p < n; p += 32 * kU) {
+    int2 q[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int pp = p + 32 * u;
+      q[u] = pp < n ? pts[pp] : make_int2(-(1 << 28), -(1 << 28));  // reads as 0
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int lx = q[u].x + bx, ly = q[u].y + by;
+      s00 += GetValue(g, wx, wy, lx, ly);
+      if (y2) s01 += GetValue(g, wx, wy, lx, ly + half);
+      if (x2) s10 += GetValue(g, wx, wy, lx + half, ly);
+      if (x2 && y2) s11 += GetValue(g, wx, wy, lx + half, ly + half);
     }
   }
-  s00 = WarpSum(s00);
-  s01 = WarpSum(s01);
-  s10 = WarpSum(s10);
-  s11 = WarpSum(s11);
-  int c = 0;
-  sums[c] = s00; cx[c] = xo; cy[c] = yo; ++c;
-  if (nyk == 2) { sums[c] = s01; cx[c] = xo; cy[c] = yo + half; ++c; }
-  if (nxk == 2) {
-    sums[c] = s10; cx[c] = xo + half; cy[c] = yo; ++c;
-    if (nyk == 2) { sums[c] = s11; cx[c] = xo + half; cy[c] = yo + half; ++c; }
-  }
-  return c;
+  sums[0] = WarpSum(s00);
+  sums[1] = WarpSum(s01);
+  sums[2] = WarpSum(s10);
+  sums[3] = WarpSum(s11);
+  return 1u | (y2 ? 2u : 0u) | (x2 ? 4u : 0u) | ((x2 && y2) ? 8u : 0u);
 }
 
 // Greedy dives: one warp per scan starts at the scan's best lowest-resolution
@@ -489,15 +491,17 @@ k_dive(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
   int leaf_sum = best;
   unsigned long long scored = 0;
   while (h > 0) {
-    int sums[4], cx[4], cy[4];
-    const int c = ScoreChildren(st, si, pts, jb.n, xo, yo, h, lane, sums, cx, cy);
-    scored += c;
-    int b = 0;
-    for (int t = 1; t < c; ++t)
-      if (sums[t] > sums[b]) b = t;
-    xo = cx[b];
-    yo = cy[b];
-    leaf_sum = sums[b];
+    int sums[4];
+    const unsigned valid = ScoreChildren(st, si, pts, jb.n, xo, yo, h, lane, sums);
+    scored += __popc(valid);
+    const int half = 1 << (h - 1);
+    int b = 0, bs = sums[0];
+#pragma unroll
+    for (int t = 1; t < 4; ++t)
+      if (((valid >> t) & 1u) && sums[t] > bs) { b = t; bs = sums[t]; }
+    xo += (b >> 1) * half;
+    yo += (b & 1) * half;
+    leaf_sum = bs;
     --h;
   }
   if (lane == 0) {
@@ -571,35 +575,44 @@ k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
   if (!(nd.score >= OrderedToFloat(lb[si.job]))) return;
   const int2* __restrict__ pts = dscan + jb.dscan_off +
                                  static_cast<long long>(nd.scan - jb.scan_base) * jb.n;
-  int sums[4], cx[4], cy[4];
-  const int c = ScoreChildren(st, si, pts, jb.n, nd.xo, nd.yo, h, lane, sums, cx, cy);
+  int sums[4];
+  const unsigned valid = ScoreChildren(st, si, pts, jb.n, nd.xo, nd.yo, h, lane, sums);
   if (lane != 0) return;
-  atomicAdd(&counters[0], (unsigned long long)c);
+  atomicAdd(&counters[0], (unsigned long long)__popc(valid));
   atomicAdd(&counters[1], 1ull);
+  const int half = 1 << (h - 1);
   float sc[4];
-  for (int t = 0; t < c; ++t) sc[t] = ToScore(st, sums[t], jb.n);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) sc[t] = ToScore(st, sums[t], jb.n);
   if (h - 1 == 0) {
-    for (int t = 0; t < c; ++t) {
-      if (!(sc[t] > jb.min_score)) continue;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (!((valid >> t) & 1u) || !(sc[t] > jb.min_score)) continue;
       const unsigned o = FloatToOrdered(sc[t]);
       const unsigned old = atomicMax(&lb[si.job], o);
       if (o >= old) {
         const int idx = atomicAdd(leaf_count, 1);
-        if (idx < leaf_cap) leaves[idx] = Node{nd.scan, cx[t], cy[t], sc[t]};
-        else *overflow = 1;
+        if (idx < leaf_cap)
+          leaves[idx] = Node{nd.scan, nd.xo + (t >> 1) * half, nd.yo + (t & 1) * half, sc[t]};
+        else
+          *overflow = 1;
       }
     }
   } else {
     const float bound = OrderedToFloat(lb[si.job]);
-    int keep = 0;
-    for (int t = 0; t < c; ++t)
-      if (sc[t] > jb.min_score && sc[t] >= bound) ++keep;
+    unsigned keep = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (((valid >> t) & 1u) && sc[t] > jb.min_score && sc[t] >= bound) keep |= 1u << t;
     if (keep) {
-      int idx = atomicAdd(next_count, keep);
-      for (int t = 0; t < c; ++t) {
-        if (sc[t] > jb.min_score && sc[t] >= bound) {
-          if (idx < next_cap) next[idx] = Node{nd.scan, cx[t], cy[t], sc[t]};
-          else *overflow = 1;
+      int idx = atomicAdd(next_count, __popc(keep));
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if ((keep >> t) & 1u) {
+          if (idx < next_cap)
+            next[idx] = Node{nd.scan, nd.xo + (t >> 1) * half, nd.yo + (t & 1) * half, sc[t]};
+          else
+            *overflow = 1;
           ++idx;
         }
       }
