@@ -1,0 +1,46 @@
+// Compiles the drop-in adapter classes against the stand-in headers and links
+// them to libcsm_b200.so.  With a GPU it runs one match through the reference-
+// shaped C++ API; without one it only checks that the ABI reports CSM_E_CUDA
+// (no CPU fallback) — either way the binary proves the adapter builds and links.
+#include <cmath>
+#include <cstdio>
+
+#include "scan_matchers_b200.h"
+
+using namespace cartographer;
+
+int main() {
+  int32_t devices = 0;
+  if (csm_device_count(&devices) != CSM_OK || devices == 0) {
+    std::printf("adapter_selftest: no CUDA device (%s) — link check only\n",
+                csm_last_error_string());
+    return 0;
+  }
+  const int n = 120;
+  std::vector<uint16_t> cells(n * n, 0);
+  for (int i = 20; i < 100; ++i) {  // an L-shaped wall, p ~ 0.8
+    cells[40 * n + i] = 5000;
+    cells[i * n + 30] = 5000;
+  }
+  mapping::Grid2D grid(mapping::MapLimits(0.05, 3.0, 3.0, mapping::CellLimits{n, n}), 0.1f, 0.9f,
+                       cells);
+  mapping::scan_matching::proto::FastCorrelativeScanMatcherOptions2D options;
+  options.set_linear_search_window(1.0);
+  options.set_angular_search_window(0.3);
+  options.set_branch_and_bound_depth(4);
+  mapping::scan_matching::FastCorrelativeScanMatcher2D matcher(grid, options);
+  sensor::PointCloud cloud;
+  for (int i = 20; i < 100; i += 2) {
+    // world coordinates of the wall cells: x = max_x - (cy + .5) res, y = max_y - (cx + .5) res
+    cloud.push_back({{{float(3.0 - (40 + 0.5) * 0.05), float(3.0 - (i + 0.5) * 0.05), 0.f}}});
+    cloud.push_back({{{float(3.0 - (i + 0.5) * 0.05), float(3.0 - (30 + 0.5) * 0.05), 0.f}}});
+  }
+  float score = 0.f;
+  transform::Rigid2d pose;
+  const bool found = matcher.Match(transform::Rigid2d({0.2, -0.15}, 0.05), cloud, 0.5f, &score, &pose);
+  std::printf("adapter_selftest: found=%d score=%.4f pose=(%.3f, %.3f, %.4f)\n", found, score,
+              pose.translation().x(), pose.translation().y(), pose.rotation().angle());
+  if (!found || std::fabs(pose.translation().x()) > 0.051 || std::fabs(pose.translation().y()) > 0.051)
+    return 1;
+  return 0;
+}
