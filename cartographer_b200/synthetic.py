@@ -163,3 +163,139 @@ def cast_scan(occ, grid, pose, beams=1081, fov_deg=270.0, max_range=30.0, noise=
     pts[:, 0] = (ranges * np.cos(ang)).astype(np.float32)
     pts[:, 1] = (ranges * np.sin(ang)).astype(np.float32)
     return pts
+
+
+# ===========================================================================
+# 3D
+# ===========================================================================
+def probability_to_value(p):
+    """mapping/probability_values.h:91-93 (ProbabilityToValue) in float32."""
+    p = np.clip(np.asarray(p, np.float32), K_MIN_P, K_MAX_P)
+    scaled = (p - K_MIN_P) * (np.float32(32766.0) / (K_MAX_P - K_MIN_P))
+    return (np.floor(scaled.astype(np.float64) + 0.5).astype(np.int64) + 1).astype(np.uint16)
+
+
+class HybridGridSpec:
+    """Flat record of a HybridGrid: voxel indices (n x 3 int32), values (n uint16)."""
+
+    def __init__(self, resolution, indices, values):
+        self.resolution = float(np.float32(resolution))
+        self.indices = np.ascontiguousarray(indices, np.int32).reshape(-1, 3)
+        self.values = np.ascontiguousarray(values, np.uint16).reshape(-1)
+
+
+def cell_index_3d(points, resolution):
+    """HybridGridBase::GetCellIndex (mapping/3d/hybrid_grid.h:428-433): lround(p / res)."""
+    q = np.asarray(points, np.float32) / np.float32(resolution)
+    return (np.sign(q) * np.floor(np.abs(q).astype(np.float64) + 0.5)).astype(np.int32)
+
+
+def grid_from_points(points, resolution, seed=0, p_lo=0.6, p_hi=0.9):
+    """Voxelise surface points into a HybridGrid record with hit probabilities."""
+    idx = np.unique(cell_index_3d(points, resolution), axis=0)
+    rng = np.random.RandomState(seed + 31)
+    vals = probability_to_value(rng.uniform(p_lo, p_hi, len(idx)).astype(np.float32))
+    return HybridGridSpec(resolution, idx, vals)
+
+
+def make_building(seed, size_m=40.0, height_m=6.0, cell=0.1):
+    """Boolean occupancy volume occ[z, y, x] of a two-storey box-and-pillars building
+    (walls extruded from the 2D floor plan, floor slabs at z = 0, h/2, h) centred at
+    the origin in x/y, z in [0, height]."""
+    occ2, _, _ = make_floorplan(seed, size_m=size_m, resolution=cell,
+                                rooms=max(2, int(6 * size_m / 40.0)),
+                                pillars=max(3, int(12 * size_m / 40.0)))
+    n = occ2.shape[0]
+    nz = int(round(height_m / cell)) + 1
+    occ = np.zeros((nz, n, n), bool)
+    occ[:] = occ2[None, :, :]
+    for zs in (0, nz // 2, nz - 1):
+        occ[zs] = True
+    return occ, cell, np.array([-size_m / 2.0, -size_m / 2.0, 0.0])
+
+
+def building_surface_points(occ, cell, origin):
+    z, y, x = np.nonzero(occ)
+    return (np.stack([x, y, z], axis=1).astype(np.float32) + 0.5) * np.float32(cell) + \
+        origin.astype(np.float32)
+
+
+def cast_lidar_3d(occ, cell, origin, pose_xyzyaw, rings=16, azimuths=2048, vfov_deg=15.0,
+                  max_range=20.0, noise=0.01, seed=0):
+    """Multi-ring lidar (VLP-16 like) ray-cast in the occupancy volume.  Returns the
+    hit points in the sensor frame (rays without a hit inside max_range are dropped)."""
+    rng = np.random.RandomState(seed)
+    el = np.deg2rad(np.linspace(-vfov_deg, vfov_deg, rings))
+    az = np.linspace(-math.pi, math.pi, azimuths, endpoint=False)
+    E, A = np.meshgrid(el, az, indexing="ij")
+    d_s = np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], axis=-1).reshape(-1, 3)
+    yaw = pose_xyzyaw[3]
+    c, s = math.cos(yaw), math.sin(yaw)
+    R = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+    d_w = d_s @ R.T
+    o = np.asarray(pose_xyzyaw[:3], np.float64)
+    nrays = len(d_w)
+    ranges = np.full(nrays, np.inf)
+    alive = np.ones(nrays, bool)
+    step = cell * 0.5
+    nz, ny, nx = occ.shape
+    ts = np.arange(1, int(max_range / step) + 1) * step
+    for t0 in range(0, len(ts), 64):
+        t = ts[t0:t0 + 64]
+        idx = np.nonzero(alive)[0]
+        if len(idx) == 0:
+            break
+        p = o[None, None, :] + d_w[idx, None, :] * t[None, :, None]
+        c3 = np.floor((p - origin[None, None, :]) / cell).astype(np.int64)
+        inside = ((c3[..., 0] >= 0) & (c3[..., 0] < nx) & (c3[..., 1] >= 0) & (c3[..., 1] < ny) &
+                  (c3[..., 2] >= 0) & (c3[..., 2] < nz))
+        hit = np.zeros(inside.shape, bool)
+        ci = c3[inside]
+        hit[inside] = occ[ci[:, 2], ci[:, 1], ci[:, 0]]
+        any_hit = hit.any(axis=1)
+        first = hit.argmax(axis=1)
+        ranges[idx[any_hit]] = t[first[any_hit]]
+        alive[idx[any_hit]] = False
+    ok = np.isfinite(ranges)
+    r = ranges[ok] + rng.normal(0.0, noise, ok.sum())
+    return (d_s[ok] * r[:, None]).astype(np.float32)
+
+
+def voxel_downsample(points, size):
+    """One point per `size` voxel (first occurrence) — stand-in for sensor::VoxelFilter."""
+    key = np.floor(np.asarray(points, np.float64) / size).astype(np.int64)
+    _, first = np.unique(key, axis=0, return_index=True)
+    return np.ascontiguousarray(np.asarray(points, np.float32)[np.sort(first)])
+
+
+def rotational_histogram(points, size=120, slice_height=0.2):
+    """Stand-in for RotationalScanMatcher::ComputeHistogram (producer side, out of scope;
+    rotational_scan_matcher.cc:164-176): per z-slice, points sorted by angle around the
+    slice centroid, histogram of the direction of consecutive-point segments weighted
+    by how orthogonal they are to the ray from the centroid."""
+    pts = np.asarray(points, np.float64)
+    hist = np.zeros(size, np.float32)
+    sl = np.round(pts[:, 2] / slice_height).astype(np.int64)
+    for s in np.unique(sl):
+        p = pts[sl == s]
+        if len(p) < 3:
+            continue
+        cen = p.mean(axis=0)
+        d = p[:, :2] - cen[:2]
+        keep = np.linalg.norm(d, axis=1) >= 0.2
+        p, d = p[keep], d[keep]
+        order = np.argsort(np.arctan2(d[:, 1], d[:, 0]), kind="stable")
+        p, d = p[order], d[order]
+        delta = p[1:, :2] - p[:-1, :2]
+        dist = np.linalg.norm(delta, axis=1)
+        direction = d[1:]
+        ok = (dist >= 0.2) & (dist <= 0.9) & (np.linalg.norm(direction, axis=1) >= 0.2)
+        if not ok.any():
+            continue
+        delta, direction, dist = delta[ok], direction[ok], dist[ok]
+        ang = np.mod(np.arctan2(delta[:, 1], delta[:, 0]), math.pi)
+        val = np.maximum(0.0, 1.0 - np.abs(np.sum(delta / dist[:, None] * direction /
+                                                  np.linalg.norm(direction, axis=1)[:, None], axis=1)))
+        b = np.clip(np.floor(size * ang / math.pi).astype(np.int64), 0, size - 1)
+        np.add.at(hist, b, val.astype(np.float32))
+    return hist

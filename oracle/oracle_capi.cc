@@ -8,6 +8,7 @@
 #include <thread>
 
 #include "oracle_2d.h"
+#include "oracle_3d.h"
 
 using namespace oracle;
 
@@ -319,6 +320,157 @@ double orc_fast2d_batch(void** matchers, const int32_t* job_matcher, const int32
   for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
   for (std::thread& t : pool) t.join();
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+
+// ===========================================================================
+// 3D
+// ===========================================================================
+namespace {
+struct Fast3DHandle {
+  const HybridGrid* hi;
+  const HybridGrid* lo;
+  std::vector<float> histogram;
+  FastOptions3D options;
+  std::unique_ptr<FastCorrelativeScanMatcher3D> matcher;
+};
+Rigid3d MakeRigid3d(const double* p) {  // {tx,ty,tz, qw,qx,qy,qz}
+  return Rigid3d{Vec3d{p[0], p[1], p[2]}, Quatd{p[3], p[4], p[5], p[6]}};
+}
+NodeData3D MakeNode(const double* gravity, const float* hi_xyz, int n_hi, const float* lo_xyz,
+                    int n_lo, const float* hist, int hist_n) {
+  NodeData3D d;
+  d.gravity_alignment = Quatd{gravity[0], gravity[1], gravity[2], gravity[3]};
+  d.high_resolution_point_cloud = MakeCloud(hi_xyz, n_hi);
+  d.low_resolution_point_cloud = MakeCloud(lo_xyz, n_lo);
+  d.rotational_scan_matcher_histogram.assign(hist, hist + hist_n);
+  return d;
+}
+}  // namespace
+
+void* orc_hybrid_create(float resolution, const int32_t* idx, const uint16_t* values, int64_t n) {
+  HybridGrid* g = new HybridGrid(resolution);
+  for (int64_t i = 0; i < n; ++i)
+    *g->mutable_value(Array3i{idx[3 * i], idx[3 * i + 1], idx[3 * i + 2]}) = values[i];
+  return g;
+}
+void orc_hybrid_destroy(void* h) { delete static_cast<HybridGrid*>(h); }
+int orc_hybrid_grid_size(void* h) { return static_cast<HybridGrid*>(h)->grid_size(); }
+void orc_hybrid_get_cell_index(float resolution, const float* p, int32_t* out) {
+  const HybridGrid g(resolution);
+  const Array3i c = g.GetCellIndex(Vec3f{p[0], p[1], p[2]});
+  out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
+float orc_hybrid_get_probability(void* h, int x, int y, int z) {
+  return static_cast<HybridGrid*>(h)->GetProbability(Array3i{x, y, z});
+}
+
+void* orc_fast3d_create(void* hi, void* lo, const float* hist, int hist_n, int bb_depth,
+                        int full_res_depth, double min_rot, double min_low, double lin_xy,
+                        double lin_z, double ang) {
+  Fast3DHandle* f = new Fast3DHandle;
+  f->hi = static_cast<HybridGrid*>(hi);
+  f->lo = static_cast<HybridGrid*>(lo);
+  f->histogram.assign(hist, hist + hist_n);
+  f->options = FastOptions3D{bb_depth, full_res_depth, min_rot, min_low, lin_xy, lin_z, ang};
+  f->matcher.reset(new FastCorrelativeScanMatcher3D(*f->hi, f->lo, &f->histogram, f->options));
+  return f;
+}
+void orc_fast3d_destroy(void* h) { delete static_cast<Fast3DHandle*>(h); }
+
+// Dense dump of one precomputation level over its bounding box.  out may be null
+// (query lo/dims first).  Layout: ((z - lo.z) * dims.y + (y - lo.y)) * dims.x + (x - lo.x).
+void orc_fast3d_level(void* h, int depth, int32_t* lo, int32_t* dims, uint8_t* out) {
+  Fast3DHandle* f = static_cast<Fast3DHandle*>(h);
+  const PrecomputationGrid3D& g = f->matcher->stack().Get(depth);
+  int mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+  g.ForEach([&](const Array3i& c, uint8_t) {
+    mn[0] = std::min(mn[0], c.x); mn[1] = std::min(mn[1], c.y); mn[2] = std::min(mn[2], c.z);
+    mx[0] = std::max(mx[0], c.x); mx[1] = std::max(mx[1], c.y); mx[2] = std::max(mx[2], c.z);
+  });
+  if (mn[0] > mx[0]) { for (int i = 0; i < 3; ++i) { lo[i] = 0; dims[i] = 0; } return; }
+  if (!out) {
+    for (int i = 0; i < 3; ++i) { lo[i] = mn[i]; dims[i] = mx[i] - mn[i] + 1; }
+    return;
+  }
+  // caller passes the lo/dims it wants dumped (may be larger than the bbox)
+  const int64_t nx = dims[0], ny = dims[1];
+  std::memset(out, 0, static_cast<size_t>(dims[0]) * dims[1] * dims[2]);
+  g.ForEach([&](const Array3i& c, uint8_t v) {
+    const int64_t x = c.x - lo[0], y = c.y - lo[1], z = c.z - lo[2];
+    if (x >= 0 && y >= 0 && z >= 0 && x < dims[0] && y < dims[1] && z < dims[2])
+      out[(z * ny + y) * nx + x] = v;
+  });
+}
+
+int orc_fast3d_match(void* h, int full, const double* node_pose, const double* submap_pose,
+                     const double* gravity, const float* hi_xyz, int n_hi, const float* lo_xyz,
+                     int n_lo, const float* hist, int hist_n, float min_score, float* score,
+                     double* pose_out, float* rot_score, float* low_score, int64_t* stats_out) {
+  Fast3DHandle* f = static_cast<Fast3DHandle*>(h);
+  const NodeData3D data = MakeNode(gravity, hi_xyz, n_hi, lo_xyz, n_lo, hist, hist_n);
+  MatchStats3D st;
+  std::unique_ptr<Result3D> r;
+  if (full) {
+    const Rigid3d n = MakeRigid3d(node_pose), s = MakeRigid3d(submap_pose);
+    r = f->matcher->MatchFullSubmap(n.q, s.q, data, min_score, &st);
+  } else {
+    r = f->matcher->Match(MakeRigid3d(node_pose), MakeRigid3d(submap_pose), data, min_score, &st);
+  }
+  if (stats_out) {
+    stats_out[0] = st.candidates_scored;
+    stats_out[1] = st.lowest_resolution_candidates;
+    stats_out[2] = st.nodes_expanded;
+    stats_out[3] = st.low_resolution_evaluations;
+    stats_out[4] = st.num_scans;
+    stats_out[5] = st.num_angles;
+    stats_out[6] = st.best_scan_index;
+    stats_out[7] = st.best_x;
+    stats_out[8] = st.best_y;
+    stats_out[9] = st.best_z;
+  }
+  if (!r) return 0;
+  *score = r->score;
+  pose_out[0] = r->pose_estimate.t.x; pose_out[1] = r->pose_estimate.t.y;
+  pose_out[2] = r->pose_estimate.t.z; pose_out[3] = r->pose_estimate.q.w;
+  pose_out[4] = r->pose_estimate.q.x; pose_out[5] = r->pose_estimate.q.y;
+  pose_out[6] = r->pose_estimate.q.z;
+  *rot_score = r->rotational_score;
+  *low_score = r->low_resolution_score;
+  return 1;
+}
+
+// Discrete scans of a match (test hook).  cells may be null to query num_scans.
+int orc_fast3d_discrete_scans(void* h, int full, const double* node_pose,
+                              const double* submap_pose, const double* gravity,
+                              const float* hi_xyz, int n_hi, const float* hist, int hist_n,
+                              int32_t* cells /* S*n*3 */, float* poses /* S*7 */,
+                              float* rot_scores /* S */) {
+  Fast3DHandle* f = static_cast<Fast3DHandle*>(h);
+  const NodeData3D data = MakeNode(gravity, hi_xyz, n_hi, hi_xyz, 0, hist, hist_n);
+  const auto scans = f->matcher->GenerateDiscreteScansForTest(
+      full != 0, MakeRigid3d(node_pose), MakeRigid3d(submap_pose), data);
+  if (cells) {
+    size_t k = 0;
+    for (size_t s = 0; s < scans.size(); ++s) {
+      for (const Array3i& c : scans[s].cell_indices_per_depth[0]) {
+        cells[k++] = c.x; cells[k++] = c.y; cells[k++] = c.z;
+      }
+      const Rigid3f& p = scans[s].pose;
+      const float v[7] = {p.t.x, p.t.y, p.t.z, p.q.w, p.q.x, p.q.y, p.q.z};
+      std::memcpy(poses + 7 * s, v, sizeof(v));
+      rot_scores[s] = scans[s].rotational_score;
+    }
+  }
+  return static_cast<int>(scans.size());
+}
+
+void orc_rotational_match(const float* submap_hist, const float* hist, int n, float initial_angle,
+                          const float* angles, int m, float* out) {
+  const std::vector<float> a(submap_hist, submap_hist + n), b(hist, hist + n);
+  const std::vector<float> r =
+      RotationalMatch(a, b, initial_angle, std::vector<float>(angles, angles + m));
+  std::memcpy(out, r.data(), sizeof(float) * m);
 }
 
 }  // extern "C"

@@ -42,9 +42,9 @@ def lib():
         _lib.orc_fast2d_create.restype = C.c_void_p
         _lib.orc_rt2d_match.restype = C.c_double
         _lib.orc_fast2d_batch.restype = C.c_double
-        for name in ("orc_fast3d_create", "orc_hybrid_create"):
-            if hasattr(_lib, name):
-                getattr(_lib, name).restype = C.c_void_p
+        _lib.orc_fast3d_create.restype = C.c_void_p
+        _lib.orc_hybrid_create.restype = C.c_void_p
+        _lib.orc_hybrid_get_probability.restype = C.c_float
     return _lib
 
 
@@ -280,3 +280,135 @@ def fast2d_batch(matchers, job_matcher, job_cloud, job_init_pose, clouds, full, 
                                   _p(scores, C.c_float), _p(poses, C.c_double),
                                   _p(cs, C.c_int64))
     return secs, found, scores, poses, cs
+
+
+# ===========================================================================
+# 3D
+# ===========================================================================
+STAT3_KEYS = ("candidates_scored", "lowest_resolution_candidates", "nodes_expanded",
+              "low_resolution_evaluations", "num_scans", "num_angles", "best_scan_index",
+              "best_x", "best_y", "best_z")
+
+
+def hybrid_get_cell_index(resolution, p):
+    p = _f32(p)
+    out = np.zeros(3, np.int32)
+    lib().orc_hybrid_get_cell_index(C.c_float(resolution), _p(p, C.c_float), _p(out, C.c_int32))
+    return tuple(int(v) for v in out)
+
+
+class HybridGrid:
+    """Sparse voxel grid given as (indices n x 3 int32, values n uint16) — the flat
+    form of proto::HybridGrid (mapping/proto/hybrid_grid.proto:19-28)."""
+
+    def __init__(self, resolution, indices, values):
+        self.resolution = float(np.float32(resolution))
+        self.indices = _i32(indices).reshape(-1, 3)
+        self.values = _u16(values).reshape(-1)
+        lib().orc_hybrid_get_probability.restype = C.c_float
+        self._h = C.c_void_p(lib().orc_hybrid_create(
+            C.c_float(resolution), _p(self.indices, C.c_int32), _p(self.values, C.c_uint16),
+            C.c_int64(len(self.values))))
+
+    def grid_size(self):
+        return int(lib().orc_hybrid_grid_size(self._h))
+
+    def get_probability(self, x, y, z):
+        return float(lib().orc_hybrid_get_probability(self._h, C.c_int(x), C.c_int(y), C.c_int(z)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_hybrid_destroy(self._h)
+            self._h = None
+
+
+class FastCorrelativeScanMatcher3D:
+    def __init__(self, hi, lo, histogram, options):
+        """options: dict with branch_and_bound_depth, full_resolution_depth,
+        min_rotational_score, min_low_resolution_score, linear_xy_search_window,
+        linear_z_search_window, angular_search_window."""
+        self.hi, self.lo = hi, lo
+        self.histogram = _f32(histogram).reshape(-1)
+        o = options
+        self._h = C.c_void_p(lib().orc_fast3d_create(
+            hi._h, lo._h, _p(self.histogram, C.c_float), C.c_int(len(self.histogram)),
+            C.c_int(o["branch_and_bound_depth"]), C.c_int(o["full_resolution_depth"]),
+            C.c_double(o["min_rotational_score"]), C.c_double(o["min_low_resolution_score"]),
+            C.c_double(o["linear_xy_search_window"]), C.c_double(o["linear_z_search_window"]),
+            C.c_double(o["angular_search_window"])))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_fast3d_destroy(self._h)
+            self._h = None
+
+    def _match(self, full, node_pose, submap_pose, node, min_score):
+        npose = np.ascontiguousarray(node_pose, np.float64)
+        spose = np.ascontiguousarray(submap_pose, np.float64)
+        grav = np.ascontiguousarray(node["gravity_alignment"], np.float64)
+        hi, lo = _f32(node["high_resolution_point_cloud"]), _f32(node["low_resolution_point_cloud"])
+        hist = _f32(node["rotational_scan_matcher_histogram"]).reshape(-1)
+        score, rot, low = C.c_float(0), C.c_float(0), C.c_float(0)
+        pose = np.zeros(7, np.float64)
+        stats = np.zeros(12, np.int64)
+        found = lib().orc_fast3d_match(
+            self._h, C.c_int(int(full)), _p(npose, C.c_double), _p(spose, C.c_double),
+            _p(grav, C.c_double), _p(hi, C.c_float), C.c_int(len(hi)), _p(lo, C.c_float),
+            C.c_int(len(lo)), _p(hist, C.c_float), C.c_int(len(hist)), C.c_float(min_score),
+            C.byref(score), _p(pose, C.c_double), C.byref(rot), C.byref(low), _p(stats, C.c_int64))
+        return dict(found=bool(found), score=np.float32(score.value), pose=pose,
+                    rotational_score=np.float32(rot.value),
+                    low_resolution_score=np.float32(low.value),
+                    **{k: int(stats[i]) for i, k in enumerate(STAT3_KEYS)})
+
+    def match(self, node_pose, submap_pose, node, min_score):
+        return self._match(False, node_pose, submap_pose, node, min_score)
+
+    def match_full_submap(self, node_rotation, submap_rotation, node, min_score):
+        return self._match(True, [0, 0, 0] + list(node_rotation), [0, 0, 0] + list(submap_rotation),
+                           node, min_score)
+
+    def level(self, depth):
+        lo, dims = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        lib().orc_fast3d_level(self._h, C.c_int(depth), _p(lo, C.c_int32), _p(dims, C.c_int32),
+                               None)
+        out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
+        if out.size:
+            lib().orc_fast3d_level(self._h, C.c_int(depth), _p(lo, C.c_int32),
+                                   _p(dims, C.c_int32), _p(out, C.c_uint8))
+        return lo, out
+
+    def level_box(self, depth, lo, dims):
+        lo, dims = _i32(lo), _i32(dims)
+        out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
+        lib().orc_fast3d_level(self._h, C.c_int(depth), _p(lo, C.c_int32), _p(dims, C.c_int32),
+                               _p(out, C.c_uint8))
+        return out
+
+    def discrete_scans(self, full, node_pose, submap_pose, node):
+        npose = np.ascontiguousarray(node_pose, np.float64)
+        spose = np.ascontiguousarray(submap_pose, np.float64)
+        grav = np.ascontiguousarray(node["gravity_alignment"], np.float64)
+        hi = _f32(node["high_resolution_point_cloud"])
+        hist = _f32(node["rotational_scan_matcher_histogram"]).reshape(-1)
+        args = (self._h, C.c_int(int(full)), _p(npose, C.c_double), _p(spose, C.c_double),
+                _p(grav, C.c_double), _p(hi, C.c_float), C.c_int(len(hi)), _p(hist, C.c_float),
+                C.c_int(len(hist)))
+        S = lib().orc_fast3d_discrete_scans(*args, None, None, None)
+        cells = np.zeros((S, len(hi), 3), np.int32)
+        poses = np.zeros((S, 7), np.float32)
+        rot = np.zeros(S, np.float32)
+        if S:
+            lib().orc_fast3d_discrete_scans(*args, _p(cells, C.c_int32), _p(poses, C.c_float),
+                                            _p(rot, C.c_float))
+        return cells, poses, rot
+
+
+def rotational_match(submap_hist, hist, initial_angle, angles):
+    a, b = _f32(submap_hist).reshape(-1), _f32(hist).reshape(-1)
+    ang = _f32(angles).reshape(-1)
+    out = np.zeros(len(ang), np.float32)
+    lib().orc_rotational_match(_p(a, C.c_float), _p(b, C.c_float), C.c_int(len(a)),
+                               C.c_float(initial_angle), _p(ang, C.c_float), C.c_int(len(ang)),
+                               _p(out, C.c_float))
+    return out
