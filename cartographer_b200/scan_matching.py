@@ -206,3 +206,174 @@ __all__ = ["FastCorrelativeScanMatcherOptions2D", "RealTimeCorrelativeScanMatche
            "FastCorrelativeScanMatcher2D", "RealTimeCorrelativeScanMatcher2D", "DeviceCloud",
            "match_batch", "kernel_launch_count", "device_count", "JOB2D_DTYPE",
            "RESULT2D_DTYPE", "_lib"]
+
+
+# ===========================================================================
+# 3D: FastCorrelativeScanMatcher3D (fast_correlative_scan_matcher_3d.h:66-101)
+# ===========================================================================
+class CsmOptions3D(C.Structure):
+    _fields_ = [("branch_and_bound_depth", C.c_int32), ("full_resolution_depth", C.c_int32),
+                ("min_rotational_score", C.c_double), ("min_low_resolution_score", C.c_double),
+                ("linear_xy_search_window", C.c_double), ("linear_z_search_window", C.c_double),
+                ("angular_search_window", C.c_double)]
+
+
+class CsmNode3D(C.Structure):
+    _fields_ = [("high_resolution_point_cloud", C.POINTER(C.c_float)), ("num_high", C.c_int32),
+                ("low_resolution_point_cloud", C.POINTER(C.c_float)), ("num_low", C.c_int32),
+                ("rotational_scan_matcher_histogram", C.POINTER(C.c_float)),
+                ("histogram_size", C.c_int32), ("gravity_alignment", C.c_double * 4)]
+
+
+class CsmResult3D(C.Structure):
+    _fields_ = [("found", C.c_int32), ("score", C.c_float), ("pose_estimate", C.c_double * 7),
+                ("rotational_score", C.c_float), ("low_resolution_score", C.c_float),
+                ("best_scan_index", C.c_int32), ("best_offset", C.c_int32 * 3),
+                ("leaves_tied", C.c_int32), ("reserved", C.c_int32)]
+
+
+@dataclass
+class FastCorrelativeScanMatcherOptions3D:
+    """proto/scan_matching/fast_correlative_scan_matcher_options_3d.proto; defaults from
+    configuration_files/pose_graph.lua:40-48."""
+    branch_and_bound_depth: int = 8
+    full_resolution_depth: int = 3
+    min_rotational_score: float = 0.77
+    min_low_resolution_score: float = 0.55
+    linear_xy_search_window: float = 5.0
+    linear_z_search_window: float = 1.0
+    angular_search_window: float = 0.2617993877991494  # math.radians(15.)
+
+
+@dataclass
+class TrajectoryNodeData3D:
+    """mapping/trajectory_node.h:45-63 — the fields the 3D matcher reads."""
+    high_resolution_point_cloud: np.ndarray
+    low_resolution_point_cloud: np.ndarray
+    rotational_scan_matcher_histogram: np.ndarray
+    gravity_alignment: tuple = (1.0, 0.0, 0.0, 0.0)
+
+
+class _NodeHolder:
+    def __init__(self, node):
+        self.hi = _f32(node.high_resolution_point_cloud)
+        lo = np.ascontiguousarray(node.low_resolution_point_cloud, np.float32).reshape(-1, 3)
+        self.lo = lo
+        self.hist = np.ascontiguousarray(node.rotational_scan_matcher_histogram,
+                                         np.float32).reshape(-1)
+        self.c = CsmNode3D()
+        self.c.high_resolution_point_cloud = ptr(self.hi, C.c_float)
+        self.c.num_high = len(self.hi)
+        self.c.low_resolution_point_cloud = ptr(self.lo, C.c_float)
+        self.c.num_low = len(self.lo)
+        self.c.rotational_scan_matcher_histogram = ptr(self.hist, C.c_float)
+        self.c.histogram_size = len(self.hist)
+        self.c.gravity_alignment = (C.c_double * 4)(*[float(v) for v in node.gravity_alignment])
+
+
+class FastCorrelativeScanMatcher3D:
+    """FastCorrelativeScanMatcher3D(hybrid_grid, low_resolution_hybrid_grid,
+    rotational_scan_matcher_histogram, options).  Grids are records with
+    .resolution, .indices (n x 3 int32), .values (n uint16)."""
+
+    def __init__(self, hybrid_grid, low_resolution_hybrid_grid,
+                 rotational_scan_matcher_histogram, options, device=0, grid_size_in_voxels=0):
+        self.options = options
+        hist = np.ascontiguousarray(rotational_scan_matcher_histogram, np.float32).reshape(-1)
+        hi_idx = np.ascontiguousarray(hybrid_grid.indices, np.int32).reshape(-1, 3)
+        hi_val = np.ascontiguousarray(hybrid_grid.values, np.uint16).reshape(-1)
+        lo_idx = np.ascontiguousarray(low_resolution_hybrid_grid.indices, np.int32).reshape(-1, 3)
+        lo_val = np.ascontiguousarray(low_resolution_hybrid_grid.values, np.uint16).reshape(-1)
+        o = CsmOptions3D(options.branch_and_bound_depth, options.full_resolution_depth,
+                         options.min_rotational_score, options.min_low_resolution_score,
+                         options.linear_xy_search_window, options.linear_z_search_window,
+                         options.angular_search_window)
+        self._h = C.c_void_p()
+        check(lib().csm_matcher3d_create(
+            ptr(hi_idx, C.c_int32), ptr(hi_val, C.c_uint16), C.c_int64(len(hi_val)),
+            C.c_float(hybrid_grid.resolution), C.c_int32(grid_size_in_voxels),
+            ptr(lo_idx, C.c_int32), ptr(lo_val, C.c_uint16), C.c_int64(len(lo_val)),
+            C.c_float(low_resolution_hybrid_grid.resolution), ptr(hist, C.c_float),
+            C.c_int32(len(hist)), C.byref(o), C.c_int32(device), C.byref(self._h)))
+        self.last_stats = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().csm_matcher3d_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _match(self, full, node_pose, submap_pose, constant_data, min_score):
+        holder = _NodeHolder(constant_data)
+        npose = np.ascontiguousarray(node_pose, np.float64)
+        spose = np.ascontiguousarray(submap_pose, np.float64)
+        res = CsmResult3D()
+        stats = CsmStats()
+        check(lib().csm_match3d(self._h, C.byref(holder.c), ptr(npose, C.c_double),
+                                ptr(spose, C.c_double), C.c_int32(int(full)),
+                                C.c_float(min_score), C.byref(res), C.byref(stats)))
+        self.last_stats = stats.as_dict()
+        self.last_result = res
+        if not res.found:
+            return None
+        return dict(score=np.float32(res.score), pose_estimate=np.array(res.pose_estimate[:]),
+                    rotational_score=np.float32(res.rotational_score),
+                    low_resolution_score=np.float32(res.low_resolution_score),
+                    best_scan_index=res.best_scan_index, best_offset=tuple(res.best_offset[:]),
+                    leaves_tied=res.leaves_tied)
+
+    def Match(self, global_node_pose, global_submap_pose, constant_data, min_score):
+        """-> Result dict or None (nullptr), fast_correlative_scan_matcher_3d.cc:127-144.
+        Poses are [tx, ty, tz, qw, qx, qy, qz]."""
+        return self._match(False, global_node_pose, global_submap_pose, constant_data, min_score)
+
+    def MatchFullSubmap(self, global_node_rotation, global_submap_rotation, constant_data,
+                        min_score):
+        """fast_correlative_scan_matcher_3d.cc:146-170; rotations are [qw, qx, qy, qz]."""
+        return self._match(True, [0, 0, 0] + list(global_node_rotation),
+                           [0, 0, 0] + list(global_submap_rotation), constant_data, min_score)
+
+    # -- test hooks ------------------------------------------------------------------
+    def precomputation_grid(self, depth, lo=None, dims=None):
+        blo, bdims = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        check(lib().csm_matcher3d_read_level(self._h, C.c_int32(depth), ptr(blo, C.c_int32),
+                                             ptr(bdims, C.c_int32), None))
+        if lo is None:
+            lo, dims = blo, bdims
+        lo = np.ascontiguousarray(lo, np.int32)
+        dims = np.ascontiguousarray(dims, np.int32)
+        out = np.zeros((dims[2], dims[1], dims[0]), np.uint8)
+        if out.size:
+            check(lib().csm_matcher3d_read_level(self._h, C.c_int32(depth), ptr(lo, C.c_int32),
+                                                 ptr(dims, C.c_int32), ptr(out, C.c_uint8)))
+        return lo, out
+
+    def discretize(self, full, node_pose, submap_pose, constant_data):
+        holder = _NodeHolder(constant_data)
+        npose = np.ascontiguousarray(node_pose, np.float64)
+        spose = np.ascontiguousarray(submap_pose, np.float64)
+        S = C.c_int32(0)
+        args = (self._h, C.byref(holder.c), ptr(npose, C.c_double), ptr(spose, C.c_double),
+                C.c_int32(int(full)), C.byref(S))
+        check(lib().csm_discretize3d(*args, None, None, None))
+        cells = np.zeros((S.value, len(holder.hi), 3), np.int32)
+        poses = np.zeros((S.value, 7), np.float32)
+        rot = np.zeros(S.value, np.float32)
+        if S.value:
+            check(lib().csm_discretize3d(*args, ptr(cells, C.c_int32), ptr(poses, C.c_float),
+                                         ptr(rot, C.c_float)))
+        return cells, poses, rot
+
+
+def rotational_match(submap_histogram, histogram, initial_angle, angles, device=0):
+    """RotationalScanMatcher::Match (rotational_scan_matcher.cc:178-189) on the device."""
+    a = np.ascontiguousarray(submap_histogram, np.float32).reshape(-1)
+    b = np.ascontiguousarray(histogram, np.float32).reshape(-1)
+    ang = np.ascontiguousarray(angles, np.float32).reshape(-1)
+    out = np.zeros(len(ang), np.float32)
+    check(lib().csm_rotational_match3d(ptr(a, C.c_float), ptr(b, C.c_float), C.c_int32(len(a)),
+                                       C.c_float(initial_angle), ptr(ang, C.c_float),
+                                       C.c_int32(len(ang)), C.c_int32(device),
+                                       ptr(out, C.c_float)))
+    return out

@@ -173,6 +173,92 @@ csm_status csm_rt_match2d(const uint16_t* cells, int32_t num_x_cells, int32_t nu
                           double rotation_delta_cost_weight, int32_t device, double* score,
                           double pose_estimate[3], csm_stats* stats /* may be NULL */);
 
+/* ==== 3D: FastCorrelativeScanMatcher3D ====================================== */
+/* A HybridGrid crosses the ABI in the flat form of proto::HybridGrid
+ * (mapping/proto/hybrid_grid.proto:19-28): voxel indices (n x {x,y,z} int32, origin
+ * centred as in mapping/3d/hybrid_grid.h:263-264) and their uint16 values. */
+
+/* proto/scan_matching/fast_correlative_scan_matcher_options_3d.proto */
+typedef struct csm_options3d {
+  int32_t branch_and_bound_depth;
+  int32_t full_resolution_depth;
+  double min_rotational_score;
+  double min_low_resolution_score;
+  double linear_xy_search_window;
+  double linear_z_search_window;
+  double angular_search_window;
+} csm_options3d;
+
+/* The matcher object: PrecomputationGridStack3D of the high-resolution grid
+ * (fast_correlative_scan_matcher_3d.cc:57-77, precomputation_grid_3d.cc:49-81), the
+ * low-resolution HybridGrid and the submap's rotational histogram — what
+ * FastCorrelativeScanMatcher3D's ctor takes (:112-123).  Unlike the reference
+ * (which keeps raw pointers to the low-res grid and histogram, :122-123) the
+ * device copies are owned by the handle.  grid_size_in_voxels is
+ * HybridGrid::grid_size() of the high-resolution grid (used by MatchFullSubmap,
+ * :151-152); pass 0 to derive it from the voxel extents. */
+typedef struct csm_matcher3d csm_matcher3d;
+csm_status csm_matcher3d_create(const int32_t* hi_indices, const uint16_t* hi_values,
+                                int64_t hi_num_voxels, float hi_resolution,
+                                int32_t hi_grid_size_in_voxels, const int32_t* lo_indices,
+                                const uint16_t* lo_values, int64_t lo_num_voxels,
+                                float lo_resolution, const float* submap_histogram,
+                                int32_t histogram_size, const csm_options3d* options,
+                                int32_t device, csm_matcher3d** out);
+csm_status csm_matcher3d_destroy(csm_matcher3d* matcher);
+/* Test hook: one precomputation level as a dense box.  With out == NULL it
+ * returns the level's bounding box (lo, dims); otherwise it fills `out`
+ * (((z-lo.z)*dims.y + (y-lo.y))*dims.x + (x-lo.x)) for the box passed in. */
+csm_status csm_matcher3d_read_level(const csm_matcher3d* matcher, int32_t depth, int32_t lo[3],
+                                    int32_t dims[3], uint8_t* out);
+
+/* TrajectoryNode::Data (mapping/trajectory_node.h:45-63), the fields the matcher reads. */
+typedef struct csm_node3d {
+  const float* high_resolution_point_cloud;   /* n x 3 */
+  int32_t num_high;
+  const float* low_resolution_point_cloud;    /* n x 3 */
+  int32_t num_low;
+  const float* rotational_scan_matcher_histogram;
+  int32_t histogram_size;
+  double gravity_alignment[4];                /* Quaterniond w, x, y, z */
+} csm_node3d;
+
+/* FastCorrelativeScanMatcher3D::Result (fast_correlative_scan_matcher_3d.h:68-73);
+ * pose_estimate = {tx, ty, tz, qw, qx, qy, qz}.  found == 0 <=> nullptr. */
+typedef struct csm_result3d {
+  int32_t found;
+  float score;
+  double pose_estimate[7];
+  float rotational_score;
+  float low_resolution_score;
+  int32_t best_scan_index;       /* index among the scans that passed the rotational filter */
+  int32_t best_offset[3];
+  int32_t leaves_tied;
+  int32_t reserved;
+} csm_result3d;
+
+/* Match (full_submap == 0, fast_correlative_scan_matcher_3d.cc:127-144; poses are
+ * Rigid3d {tx,ty,tz,qw,qx,qy,qz}) or MatchFullSubmap (full_submap != 0, :146-170;
+ * only the rotation parts of the two poses are used). */
+csm_status csm_match3d(const csm_matcher3d* matcher, const csm_node3d* node,
+                       const double global_node_pose[7], const double global_submap_pose[7],
+                       int32_t full_submap, float min_score, csm_result3d* result,
+                       csm_stats* stats /* may be NULL */);
+
+/* Test hooks: RotationalScanMatcher::Match (rotational_scan_matcher.cc:178-189) and
+ * the discrete scans of a match (GenerateDiscreteScans, :246-295): full-resolution
+ * cell indices (num_scans x n x 3), scan poses (num_scans x 7 float: t, q wxyz) and
+ * rotational scores.  Call with cells == NULL to get *num_scans. */
+csm_status csm_rotational_match3d(const float* submap_histogram, const float* histogram,
+                                  int32_t histogram_size, float initial_angle,
+                                  const float* angles, int32_t num_angles, int32_t device,
+                                  float* scores);
+csm_status csm_discretize3d(const csm_matcher3d* matcher, const csm_node3d* node,
+                            const double global_node_pose[7],
+                            const double global_submap_pose[7], int32_t full_submap,
+                            int32_t* num_scans, int32_t* cells, float* poses,
+                            float* rotational_scores);
+
 #ifdef __cplusplus
 }
 #endif
