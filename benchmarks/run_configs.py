@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""Per-config measurements for BASELINE.md (configs 1, 3, 4, 5 of BASELINE.json;
+config 2 is bench.py's headline).  Each config runs the engine through the C ABI
+on one GPU, times it, runs a bounded sample of the same jobs through the CPU oracle
+(all host threads for the batches, one thread for single matches), spot-checks
+parity on that sample, and prints one JSON line.
+
+  python benchmarks/run_configs.py [--configs 1,3,4,5] [--scale 1.0]
+
+Sizes are the BASELINE configs scaled so that the whole script ends in minutes
+(`--scale` multiplies the batch sizes); every line states the size it ran.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from cartographer_b200 import scan_matching as sm  # noqa: E402
+from cartographer_b200 import synthetic  # noqa: E402
+from oracle import pyoracle as oracle  # noqa: E402  (baseline + spot checks only)
+
+B2 = 1081 * 9 + 16
+BRT = 1081 * 10 + 16
+
+
+def sync():
+    import torch
+    torch.cuda.synchronize()
+
+
+def cfg1(scale):
+    """2D RealTimeCSM: 1081 beams vs 200x200 @5 cm, +-0.1 m / +-7 deg, weights 0.1/0.1."""
+    big, occ = synthetic.make_grid2d(7, 1000)
+    grid, occ2 = synthetic.crop_grid(big, occ, 400, 400, 200, 200)
+    rng = np.random.RandomState(1)
+    n = int(200 * scale)
+    scans, inits = [], []
+    for i in range(n):
+        pose = synthetic.random_free_pose(occ2, grid, rng, margin_cells=15)
+        scans.append(synthetic.cast_scan(occ2, grid, pose, seed=i, max_range=30.0))
+        inits.append(pose + rng.uniform(-1, 1, 3) * [0.05, 0.05, math.radians(3)])
+    opts = sm.RealTimeCorrelativeScanMatcherOptions(0.1, math.radians(7.0), 0.1, 0.1)
+    rt = sm.RealTimeCorrelativeScanMatcher2D(opts)
+    rt.Match(inits[0], scans[0], grid)
+    sync()
+    t0 = time.perf_counter()
+    cand, res = 0, []
+    for s, i in zip(scans, inits):
+        res.append(rt.Match(i, s, grid))
+        cand += rt.last_stats["candidates_scored"]
+    sync()
+    gpu_s = time.perf_counter() - t0
+    og = oracle.Grid2D(grid.cells, grid.resolution, grid.max_x, grid.max_y)
+    t0 = time.perf_counter()
+    ccand, ok = 0, True
+    for k in range(min(n, 50)):
+        w = oracle.rt2d_match(og, scans[k], inits[k], 0.1, math.radians(7.0), 0.1, 0.1)
+        ccand += w["candidates_scored"]
+        ok &= (np.float32(res[k][0]) == np.float32(w["score"])) and np.array_equal(res[k][1], w["pose"])
+    cpu_s = time.perf_counter() - t0
+    return {"config": 1, "what": "RealTimeCSM2D 1081 beams vs 200x200@5cm, 0.1m/7deg", "matches": n,
+            "gpu_cand_per_s": cand / gpu_s, "gpu_matches_per_s": n / gpu_s,
+            "gpu_algorithmic_GBps": cand * BRT / gpu_s / 1e9,
+            "cpu_cand_per_s_1thread": ccand / cpu_s, "cpu_matches_per_s_1thread": min(n, 50) / cpu_s,
+            "parity_ok": bool(ok), "note": "through csm_rt_match2d with host buffers (grid + scan H2D per call)"}
+
+
+def cfg4(scale):
+    """ConstraintBuilder2D batch: submaps x nodes, local search 7 m / 30 deg / depth 7 / 0.55."""
+    n_sub, n_node = max(2, int(12 * scale)), max(2, int(60 * scale))
+    lin, ang, depth, min_score = 7.0, math.radians(30.0), 7, 0.55
+    opts = sm.FastCorrelativeScanMatcherOptions2D(lin, ang, depth)
+    worlds = [synthetic.make_grid2d(s, 1000) for s in range(n_sub)]
+    rng = np.random.RandomState(3)
+    t0 = time.perf_counter()
+    matchers = [sm.FastCorrelativeScanMatcher2D(g, opts) for g, _ in worlds]
+    sync()
+    build_s = time.perf_counter() - t0
+    # every node scan is cast in submap (node % n_sub)'s world; against the other
+    # submaps the match is a (mostly unsuccessful) search, like a real queue
+    scans, truths = [], []
+    for nidx in range(n_node):
+        g, occ = worlds[nidx % n_sub]
+        pose = synthetic.random_free_pose(occ, g, rng)
+        scans.append(synthetic.cast_scan(occ, g, pose, seed=1000 + nidx))
+        truths.append(pose)
+    clouds = [sm.DeviceCloud(s) for s in scans]
+    jobs = np.zeros(n_sub * n_node, sm.JOB2D_DTYPE)
+    k = 0
+    for si in range(n_sub):
+        for ni in range(n_node):
+            jobs[k]["stack_index"] = si
+            jobs[k]["cloud_index"] = ni
+            jobs[k]["initial_pose"] = truths[ni] + rng.uniform(-1, 1, 3) * [3.0, 3.0, math.radians(15)]
+            jobs[k]["min_score"] = min_score
+            k += 1
+    sm.match_batch(matchers, clouds, jobs[:8], lin, ang)
+    sync()
+    t0 = time.perf_counter()
+    res, st = sm.match_batch(matchers, clouds, jobs, lin, ang)
+    sync()
+    gpu_s = time.perf_counter() - t0
+    # CPU: bounded sample on all host threads
+    threads = max(1, min(os.cpu_count() or 1, 64))
+    sample = np.arange(0, len(jobs), max(1, len(jobs) // (threads * 4)))[:threads * 4]
+    oms = {}
+    t_build0 = time.perf_counter()
+    for si in sorted({int(jobs[j]["stack_index"]) for j in sample}):
+        g = worlds[si][0]
+        oms[si] = oracle.FastCorrelativeScanMatcher2D(
+            oracle.Grid2D(g.cells, g.resolution, g.max_x, g.max_y), lin, ang, depth)
+    cpu_build_s = (time.perf_counter() - t_build0) / max(1, len(oms))
+    keys = sorted(oms)
+    secs, found, scores, poses, cs = oracle.fast2d_batch(
+        [oms[k] for k in keys], [keys.index(int(jobs[j]["stack_index"])) for j in sample],
+        [int(jobs[j]["cloud_index"]) for j in sample],
+        np.array([jobs[j]["initial_pose"] for j in sample]), scans, False, min_score, threads)
+    ok = True
+    for i, j in enumerate(sample):
+        ok &= bool(res[j]["found"]) == bool(found[i])
+        if found[i]:
+            ok &= np.float32(res[j]["score"]) == scores[i] and np.array_equal(res[j]["pose_estimate"], poses[i])
+    return {"config": 4, "what": "ConstraintBuilder2D batch, local search 7m/30deg/depth7/min 0.55",
+            "submaps": n_sub, "nodes": n_node, "jobs": len(jobs), "found": int(res["found"].sum()),
+            "gpu_constraints_per_s": len(jobs) / gpu_s, "gpu_cand_per_s": st["candidates_scored"] / gpu_s,
+            "gpu_algorithmic_GBps": st["candidates_scored"] * B2 / gpu_s / 1e9,
+            "gpu_stack_build_ms_per_submap": 1e3 * build_s / n_sub,
+            "gpu_device_ms": st["device_ms"], "gpu_wall_ms": 1e3 * gpu_s,
+            "host_tie_resolves": st["host_tie_resolves"],
+            "cpu_threads": threads, "cpu_sample_jobs": len(sample),
+            "cpu_constraints_per_s": len(sample) / secs, "cpu_cand_per_s": float(cs.sum()) / secs,
+            "cpu_stack_build_s_per_submap": cpu_build_s, "parity_ok": bool(ok)}
+
+
+def _world3d(seed, size_m, rings, az, max_range):
+    occ, cell, origin = synthetic.make_building(seed, size_m=size_m, height_m=6.0, cell=0.1)
+    pts = synthetic.building_surface_points(occ, cell, origin)
+    hi = synthetic.grid_from_points(pts, 0.10, seed)
+    lo = synthetic.grid_from_points(pts, 0.45, seed + 1)
+    rng = np.random.RandomState(seed)
+    nodes = []
+    return occ, cell, origin, hi, lo, rng, nodes
+
+
+def _node3d(occ, cell, origin, rng, rings, az, max_range, seed, hist_n=120):
+    nz, ny, nx = occ.shape
+    for _ in range(200):
+        pose = np.array([rng.uniform(origin[0] + 4, origin[0] + nx * cell - 4),
+                         rng.uniform(origin[1] + 4, origin[1] + ny * cell - 4),
+                         rng.choice([1.2, 4.2]), rng.uniform(-math.pi, math.pi)])
+        c = np.floor((pose[:3] - origin) / cell).astype(int)
+        if not occ[c[2] - 3:c[2] + 4, c[1] - 4:c[1] + 5, c[0] - 4:c[0] + 5].any():
+            break
+    cloud = synthetic.cast_lidar_3d(occ, cell, origin, pose, rings=rings, azimuths=az,
+                                    max_range=max_range, seed=seed)
+    low = synthetic.voxel_downsample(cloud, 0.45)
+    pose7 = np.array([pose[0], pose[1], pose[2], math.cos(pose[3] / 2), 0, 0, math.sin(pose[3] / 2)])
+    c, s = math.cos(pose[3]), math.sin(pose[3])
+    world = cloud.astype(np.float64) @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]]).T + pose[:3]
+    return dict(pose=pose7, cloud=cloud, low=low, hist=synthetic.rotational_histogram(cloud, hist_n),
+                world=world.astype(np.float32))
+
+
+def cfg3_5(scale, which):
+    """3D FastCSM: config 3 = 32 k-point VLP-16-like cloud, single matches; config 5 =
+    64-ring cloud, submaps x nodes batch through ConstraintBuilder3D's executor."""
+    if which == 3:
+        rings, az, n_sub, n_node = 16, 2048, 1, max(2, int(6 * scale))
+    else:
+        rings, az, n_sub, n_node = 64, 1024, max(1, int(2 * scale)), max(2, int(4 * scale))
+    o3 = sm.FastCorrelativeScanMatcherOptions3D()  # pose_graph.lua:40-48 defaults
+    od = dict(branch_and_bound_depth=8, full_resolution_depth=3, min_rotational_score=0.77,
+              min_low_resolution_score=0.55, linear_xy_search_window=5.0,
+              linear_z_search_window=1.0, angular_search_window=math.radians(15.0))
+    min_score = 0.55
+    subs = []
+    for s in range(n_sub):
+        occ, cell, origin, hi, lo, rng, _ = _world3d(40 + s, 40.0, rings, az, 20.0)
+        nodes = [_node3d(occ, cell, origin, rng, rings, az, 20.0, 100 * s + k) for k in range(n_node)]
+        sub_hist = synthetic.rotational_histogram(np.concatenate([n["world"] for n in nodes]), 120)
+        subs.append(dict(hi=hi, lo=lo, hist=sub_hist, nodes=nodes))
+    t0 = time.perf_counter()
+    ms = [sm.FastCorrelativeScanMatcher3D(s["hi"], s["lo"], s["hist"], o3) for s in subs]
+    sync()
+    build_s = time.perf_counter() - t0
+    jobs = []
+    rng = np.random.RandomState(9)
+    for si, s in enumerate(subs):
+        for n in s["nodes"]:
+            init = n["pose"].copy()
+            init[:3] += rng.uniform(-1, 1, 3) * [2.0, 2.0, 0.3]
+            yaw = 2 * math.atan2(n["pose"][6], n["pose"][3]) + rng.uniform(-1, 1) * math.radians(8)
+            init[3:] = [math.cos(yaw / 2), 0, 0, math.sin(yaw / 2)]
+            jobs.append((si, n, init))
+    ident = [0, 0, 0, 1, 0, 0, 0]
+    mk = lambda n: sm.TrajectoryNodeData3D(n["cloud"], n["low"], n["hist"])
+    ms[jobs[0][0]].Match(jobs[0][2], ident, mk(jobs[0][1]), min_score)
+    sync()
+    t0 = time.perf_counter()
+    cand, found, results, dev_ms = 0, 0, [], 0.0
+    for si, n, init in jobs:
+        r = ms[si].Match(init, ident, mk(n), min_score)
+        results.append(r)
+        cand += ms[si].last_stats["candidates_scored"]
+        dev_ms += ms[si].last_stats["device_ms"]
+        found += r is not None
+    sync()
+    gpu_s = time.perf_counter() - t0
+    # CPU oracle on a bounded sample (single thread per match, sequential)
+    sample = jobs[:max(1, min(len(jobs), 3))]
+    ccand, ok = 0, True
+    t_cpu = 0.0
+    for si, n, init in sample:
+        s = subs[si]
+        ohi = oracle.HybridGrid(s["hi"].resolution, s["hi"].indices, s["hi"].values)
+        olo = oracle.HybridGrid(s["lo"].resolution, s["lo"].indices, s["lo"].values)
+        om = oracle.FastCorrelativeScanMatcher3D(ohi, olo, s["hist"], od)
+        node = dict(gravity_alignment=(1.0, 0.0, 0.0, 0.0), high_resolution_point_cloud=n["cloud"],
+                    low_resolution_point_cloud=n["low"], rotational_scan_matcher_histogram=n["hist"])
+        t0 = time.perf_counter()
+        w = om.match(init, ident, node, min_score)
+        t_cpu += time.perf_counter() - t0
+        ccand += w["candidates_scored"]
+        g = results[jobs.index((si, n, init))]
+        ok &= (g is not None) == w["found"]
+        if w["found"]:
+            ok &= g["score"] == w["score"] and np.array_equal(g["pose_estimate"], w["pose"])
+    npts = int(np.mean([len(n["cloud"]) for _, n, _ in jobs]))
+    b3 = npts * 13 + 20
+    return {"config": which, "what": "FastCSM3D %d rings x %d az (~%d pts) vs HybridGrid@10cm + low-res@45cm, "
+            "depth 8 / full-res 3, 5m/1m/15deg" % (rings, az, npts), "submaps": n_sub,
+            "matches": len(jobs), "found": found, "gpu_matches_per_s": len(jobs) / gpu_s,
+            "gpu_cand_per_s": cand / gpu_s, "gpu_algorithmic_GBps": cand * b3 / gpu_s / 1e9,
+            "gpu_device_ms_per_match": dev_ms / len(jobs), "gpu_wall_ms_per_match": 1e3 * gpu_s / len(jobs),
+            "gpu_matcher_build_ms": 1e3 * build_s / n_sub,
+            "cpu_sample_matches": len(sample), "cpu_matches_per_s_1thread": len(sample) / t_cpu,
+            "cpu_cand_per_s_1thread": ccand / t_cpu, "parity_ok": bool(ok)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,3,4,5")
+    ap.add_argument("--scale", type=float, default=1.0)
+    args = ap.parse_args()
+    oracle.build()
+    for c in [int(x) for x in args.configs.split(",")]:
+        t0 = time.time()
+        if c == 1:
+            out = cfg1(args.scale)
+        elif c == 4:
+            out = cfg4(args.scale)
+        else:
+            out = cfg3_5(args.scale, c)
+        out["script_seconds"] = time.time() - t0
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -304,3 +304,214 @@ class ConstraintBuilder2D:
             out[i] = allrec[r, cursor[r]]
             cursor[r] += 1
         return out
+
+
+# ===========================================================================
+# ConstraintBuilder3D (mapping/internal/constraints/constraint_builder_3d.{h,cc})
+# ===========================================================================
+RECORD3D_DTYPE = np.dtype([("submap_trajectory", "<i4"), ("submap_index", "<i4"),
+                           ("node_trajectory", "<i4"), ("node_index", "<i4"),
+                           ("found", "<u4"), ("score", "<f4"), ("pose", "<f8", (7,)),
+                           ("rotational_score", "<f4"), ("low_resolution_score", "<f4"),
+                           ("pad", "<u4", (2,))], align=True)
+assert RECORD3D_DTYPE.itemsize == 96
+
+
+@dataclass
+class ConstraintBuilderOptions3D:
+    """constraint_builder_options.proto + fast_correlative_scan_matcher_options_3d;
+    defaults from configuration_files/pose_graph.lua:18-48."""
+    sampling_ratio: float = 0.3
+    max_constraint_distance: float = 15.0
+    min_score: float = 0.55
+    global_localization_min_score: float = 0.6
+    loop_closure_translation_weight: float = 1.1e4
+    loop_closure_rotation_weight: float = 1e5
+    branch_and_bound_depth: int = 8
+    full_resolution_depth: int = 3
+    min_rotational_score: float = 0.77
+    min_low_resolution_score: float = 0.55
+    linear_xy_search_window: float = 5.0
+    linear_z_search_window: float = 1.0
+    angular_search_window: float = math.radians(15.0)
+
+
+@dataclass
+class Submap3D:
+    """What the builder needs of a Submap3D (constraint_builder_3d.cc:172-198):
+    high / low resolution hybrid grids and the rotational scan matcher histogram."""
+    high_resolution_hybrid_grid: object
+    low_resolution_hybrid_grid: object
+    rotational_scan_matcher_histogram: object
+    grid_size_in_voxels: int = 0
+
+
+@dataclass
+class _Job3:
+    submap_id: tuple
+    node_id: tuple
+    node_key: int
+    node_pose: tuple
+    submap_pose: tuple
+    full: bool
+    min_score: float
+
+
+class CudaExecutor3D:
+    """One csm_matcher3d per submap (DispatchScanMatcherConstruction,
+    constraint_builder_3d.cc:172-198); jobs run through csm_match3d."""
+
+    def __init__(self, options, device=0):
+        from . import scan_matching as sm
+        self.sm = sm
+        self.options = options
+        self.device = device
+        self.matchers = {}
+        self.stats = {"candidates_scored": 0, "device_ms": 0.0, "searched": 0}
+
+    def delete_matcher(self, submap_id):
+        m = self.matchers.pop(submap_id, None)
+        if m is not None:
+            m.close()
+
+    def run(self, jobs, submaps, nodes):
+        sm, o = self.sm, self.options
+        out = []
+        for j in jobs:
+            if j.submap_id not in self.matchers:
+                sub = submaps[j.submap_id]
+                self.matchers[j.submap_id] = sm.FastCorrelativeScanMatcher3D(
+                    sub.high_resolution_hybrid_grid, sub.low_resolution_hybrid_grid,
+                    sub.rotational_scan_matcher_histogram,
+                    sm.FastCorrelativeScanMatcherOptions3D(
+                        o.branch_and_bound_depth, o.full_resolution_depth,
+                        o.min_rotational_score, o.min_low_resolution_score,
+                        o.linear_xy_search_window, o.linear_z_search_window,
+                        o.angular_search_window),
+                    device=self.device, grid_size_in_voxels=sub.grid_size_in_voxels)
+            m = self.matchers[j.submap_id]
+            r = m._match(j.full, j.node_pose, j.submap_pose, nodes[j.node_key], j.min_score)
+            self.stats["candidates_scored"] += m.last_stats["candidates_scored"]
+            self.stats["device_ms"] += m.last_stats["device_ms"]
+            self.stats["searched"] += 1
+            out.append(r)
+        return out
+
+
+class ConstraintBuilder3D:
+    """constraint_builder_3d.h:59-114 over the 3D engine; same sharding / single
+    all_gather scheme as ConstraintBuilder2D.  Constraint poses are the fast
+    matcher's pose_estimate (submap <- node), i.e. pre-Ceres (:265-275)."""
+
+    def __init__(self, options, executor=None, process_group=None, device=0):
+        self.options = options
+        self.executor = executor if executor is not None else CudaExecutor3D(options, device)
+        self.pg = process_group
+        self.device = device
+        self._jobs, self._submaps, self._nodes = [], {}, {}
+        self._submap_order, self._samplers = {}, {}
+        self._when_done = None
+        self.num_started_nodes = 0
+        self.num_finished_nodes = 0
+        self.last_records = None
+
+    def _register(self, submap_id, submap, constant_data):
+        self._submaps[submap_id] = submap
+        self._submap_order.setdefault(submap_id, len(self._submap_order))
+        key = id(constant_data)
+        self._nodes[key] = constant_data
+        return key
+
+    def MaybeAddConstraint(self, submap_id, submap, node_id, constant_data, global_node_pose,
+                           global_submap_pose):
+        """constraint_builder_3d.cc:79-114; poses are [tx,ty,tz,qw,qx,qy,qz]."""
+        d = np.asarray(global_node_pose[:3], float) - np.asarray(global_submap_pose[:3], float)
+        if float(np.sqrt((d * d).sum())) > self.options.max_constraint_distance:
+            return
+        sampler = self._samplers.setdefault(submap_id,
+                                            FixedRatioSampler(self.options.sampling_ratio))
+        if not sampler.Pulse():
+            return
+        key = self._register(submap_id, submap, constant_data)
+        self._jobs.append(_Job3(submap_id, node_id, key, tuple(global_node_pose),
+                                tuple(global_submap_pose), False, self.options.min_score))
+
+    def MaybeAddGlobalConstraint(self, submap_id, submap, node_id, constant_data,
+                                 global_node_rotation, global_submap_rotation):
+        """constraint_builder_3d.cc:116-142; rotations are [qw,qx,qy,qz]."""
+        key = self._register(submap_id, submap, constant_data)
+        self._jobs.append(_Job3(submap_id, node_id, key, (0, 0, 0) + tuple(global_node_rotation),
+                                (0, 0, 0) + tuple(global_submap_rotation), True,
+                                self.options.global_localization_min_score))
+
+    def NotifyEndOfNode(self):
+        self.num_started_nodes += 1
+
+    def GetNumFinishedNodes(self):
+        return self.num_finished_nodes
+
+    def DeleteScanMatcher(self, submap_id):
+        if hasattr(self.executor, "delete_matcher"):
+            self.executor.delete_matcher(submap_id)
+        self._samplers.pop(submap_id, None)
+
+    def WhenDone(self, callback):
+        if self._when_done is not None:
+            raise RuntimeError("WhenDone called twice")
+        self._when_done = callback
+        rank, world = (0, 1)
+        if self.pg is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(self.pg), dist.get_world_size(self.pg)
+        jobs = self._jobs
+        mine = [i for i, j in enumerate(jobs) if self._submap_order[j.submap_id] % world == rank]
+        out = self.executor.run([jobs[i] for i in mine], self._submaps, self._nodes)
+        local = np.zeros(len(mine), RECORD3D_DTYPE)
+        for rec, i, r in zip(local, mine, out):
+            j = jobs[i]
+            rec["submap_trajectory"], rec["submap_index"] = j.submap_id
+            rec["node_trajectory"], rec["node_index"] = j.node_id
+            if r is not None:
+                rec["found"] = 1
+                rec["score"] = r["score"]
+                rec["pose"] = r["pose_estimate"]
+                rec["rotational_score"] = r["rotational_score"]
+                rec["low_resolution_score"] = r["low_resolution_score"]
+        records = _allgather_records(self, local, len(jobs), rank, world, RECORD3D_DTYPE)
+        self.last_records = records
+        result = [Constraint((int(r["submap_trajectory"]), int(r["submap_index"])),
+                             (int(r["node_trajectory"]), int(r["node_index"])),
+                             tuple(float(v) for v in r["pose"]),
+                             self.options.loop_closure_translation_weight,
+                             self.options.loop_closure_rotation_weight, "INTER_SUBMAP",
+                             float(r["score"])) for r in records if r["found"]]
+        self._jobs, self._nodes = [], {}
+        self.num_finished_nodes = self.num_started_nodes
+        cb, self._when_done = self._when_done, None
+        cb(result)
+        return result
+
+
+def _allgather_records(builder, local, total, rank, world, dtype):
+    """Shared single-collective exchange (see ConstraintBuilder2D._allgather)."""
+    if world == 1:
+        return local
+    import torch
+    import torch.distributed as dist
+    owner = [builder._submap_order[j.submap_id] % world for j in builder._jobs]
+    counts = [owner.count(r) for r in range(world)]
+    cap = max(1, max(counts))
+    backend = dist.get_backend(builder.pg)
+    dev = torch.device("cuda", builder.device) if backend == "nccl" else torch.device("cpu")
+    send = np.zeros(cap, dtype)
+    send[:len(local)] = local
+    t_send = torch.from_numpy(send.view(np.uint8).reshape(-1).copy()).to(dev)
+    t_recv = torch.empty(world * cap * dtype.itemsize, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(t_recv, t_send, group=builder.pg)
+    allrec = np.frombuffer(t_recv.cpu().numpy().tobytes(), dtype=dtype).reshape(world, cap)
+    out = np.zeros(total, dtype)
+    cursor = [0] * world
+    for i, r in enumerate(owner):
+        out[i] = allrec[r, cursor[r]]
+        cursor[r] += 1
+    return out

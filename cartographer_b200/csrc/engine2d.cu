@@ -148,7 +148,7 @@ __device__ __forceinline__ V3 RotateRn(float qw, const V3& qv, const V3& v) {
 // lowest-resolution candidates per axis (fast...2d.cc:281-292).
 __global__ void __launch_bounds__(128)
 k_discretize(const JobDev* __restrict__ jobs, const int* __restrict__ scan_job,
-             int2* __restrict__ dscan, ScanInfo* __restrict__ info, int shrink,
+             short2* __restrict__ dscan, ScanInfo* __restrict__ info, int shrink,
              unsigned long long* __restrict__ counters) {
   const int sg = blockIdx.x;
   const int j = scan_job[sg];
@@ -159,7 +159,7 @@ k_discretize(const JobDev* __restrict__ jobs, const int* __restrict__ scan_job,
   // Quaternionf(AngleAxisf(a, UnitZ)): w = cos(ha), vec = sin(ha) * (0, 0, 1)
   const V3 qk{__fmul_rn(cs.y, 0.f), __fmul_rn(cs.y, 0.f), __fmul_rn(cs.y, 1.f)};
   const V3 q0{jb.q0x, jb.q0y, jb.q0z};
-  int2* out = dscan + jb.dscan_off + static_cast<long long>(k) * jb.n;
+  short2* out = dscan + jb.dscan_off + static_cast<long long>(k) * jb.n;
   int min_ix = INT_MAX, max_ix = INT_MIN, min_iy = INT_MAX, max_iy = INT_MIN;
   for (int p = threadIdx.x; p < jb.n; p += blockDim.x) {
     const V3 v{jb.xyz[3 * p], jb.xyz[3 * p + 1], jb.xyz[3 * p + 2]};
@@ -175,7 +175,11 @@ k_discretize(const JobDev* __restrict__ jobs, const int* __restrict__ scan_job,
                                           st.resolution), 0.5);
     const int ix = static_cast<int>(llround(fx));
     const int iy = static_cast<int>(llround(fy));
-    out[p] = make_int2(ix, iy);
+    // cells are kept as 2 x int16 (grids are < 32 k cells per axis; points farther
+    // than 30 k cells from the origin read as 0 for every candidate either way)
+    out[p] = make_short2(static_cast<short>(max(-30000, min(30000, ix))),
+                         static_cast<short>(max(-30000, min(30000, iy))));
+    if (shrink && (abs(ix) > 30000 || abs(iy) > 30000)) counters[7] = 1ull;  // reported as an error
     min_ix = min(min_ix, ix);
     max_ix = max(max_ix, ix);
     min_iy = min(min_iy, iy);
@@ -231,7 +235,7 @@ k_discretize(const JobDev* __restrict__ jobs, const int* __restrict__ scan_job,
 }
 
 csm_status LaunchDiscretize2D(cudaStream_t stream, const JobDev* jobs, const int* scan_job,
-                              int total_scans, int2* dscan, ScanInfo* info, int shrink,
+                              int total_scans, short2* dscan, ScanInfo* info, int shrink,
                               unsigned long long* counters) {
   k_discretize<<<total_scans, 128, 0, stream>>>(jobs, scan_job, dscan, info, shrink, counters);
   CSM_LAUNCH_CHECK();
@@ -245,7 +249,7 @@ csm_status LaunchDiscretize2D(cudaStream_t stream, const JobDev* jobs, const int
 // follows the reference's generation order (x outer, y inner; fast...2d.cc:296-309).
 __global__ void __launch_bounds__(256)
 k_score_top_gather(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
-                   const int2* __restrict__ dscan, int* __restrict__ top_sum,
+                   const short2* __restrict__ dscan, int* __restrict__ top_sum,
                    const long long* __restrict__ scan_slot_base, int total_scans,
                    long long total_slots) {
   const int lane = threadIdx.x & 31;
@@ -267,13 +271,13 @@ k_score_top_gather(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__
   const int w1 = (1 << h) - 1;
   const uint8_t* __restrict__ g = st.level[h];
   const int wx = st.wx[h], wy = st.wy[h];
-  const int2* __restrict__ pts = dscan + jb.dscan_off +
+  const short2* __restrict__ pts = dscan + jb.dscan_off +
                                  static_cast<long long>(sg - jb.scan_base) * jb.n;
   const int i = slot / si.nyc, jy = slot - i * si.nyc;
   const int ox = si.min_x + (i << h) + w1, oy = si.min_y + (jy << h) + w1;
   int sum = 0;
   for (int p = lane; p < jb.n; p += 32) {
-    const int2 c = pts[p];
+    const short2 c = pts[p];
     sum += GetValue(g, wx, wy, c.x + ox, c.y + oy);
   }
   sum = WarpSum(sum);
@@ -294,7 +298,7 @@ constexpr int kDenseChunk = 256;  // <= 257 so the packed u16 sums cannot overfl
 template <int kQuads>
 __global__ void __launch_bounds__(kDenseThreads)
 k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
-                  const int2* __restrict__ dscan, int* __restrict__ top_sum,
+                  const short2* __restrict__ dscan, int* __restrict__ top_sum,
                   const long long* __restrict__ scan_slot_base, int total_scans) {
   __shared__ int4 s_pt[kDenseChunk];  // {D index of lattice origin, qx, qy, 0}
   for (int sg = blockIdx.x; sg < total_scans; sg += gridDim.x) {
@@ -308,7 +312,7 @@ k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ 
     const uint8_t* __restrict__ dec = st.dec4 + 16;
     const int qr = (si.nxc + 3) >> 2;       // quads per lattice row
     const int quads = qr * si.nyc;
-    const int2* __restrict__ pts = dscan + jb.dscan_off +
+    const short2* __restrict__ pts = dscan + jb.dscan_off +
                                    static_cast<long long>(sg - jb.scan_base) * jb.n;
     int* __restrict__ out = top_sum + scan_slot_base[sg];
     for (int u0 = 0; u0 < quads; u0 += kDenseThreads * kQuads) {
@@ -329,7 +333,7 @@ k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ 
           const int p = p0 + t;
           int4 d = make_int4(0, -(1 << 24), -(1 << 24), 0);
           if (p < jb.n) {
-            const int2 c = pts[p];
+            const short2 c = pts[p];
             const int bx = c.x + si.min_x + s - 1, by = c.y + si.min_y + s - 1;
             const int qx = bx >> h, qy = by >> h;          // floor division
             const int ax = bx & (s - 1), ay = by & (s - 1);
@@ -385,7 +389,7 @@ k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ 
 struct ListCand { int scan; int xo, yo, level; };
 __global__ void __launch_bounds__(256)
 k_score_list(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
-             const int2* __restrict__ dscan, const ListCand* __restrict__ cands, int count,
+             const short2* __restrict__ dscan, const ListCand* __restrict__ cands, int count,
              int* __restrict__ sums, float* __restrict__ scores) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -396,11 +400,11 @@ k_score_list(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
   const int w1 = (1 << c.level) - 1;
   const uint8_t* __restrict__ g = st.level[c.level];
   const int wx = st.wx[c.level], wy = st.wy[c.level];
-  const int2* __restrict__ pts = dscan + jb.dscan_off +
+  const short2* __restrict__ pts = dscan + jb.dscan_off +
                                  static_cast<long long>(c.scan - jb.scan_base) * jb.n;
   int sum = 0;
   for (int p = lane; p < jb.n; p += 32) {
-    const int2 q = pts[p];
+    const short2 q = pts[p];
     sum += GetValue(g, wx, wy, q.x + c.xo + w1, q.y + c.yo + w1);
   }
   sum = WarpSum(sum);
@@ -418,7 +422,7 @@ k_score_list(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
 // so that 4 point loads + up to 16 cell gathers overlap (the loop is
 // latency-bound otherwise).  Returns the valid mask; sums[t] is 0 if invalid.
 __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const ScanInfo& si,
-                                                  const int2* __restrict__ pts, int n, int xo,
+                                                  const short2* __restrict__ pts, int n, int xo,
                                                   int yo, int h, int lane, int sums[4]) {
   const int half = 1 << (h - 1);
   const bool x2 = !(xo + half > si.max_x);
@@ -431,11 +435,11 @@ __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const Scan
   const int bx = xo + w1, by = yo + w1;
   constexpr int kU = 4;
   for (int p = lane; p < n; p += 32 * kU) {
-    int2 q[kU];
+    short2 q[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int pp = p + 32 * u;
-      q[u] = pp < n ? pts[pp] : make_int2(-(1 << 28), -(1 << 28));  // reads as 0
+      q[u] = pp < n ? pts[pp] : make_short2(-32768, -32768);  // reads as 0
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -460,7 +464,7 @@ __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const Scan
 // fast...2d.cc:335-378, only later).
 __global__ void __launch_bounds__(256)
 k_dive(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
-       const int2* __restrict__ dscan, const int* __restrict__ top_sum,
+       const short2* __restrict__ dscan, const int* __restrict__ top_sum,
        const long long* __restrict__ scan_slot_base, int total_scans,
        unsigned* __restrict__ lb, unsigned long long* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
@@ -486,7 +490,7 @@ k_dive(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
   int h = st.depth - 1;
   const int i = best_slot / si.nyc, jy = best_slot - i * si.nyc;
   int xo = si.min_x + (i << h), yo = si.min_y + (jy << h);
-  const int2* __restrict__ pts = dscan + jb.dscan_off +
+  const short2* __restrict__ pts = dscan + jb.dscan_off +
                                  static_cast<long long>(sg - jb.scan_base) * jb.n;
   int leaf_sum = best;
   unsigned long long scored = 0;
@@ -560,7 +564,7 @@ k_filter_top(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
 // at h-1 == 0, raises the job's bound and records the leaf.
 __global__ void __launch_bounds__(256)
 k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
-         const int2* __restrict__ dscan, const Node* __restrict__ parents, int count, int h,
+         const short2* __restrict__ dscan, const Node* __restrict__ parents, int count, int h,
          unsigned* __restrict__ lb, Node* __restrict__ next, int* __restrict__ next_count,
          int next_cap, Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
          int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
@@ -573,7 +577,7 @@ k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
   const StackDev& st = *jb.stack;
   // bound may have risen since the node was queued
   if (!(nd.score >= OrderedToFloat(lb[si.job]))) return;
-  const int2* __restrict__ pts = dscan + jb.dscan_off +
+  const short2* __restrict__ pts = dscan + jb.dscan_off +
                                  static_cast<long long>(nd.scan - jb.scan_base) * jb.n;
   int sums[4];
   const unsigned valid = ScoreChildren(st, si, pts, jb.n, nd.xo, nd.yo, h, lane, sums);
@@ -986,7 +990,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   CSM_TRY(d_scan_job.Reserve(sizeof(int) * plan.total_scans));
   CSM_TRY(d_slot_base.Reserve(sizeof(long long) * plan.total_scans));
   CSM_TRY(d_info.Reserve(sizeof(ScanInfo) * plan.total_scans));
-  CSM_TRY(d_dscan.Reserve(sizeof(int2) * plan.total_points));
+  CSM_TRY(d_dscan.Reserve(sizeof(short2) * plan.total_points));
   CSM_TRY(d_lb.Reserve(sizeof(unsigned) * num_jobs));
   CSM_TRY(d_ctr.Reserve(sizeof(unsigned long long) * 8 + sizeof(int) * 32));
   for (int j = 0; j < num_jobs; ++j) plan.jobs[j].trig = d_trig.as<float2>() + trig_off[j];
@@ -1007,7 +1011,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   const int total_scans = static_cast<int>(plan.total_scans);
   ProfBegin(ctx);
   k_discretize<<<total_scans, 128, 0, s>>>(d_jobs.as<JobDev>(), d_scan_job.as<int>(),
-                                           d_dscan.as<int2>(), d_info.as<ScanInfo>(), 1, ctr);
+                                           d_dscan.as<short2>(), d_info.as<ScanInfo>(), 1, ctr);
   CSM_LAUNCH_CHECK();
   ProfEnd(ctx, "k_discretize", static_cast<double>(plan.total_points));
 
@@ -1016,10 +1020,17 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     h_info.resize(total_scans);
     CSM_CUDA(cudaMemcpyAsync(h_info.data(), d_info.p, sizeof(ScanInfo) * total_scans,
                              cudaMemcpyDeviceToHost, s));
-    if (out_dscan)
-      CSM_CUDA(cudaMemcpyAsync(out_dscan, d_dscan.p, sizeof(int2) * plan.total_points,
+    std::vector<short2> h_ds;
+    if (out_dscan) {
+      h_ds.resize(plan.total_points);
+      CSM_CUDA(cudaMemcpyAsync(h_ds.data(), d_dscan.p, sizeof(short2) * plan.total_points,
                                cudaMemcpyDeviceToHost, s));
+    }
     CSM_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < h_ds.size(); ++i) {
+      out_dscan[2 * i] = h_ds[i].x;
+      out_dscan[2 * i + 1] = h_ds[i].y;
+    }
     if (out_bounds)
       for (int i = 0; i < total_scans; ++i) {
         out_bounds[4 * i + 0] = h_info[i].min_x;
@@ -1054,18 +1065,20 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   ProfBegin(ctx);
   if (use_gather_top) {
     k_score_top_gather<<<DivUp(plan.total_slots * 32, 256), 256, 0, s>>>(
-        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
         d_slot_base.as<long long>(), total_scans, plan.total_slots);
   } else {
     const int max_quads = (max_cap_x + 3) / 4 * max_cap_y;
     const int grid = std::min(total_scans, ctx->sm_count * 128);
 #define CSM_DENSE(Q)                                                                       \
     k_score_top_dense<Q><<<grid, kDenseThreads, 0, s>>>(                                   \
-        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),   \
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),   \
         d_slot_base.as<long long>(), total_scans)
-    if (max_quads <= kDenseThreads) CSM_DENSE(1);
-    else if (max_quads <= 2 * kDenseThreads) CSM_DENSE(2);
-    else CSM_DENSE(4);
+    // `max_quads` is an a-priori upper bound (the real lattice is only known on the
+    // device after ShrinkToFit); extra quads per thread would execute predicated-off
+    // work, so one quad per thread and extra passes for larger lattices is faster.
+    (void)max_quads;
+    CSM_DENSE(1);
 #undef CSM_DENSE
   }
   CSM_LAUNCH_CHECK();
@@ -1091,7 +1104,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   if (g_profile_on.load()) prof_scored();
   ProfBegin(ctx);
   k_dive<<<DivUp(static_cast<long long>(total_scans) * 32, 256), 256, 0, s>>>(
-      d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_top.as<int>(),
+      d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
       d_slot_base.as<long long>(), total_scans, d_lb.as<unsigned>(), ctr);
   CSM_LAUNCH_CHECK();
   if (g_profile_on.load()) {
@@ -1177,7 +1190,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     if (h - 1 >= 1) CSM_CUDA(cudaMemsetAsync(ictr + (h - 1), 0, sizeof(int), s));
     ProfBegin(ctx);
     k_expand<<<DivUp(static_cast<long long>(chunk) * 32, 256), 256, 0, s>>>(
-        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), queue_ptr(h) + start,
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), queue_ptr(h) + start,
         chunk, h, d_lb.as<unsigned>(), h - 1 >= 1 ? queue_ptr(h - 1) : nullptr,
         ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap, d_leaves.as<Node>(), leaf_count, kLeafCap,
         overflow, ctr);
@@ -1223,6 +1236,14 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
   CSM_CUDA(cudaStreamSynchronize(s));
   const int n_best = hp[17];
+  {
+    unsigned long long clamp_flag = 0;
+    CSM_CUDA(cudaMemcpy(&clamp_flag, ctr + 7, sizeof(clamp_flag), cudaMemcpyDeviceToHost));
+    if (clamp_flag) {
+      SetError("a scan point lies more than 30000 cells from the grid origin (int16 cell indices)");
+      return CSM_E_CAPACITY;
+    }
+  }
   std::vector<Node> best(n_best);
   std::vector<unsigned> lbh(num_jobs);
   unsigned long long hctr[8];
@@ -1274,7 +1295,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
       CSM_CUDA(cudaMemcpyAsync(d_lc.p, lc.data(), sizeof(ListCand) * lc.size(),
                                cudaMemcpyHostToDevice, s));
       k_score_list<<<DivUp(static_cast<long long>(lc.size()) * 32, 256), 256, 0, s>>>(
-          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_lc.as<ListCand>(),
+          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_lc.as<ListCand>(),
           static_cast<int>(lc.size()), nullptr, d_ls.as<float>());
       CSM_LAUNCH_CHECK();
       CSM_CUDA(cudaMemcpyAsync(anc.data(), d_ls.p, sizeof(float) * lc.size(),
@@ -1521,19 +1542,24 @@ csm_status csm_score_candidates2d(const csm_stack2d* stack, int32_t level,
   const size_t npts = static_cast<size_t>(num_scans) * n;
   CSM_TRY(d_jobs.Reserve(sizeof(JobDev)));
   CSM_TRY(d_info.Reserve(sizeof(ScanInfo) * num_scans));
-  CSM_TRY(d_dscan.Reserve(sizeof(int2) * npts));
+  CSM_TRY(d_dscan.Reserve(sizeof(short2) * npts));
+  std::vector<short2> h_ds(npts);
+  for (size_t i = 0; i < npts; ++i)
+    h_ds[i] = make_short2(
+        static_cast<short>(std::max(-30000, std::min(30000, discrete_scans[2 * i]))),
+        static_cast<short>(std::max(-30000, std::min(30000, discrete_scans[2 * i + 1]))));
   CSM_TRY(d_lc.Reserve(sizeof(ListCand) * num_candidates));
   CSM_TRY(d_sc.Reserve(sizeof(float) * num_candidates));
   CSM_TRY(d_su.Reserve(sizeof(int) * num_candidates));
   CSM_CUDA(cudaMemcpyAsync(d_jobs.p, &jd, sizeof(jd), cudaMemcpyHostToDevice, s));
   CSM_CUDA(cudaMemcpyAsync(d_info.p, info.data(), sizeof(ScanInfo) * num_scans,
                            cudaMemcpyHostToDevice, s));
-  CSM_CUDA(cudaMemcpyAsync(d_dscan.p, discrete_scans, sizeof(int2) * npts,
+  CSM_CUDA(cudaMemcpyAsync(d_dscan.p, h_ds.data(), sizeof(short2) * npts,
                            cudaMemcpyHostToDevice, s));
   CSM_CUDA(cudaMemcpyAsync(d_lc.p, lc.data(), sizeof(ListCand) * num_candidates,
                            cudaMemcpyHostToDevice, s));
   k_score_list<<<DivUp(static_cast<long long>(num_candidates) * 32, 256), 256, 0, s>>>(
-      d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<int2>(), d_lc.as<ListCand>(),
+      d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_lc.as<ListCand>(),
       num_candidates, d_su.as<int>(), d_sc.as<float>());
   CSM_LAUNCH_CHECK();
   CSM_CUDA(cudaMemcpyAsync(scores, d_sc.p, sizeof(float) * num_candidates,

@@ -64,7 +64,7 @@ struct Node {  // 16 B
 // Launches K2 (rotate + discretise + optional ShrinkToFit) for `total_scans`
 // scans on `stream`; defined in engine2d.cu, shared with the real-time matcher.
 csm_status LaunchDiscretize2D(cudaStream_t stream, const JobDev* jobs, const int* scan_job,
-                              int total_scans, int2* dscan, ScanInfo* info, int shrink,
+                              int total_scans, short2* dscan, ScanInfo* info, int shrink,
                               unsigned long long* counters);
 
 }  // namespace csm

@@ -35,7 +35,7 @@ __device__ __forceinline__ float GetProbability(const uint16_t* __restrict__ cel
 // One thread per candidate, candidates in the reference's generation order
 // (scan-major, x outer, y inner; real_time...2d.cc:98-111).
 __global__ void __launch_bounds__(128)
-k_rt_score(const uint16_t* __restrict__ cells, const int2* __restrict__ dscan,
+k_rt_score(const uint16_t* __restrict__ cells, const short2* __restrict__ dscan,
            const double* __restrict__ weight, RtParams P, float* __restrict__ scores) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int per_scan = P.width * P.width;
@@ -44,10 +44,10 @@ k_rt_score(const uint16_t* __restrict__ cells, const int2* __restrict__ dscan,
   const int r = c - scan * per_scan;
   const int xo = -P.lin + r / P.width;
   const int yo = -P.lin + r % P.width;
-  const int2* __restrict__ pts = dscan + static_cast<size_t>(scan) * P.n;
+  const short2* __restrict__ pts = dscan + static_cast<size_t>(scan) * P.n;
   float sum = 0.f;
   for (int p = 0; p < P.n; ++p) {
-    const int2 q = pts[p];
+    const short2 q = pts[p];
     sum = __fadd_rn(sum, GetProbability(cells, P, q.x + xo, q.y + yo));
   }
   float score = __fdiv_rn(sum, __int2float_rn(P.n));
@@ -196,7 +196,7 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
   CSM_TRY(d_job.Reserve(sizeof(JobDev)));
   CSM_TRY(d_sj.Reserve(sizeof(int) * num_scans));
   CSM_TRY(d_info.Reserve(sizeof(ScanInfo) * num_scans));
-  CSM_TRY(d_dscan.Reserve(sizeof(int2) * static_cast<size_t>(num_scans) * n));
+  CSM_TRY(d_dscan.Reserve(sizeof(short2) * static_cast<size_t>(num_scans) * n));
   CSM_TRY(d_scores.Reserve(sizeof(float) * num_cand));
   CSM_TRY(d_misc.Reserve(64));
 
@@ -222,7 +222,7 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
   CSM_CUDA(cudaMemsetAsync(d_sj.p, 0, sizeof(int) * num_scans, s));
   CSM_CUDA(cudaMemsetAsync(d_misc.p, 0, 64, s));
   CSM_TRY(LaunchDiscretize2D(s, d_job.as<JobDev>(), d_sj.as<int>(), num_scans,
-                             d_dscan.as<int2>(), d_info.as<ScanInfo>(), 0,
+                             d_dscan.as<short2>(), d_info.as<ScanInfo>(), 0,
                              d_misc.as<unsigned long long>()));
   RtParams P;
   P.nx = nx;
@@ -243,7 +243,7 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
     P.min_probability = kMinProbability;
   }
   k_rt_score<<<static_cast<int>((num_cand + 127) / 128), 128, 0, s>>>(
-      d_cells.as<uint16_t>(), d_dscan.as<int2>(), d_w.as<double>(), P, d_scores.as<float>());
+      d_cells.as<uint16_t>(), d_dscan.as<short2>(), d_w.as<double>(), P, d_scores.as<float>());
   CSM_LAUNCH_CHECK();
   int* d_best = reinterpret_cast<int*>(d_misc.as<char>() + 32);
   k_first_argmax<<<1, 1024, 0, s>>>(d_scores.as<float>(), static_cast<int>(num_cand), d_best);

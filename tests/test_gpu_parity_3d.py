@@ -188,3 +188,32 @@ def test_match_3d_building_parity(oracle, sm, seed):
     assert want["found"]
     assert m.last_stats["lowest_resolution_candidates"] == want["lowest_resolution_candidates"]
     m.close()
+
+
+def test_constraint_builder_3d_on_device(oracle, sm):
+    """constraint_builder_3d_test.cc:61-: MaybeAddConstraint x2 + MaybeAddGlobalConstraint
+    per round produce INTER_SUBMAP constraints whose poses equal the oracle's matches."""
+    from cartographer_b200 import constraint_builder as cb
+    rng = np.random.RandomState(42)
+    expected = worlds3d.random_pose(rng)
+    og = worlds3d.insert_cloud(oracle, 0.05, expected)
+    opts = cb.ConstraintBuilderOptions3D(sampling_ratio=1.0, max_constraint_distance=50.0,
+                                         min_score=0.1, global_localization_min_score=0.1,
+                                         **{k: v for k, v in worlds3d.TEST_OPTIONS.items()})
+    b = cb.ConstraintBuilder3D(opts)
+    sub = cb.Submap3D(og.spec, og.spec, np.zeros(10, np.float32), og.grid_size())
+    node = _node(sm, worlds3d.node_data(worlds3d.AXIS_CLOUD))
+    ident = [0, 0, 0, 1, 0, 0, 0]
+    b.MaybeAddConstraint((0, 0), sub, (0, 0), node, ident, ident)
+    b.MaybeAddConstraint((0, 0), sub, (0, 1), node, ident, ident)
+    b.MaybeAddGlobalConstraint((0, 0), sub, (0, 2), node, [1, 0, 0, 0], [1, 0, 0, 0])
+    b.NotifyEndOfNode()
+    got = b.WhenDone(lambda r: None)
+    assert len(got) == 3 and b.GetNumFinishedNodes() == 1
+    om = oracle.FastCorrelativeScanMatcher3D(og, og, np.zeros(10, np.float32),
+                                             worlds3d.TEST_OPTIONS)
+    want = om.match(ident, ident, worlds3d.node_data(worlds3d.AXIS_CLOUD), 0.1)
+    for c in got[:2]:
+        assert c.tag == "INTER_SUBMAP" and np.float32(c.score) == want["score"]
+        np.testing.assert_array_equal(np.array(c.zbar_ij), want["pose"])
+    b.DeleteScanMatcher((0, 0))
