@@ -268,7 +268,7 @@ def voxel_downsample(points, size):
     return np.ascontiguousarray(np.asarray(points, np.float32)[np.sort(first)])
 
 
-def rotational_histogram(points, size=120, slice_height=0.2):
+def rotational_histogram(points, size=120, slice_height=0.2, jitter_deg=2.0, seed=0):
     """Stand-in for RotationalScanMatcher::ComputeHistogram (producer side, out of scope;
     rotational_scan_matcher.cc:164-176): per z-slice, points sorted by angle around the
     slice centroid, histogram of the direction of consecutive-point segments weighted
@@ -293,9 +293,83 @@ def rotational_histogram(points, size=120, slice_height=0.2):
         if not ok.any():
             continue
         delta, direction, dist = delta[ok], direction[ok], dist[ok]
-        ang = np.mod(np.arctan2(delta[:, 1], delta[:, 0]), math.pi)
+        ang = np.arctan2(delta[:, 1], delta[:, 0])
+        if jitter_deg > 0:  # real walls are not perfectly straight: broaden the peaks a little
+            ang = ang + np.random.RandomState(seed + int(s) + 977).normal(
+                0.0, math.radians(jitter_deg), len(ang))
+        ang = np.mod(ang, math.pi)
         val = np.maximum(0.0, 1.0 - np.abs(np.sum(delta / dist[:, None] * direction /
                                                   np.linalg.norm(direction, axis=1)[:, None], axis=1)))
         b = np.clip(np.floor(size * ang / math.pi).astype(np.int64), 0, size - 1)
         np.add.at(hist, b, val.astype(np.float32))
     return hist
+
+
+def rotate_histogram(hist, angle):
+    """RotationalScanMatcher::RotateHistogram (rotational_scan_matcher.cc:141-162) in
+    numpy (input generation only): rotate by `angle` with fractional-bucket interpolation."""
+    h = np.asarray(hist, np.float32)
+    n = len(h)
+    rot = -angle * n / math.pi
+    full = int(np.floor(rot))
+    frac = np.float32(rot - full)
+    idx = np.arange(n)
+    return frac * h[(idx + 1 + full) % n] + (np.float32(1.0) - frac) * h[(idx + full) % n]
+
+
+def yaw_pose7(x, y, z, yaw):
+    return np.array([x, y, z, math.cos(yaw / 2.0), 0.0, 0.0, math.sin(yaw / 2.0)])
+
+
+def random_free_pose_3d(occ, cell, origin, rng, heights=(1.2,), margin_m=4.0):
+    nz, ny, nx = occ.shape
+    for _ in range(500):
+        pose = np.array([rng.uniform(origin[0] + margin_m, origin[0] + nx * cell - margin_m),
+                         rng.uniform(origin[1] + margin_m, origin[1] + ny * cell - margin_m),
+                         rng.choice(heights), rng.uniform(-math.pi, math.pi)])
+        c = np.floor((pose[:3] - origin) / cell).astype(int)
+        if not occ[max(0, c[2] - 3):c[2] + 4, c[1] - 4:c[1] + 5, c[0] - 4:c[0] + 5].any():
+            return pose
+    raise RuntimeError("no free pose found")
+
+
+def make_submap3d(seed, size_m=40.0, rings=16, azimuths=2048, max_range=20.0, map_scans=10,
+                  hist_size=120, hi_res=0.10, lo_res=0.45):
+    """A 3D submap the way Cartographer builds one: `map_scans` lidar scans from
+    random free poses are inserted (hit voxels, p ~ U(0.6, 0.9)) into a high- and a
+    low-resolution hybrid grid, and their rotated histograms are accumulated
+    (mapping/3d/submap_3d.cc:289-293).  Returns (hi, lo, submap_histogram, world) where
+    world = (occ, cell, origin) for casting further node scans."""
+    occ, cell, origin = make_building(seed, size_m=size_m, height_m=6.0, cell=0.1)
+    rng = np.random.RandomState(seed + 101)
+    pts, hist, map_poses = [], np.zeros(hist_size, np.float32), []
+    for k in range(map_scans):
+        pose = random_free_pose_3d(occ, cell, origin, rng, heights=(1.2, 4.2))
+        map_poses.append(pose)
+        cloud = cast_lidar_3d(occ, cell, origin, pose, rings=rings, azimuths=azimuths,
+                              max_range=max_range, seed=seed * 1000 + k)
+        c, s = math.cos(pose[3]), math.sin(pose[3])
+        world = cloud.astype(np.float64) @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]]).T + pose[:3]
+        pts.append(world.astype(np.float32))
+        hist += rotate_histogram(rotational_histogram(cloud, hist_size), pose[3])
+    pts = np.concatenate(pts)
+    return (grid_from_points(pts, hi_res, seed), grid_from_points(pts, lo_res, seed + 1), hist,
+            (occ, cell, origin, map_poses))
+
+
+def make_node3d(world, rng, rings=16, azimuths=2048, max_range=20.0, seed=0, hist_size=120,
+                lo_res=0.45):
+    """A node to match against a submap: one lidar scan taken near one of the poses
+    the submap was built from (a revisit, as in loop closure)."""
+    occ, cell, origin, map_poses = world
+    for _ in range(200):
+        base = map_poses[rng.randint(len(map_poses))]
+        pose = base + np.array([rng.uniform(-0.7, 0.7), rng.uniform(-0.7, 0.7), 0.0,
+                                rng.uniform(-0.4, 0.4)])
+        c = np.floor((pose[:3] - origin) / cell).astype(int)
+        if not occ[max(0, c[2] - 2):c[2] + 3, c[1] - 2:c[1] + 3, c[0] - 2:c[0] + 3].any():
+            break
+    cloud = cast_lidar_3d(occ, cell, origin, pose, rings=rings, azimuths=azimuths,
+                          max_range=max_range, seed=seed)
+    return dict(pose=yaw_pose7(*pose), cloud=cloud, low=voxel_downsample(cloud, lo_res),
+                hist=rotational_histogram(cloud, hist_size))
