@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 from cartographer_b200 import synthetic  # noqa: E402
 
 BYTES_PER_CANDIDATE = 1081 * (8 + 1) + 16  # N*(8+1)+16 @ N=1081
-MATCHES_PER_STEP = 4
+MATCHES_PER_STEP = 16
 MIN_SCORE = 0.6          # pose_graph.lua:28 global_localization_min_score
 DEPTH = 7                # pose_graph.lua:27
 LIN, ANG = 7.0, math.radians(30.0)
@@ -66,7 +66,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                  "--format=csv,noheader,nounits", "-lms", "100"],
+                                  "--format=csv,noheader,nounits", "-lms", "20"],
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -263,12 +263,15 @@ def main():
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        res = np.zeros(MATCHES_PER_STEP, sm.RESULT2D_DTYPE)
-        c_step = 0
-        for b in range(MATCHES_PER_STEP):
-            f, s, p = matcher.MatchFullSubmap(scans[it * MATCHES_PER_STEP + b], MIN_SCORE)
-            res[b]["found"] = int(f)
-            c_step += matcher.last_stats["candidates_scored"]
+        # the step's scans start in HOST memory: upload them (csm_cloud_create = H2D),
+        # run the batch, read the results back, release the device copies
+        step_clouds = [sm.DeviceCloud(scans[it * MATCHES_PER_STEP + b], device=local_rank)
+                       for b in range(MATCHES_PER_STEP)]
+        jobs = jobs_for(0)
+        res, st_e = sm.match_batch([matcher], step_clouds, jobs, LIN, ANG)
+        c_step = st_e["candidates_scored"]
+        for c in step_clouds:
+            c.close()
         allgather_results(res)
         barrier()
         dt = time.perf_counter() - t0

@@ -307,9 +307,9 @@ k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ 
     const StackDev& st = *jb.stack;
     const int h = st.depth - 1;
     const int s = 1 << h;
-    const int id = st.dec_id, jd = st.dec_jd, ids = st.dec_ids;
-    const unsigned lpad1 = static_cast<unsigned>(st.dec_lpad) - 1u;
-    const uint8_t* __restrict__ dec = st.dec4 + 16;
+    const int id = st.dec_id[h], jd = st.dec_jd[h], ids = st.dec_ids[h];
+    const unsigned lpad1 = static_cast<unsigned>(st.dec_lpad[h]) - 1u;
+    const uint8_t* __restrict__ dec = st.dec4[h] + 16;
     const int qr = (si.nxc + 3) >> 2;       // quads per lattice row
     const int quads = qr * si.nyc;
     const short2* __restrict__ pts = dscan + jb.dscan_off +
@@ -517,12 +517,19 @@ k_dive(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
 }
 
 // Pushes every lowest-resolution candidate that can still contain the optimum
-// (score > min_score and score >= current bound) onto the top-level queue.
+// (score > min_score and score >= current bound) onto the top-level queue.  One
+// CTA per scan walks the scan's lattice ROW by ROW (y outer, x inner) and appends
+// the survivors in that order with a block-wide ordered compaction, so queue
+// neighbours are lattice neighbours along x — the direction the lattice branch
+// kernel coalesces over.
 __global__ void __launch_bounds__(256)
 k_filter_top(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
              const int* __restrict__ top_sum, const long long* __restrict__ scan_slot_base,
              int total_scans, const unsigned* __restrict__ lb, Node* __restrict__ queue,
              int* __restrict__ qcount, int qcap, int* __restrict__ overflow) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int sg = blockIdx.x; sg < total_scans; sg += gridDim.x) {
     const ScanInfo si = info[sg];
     const JobDev& jb = jobs[si.job];
@@ -531,30 +538,34 @@ k_filter_top(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
     const int slots = si.nxc * si.nyc;
     const float bound = OrderedToFloat(lb[si.job]);
     const int* __restrict__ ts = top_sum + scan_slot_base[sg];
-    for (int s0 = 0; s0 < slots; s0 += blockDim.x) {
-      const int s = s0 + threadIdx.x;
+    for (int q0 = 0; q0 < slots; q0 += blockDim.x) {
+      const int q = q0 + threadIdx.x;  // row-major lattice index
       bool keep = false;
       float score = 0.f;
-      if (s < slots) {
-        score = ToScore(st, ts[s], jb.n);
+      int i = 0, jy = 0;
+      if (q < slots) {
+        jy = q / si.nxc;
+        i = q - jy * si.nxc;
+        score = ToScore(st, ts[i * si.nyc + jy], jb.n);
         keep = score > jb.min_score && score >= bound;
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (m) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(qcount, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (keep) {
-          const int idx = base + __popc(m & ((1u << lane) - 1));
-          if (idx < qcap) {
-            const int i = s / si.nyc, jy = s - i * si.nyc;
-            queue[idx] = Node{sg, si.min_x + (i << h), si.min_y + (jy << h), score};
-          } else {
-            *overflow = 1;
-          }
-        }
+      if (lane == 0) s_warp[warp] = __popc(m);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(qcount, tot) : 0;
       }
+      __syncthreads();
+      if (keep) {
+        const int idx = s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1));
+        if (idx < qcap)
+          queue[idx] = Node{sg, si.min_x + (i << h), si.min_y + (jy << h), score};
+        else
+          *overflow = 1;
+      }
+      __syncthreads();
     }
   }
 }
@@ -562,16 +573,13 @@ k_filter_top(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
 // Branch step: one warp per parent node of level h.  Scores its children at
 // level h-1, then either pushes the survivors to the next queue (h-1 >= 1) or,
 // at h-1 == 0, raises the job's bound and records the leaf.
-__global__ void __launch_bounds__(256)
-k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
-         const short2* __restrict__ dscan, const Node* __restrict__ parents, int count, int h,
-         unsigned* __restrict__ lb, Node* __restrict__ next, int* __restrict__ next_count,
-         int next_cap, Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
-         int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
+__device__ __forceinline__ void ExpandParentWarp(
+    const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+    const short2* __restrict__ dscan, const Node nd, int h, unsigned* __restrict__ lb,
+    Node* __restrict__ next, int* __restrict__ next_count, int next_cap,
+    Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
+    int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= count) return;
-  const Node nd = parents[warp];
   const ScanInfo si = info[nd.scan];
   const JobDev& jb = jobs[si.job];
   const StackDev& st = *jb.stack;
@@ -621,6 +629,240 @@ k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
         }
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+         const short2* __restrict__ dscan, const Node* __restrict__ parents, int count, int h,
+         unsigned* __restrict__ lb, Node* __restrict__ next, int* __restrict__ next_count,
+         int next_cap, Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
+         int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= count) return;
+  ExpandParentWarp(jobs, info, dscan, parents[warp], h, lb, next, next_count, next_cap, leaves,
+                   leaf_count, leaf_cap, overflow, counters);
+}
+
+// ---- scan-grouped branch step ------------------------------------------------
+// The children of all frontier nodes of ONE rotated scan lie on that scan's
+// lattice of stride s = 2^(h-1), so — exactly like the lowest-resolution pass —
+// the cells they need for one scan point are neighbouring bytes of one tile of the
+// decimated level h-1.  Parents are first grouped by scan (counting sort), then one
+// CTA handles up to 128 parents of a scan: point descriptors are staged once in
+// shared memory and every thread fetches the 2 x 2 children of its parent with two
+// aligned 32-bit loads per point (vs. four scattered byte gathers + a point load
+// in the warp-per-parent form).
+struct WorkItem { int scan, start, count; };
+
+__global__ void k_q_count(const Node* __restrict__ nodes, int count, int* __restrict__ scan_cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) atomicAdd(&scan_cnt[nodes[i].scan], 1);
+}
+
+// exclusive prefix sums of scan_cnt (node offsets) and of ceil(cnt / 32) (work items);
+// single CTA, 1024 threads, chunks of 1024 scans.  out[0] = number of work items.
+__global__ void __launch_bounds__(1024)
+k_q_offsets(const int* __restrict__ scan_cnt, int total_scans, int* __restrict__ scan_off,
+            int* __restrict__ item_off, int* __restrict__ out) {
+  __shared__ int s_a[1024], s_b[1024];
+  __shared__ int base_a, base_b;
+  if (threadIdx.x == 0) { base_a = 0; base_b = 0; }
+  __syncthreads();
+  for (int c0 = 0; c0 < total_scans; c0 += 1024) {
+    const int i = c0 + threadIdx.x;
+    const int cnt = i < total_scans ? scan_cnt[i] : 0;
+    const int items = (cnt + 31) >> 5;
+    s_a[threadIdx.x] = cnt;
+    s_b[threadIdx.x] = items;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int va = threadIdx.x >= o ? s_a[threadIdx.x - o] : 0;
+      const int vb = threadIdx.x >= o ? s_b[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_a[threadIdx.x] += va;
+      s_b[threadIdx.x] += vb;
+      __syncthreads();
+    }
+    if (i < total_scans) {
+      scan_off[i] = base_a + s_a[threadIdx.x] - cnt;
+      item_off[i] = base_b + s_b[threadIdx.x] - items;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) { base_a += s_a[1023]; base_b += s_b[1023]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = base_b;
+}
+
+__global__ void k_q_items(const int* __restrict__ scan_cnt, const int* __restrict__ scan_off,
+                          const int* __restrict__ item_off, int total_scans,
+                          WorkItem* __restrict__ items) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= total_scans) return;
+  const int cnt = scan_cnt[s];
+  for (int k = 0; k * 32 < cnt; ++k)
+    items[item_off[s] + k] = WorkItem{s, scan_off[s] + k * 32, min(32, cnt - k * 32)};
+}
+
+// Stable within every 32-node run: lanes holding nodes of the same scan get
+// consecutive slots in lane order (one atomic per scan per warp), so the x-ordered
+// runs produced by the push code survive the grouping.
+__global__ void k_q_scatter(const Node* __restrict__ nodes, int count,
+                            const int* __restrict__ scan_off, int* __restrict__ cursor,
+                            Node* __restrict__ sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool ok = i < count;
+  Node nd = Node{-1 - lane, 0, 0, 0.f};
+  if (ok) nd = nodes[i];
+  const unsigned peers = __match_any_sync(0xffffffffu, nd.scan);
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (ok && lane == leader) base = atomicAdd(&cursor[nd.scan], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (ok) sorted[scan_off[nd.scan] + base + __popc(peers & ((1u << lane) - 1))] = nd;
+}
+
+constexpr int kLatThreads = 128;   // 4 warps, each working on its own item
+constexpr int kLatChunk = 256;
+constexpr int kLatMinParents = 8;
+__global__ void __launch_bounds__(kLatThreads)
+k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+                 const short2* __restrict__ dscan, const Node* __restrict__ sorted,
+                 const WorkItem* __restrict__ items, const int* __restrict__ num_items, int h,
+                 unsigned* __restrict__ lb,
+                 Node* __restrict__ next, int* __restrict__ next_count, int next_cap,
+                 Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
+                 int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
+  __shared__ int4 s_all[kLatThreads / 32][kLatChunk];  // {D index of lattice origin, qx, qy, 0}
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (kLatThreads / 32) + warp;
+  if (item >= *num_items) return;
+  int4* s_pt = s_all[warp];
+  const WorkItem it = items[item];
+  if (it.count < kLatMinParents) {
+    // too few parents of this scan to amortise the shared point staging
+    for (int k = 0; k < it.count; ++k)
+      ExpandParentWarp(jobs, info, dscan, sorted[it.start + k], h, lb, next, next_count,
+                       next_cap, leaves, leaf_count, leaf_cap, overflow, counters);
+    return;
+  }
+  const ScanInfo si = info[it.scan];
+  const JobDev& jb = jobs[si.job];
+  const StackDev& st = *jb.stack;
+  const int lv = h - 1;            // level of the children
+  const int s = 1 << lv;           // = half width = lattice stride
+  const int id = st.dec_id[lv], jd = st.dec_jd[lv], ids = st.dec_ids[lv];
+  const unsigned lpad1 = static_cast<unsigned>(st.dec_lpad[lv]) - 1u;
+  const uint8_t* __restrict__ dec = st.dec4[lv] + 16;
+  const short2* __restrict__ pts = dscan + jb.dscan_off +
+                                   static_cast<long long>(it.scan - jb.scan_base) * jb.n;
+  const bool active = lane < it.count;
+  Node nd = Node{it.scan, si.min_x, si.min_y, 0.f};
+  if (active) nd = sorted[it.start + lane];
+  // the bound may have risen since the node was queued
+  const bool live = active && nd.score >= OrderedToFloat(lb[si.job]);
+  const int i0 = (nd.xo - si.min_x) >> lv, j0 = (nd.yo - si.min_y) >> lv;  // lattice coords
+  const int toff = j0 * ids + i0;
+  const bool x2 = !(nd.xo + s > si.max_x), y2 = !(nd.yo + s > si.max_y);
+  unsigned sum0 = 0, sum1 = 0, sum2 = 0, sum3 = 0;  // slots 2*ix+iy: 00, 01, 10, 11
+  for (int p0 = 0; p0 < jb.n; p0 += kLatChunk) {
+    __syncwarp();
+    for (int t = lane; t < kLatChunk; t += 32) {
+      const int p = p0 + t;
+      int4 d = make_int4(0, -(1 << 24), -(1 << 24), 0);
+      if (p < jb.n) {
+        const short2 c = pts[p];
+        const int bx = c.x + si.min_x + s - 1, by = c.y + si.min_y + s - 1;
+        const int qx = bx >> lv, qy = by >> lv;
+        const int ax = bx & (s - 1), ay = by & (s - 1);
+        d = make_int4(((ay * s + ax) * jd + qy) * ids + qx, qx, qy, 0);
+      }
+      s_pt[t] = d;
+    }
+    __syncwarp();
+    if (live) {
+      const int cnt = min(kLatChunk, jb.n - p0);
+      unsigned r0 = 0, r1 = 0;  // packed u16 pairs: (col I, col I+1) of row J / row J+1
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const int4 d = s_pt[t];
+        const int J = d.z + j0;
+        const int c3 = d.y + i0 + 3;
+        if (static_cast<unsigned>(c3) < static_cast<unsigned>(id + 3)) {
+          const int a = d.x + toff;
+          const unsigned k = static_cast<unsigned>(a) & 3u;
+          const uint8_t* q = dec + static_cast<long long>(a) + static_cast<long long>(k * lpad1);
+          if (static_cast<unsigned>(J) < static_cast<unsigned>(jd))
+            r0 += __byte_perm(__ldg(reinterpret_cast<const unsigned*>(q)), 0u, 0x4140);
+          if (static_cast<unsigned>(J + 1) < static_cast<unsigned>(jd))
+            r1 += __byte_perm(__ldg(reinterpret_cast<const unsigned*>(q + ids)), 0u, 0x4140);
+        }
+      }
+      sum0 += r0 & 0xffffu;   // (ix 0, iy 0): col I,   row J
+      sum2 += r0 >> 16;       // (ix 1, iy 0): col I+1, row J
+      sum1 += r1 & 0xffffu;   // (ix 0, iy 1): col I,   row J+1
+      sum3 += r1 >> 16;       // (ix 1, iy 1)
+    }
+  }
+  const unsigned valid = live ? (1u | (y2 ? 2u : 0u) | (x2 ? 4u : 0u) | ((x2 && y2) ? 8u : 0u)) : 0u;
+  if (live) {
+    atomicAdd(&counters[0], (unsigned long long)__popc(valid));
+    atomicAdd(&counters[1], 1ull);
+  }
+  const int sums[4] = {static_cast<int>(sum0), static_cast<int>(sum1), static_cast<int>(sum2),
+                       static_cast<int>(sum3)};
+  float sc[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) sc[t] = ToScore(st, sums[t], jb.n);
+  if (lv == 0) {
+    if (!live) return;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (!((valid >> t) & 1u) || !(sc[t] > jb.min_score)) continue;
+      const unsigned o = FloatToOrdered(sc[t]);
+      const unsigned old = atomicMax(&lb[si.job], o);
+      if (o >= old) {
+        const int idx = atomicAdd(leaf_count, 1);
+        if (idx < leaf_cap)
+          leaves[idx] = Node{nd.scan, nd.xo + (t >> 1) * s, nd.yo + (t & 1) * s, sc[t]};
+        else
+          *overflow = 1;
+      }
+    }
+    return;
+  }
+  // Survivors are appended row by row (all lanes' children of lattice row 2*j0, then
+  // row 2*j0+1; within a row in lane order, x ascending) with one atomic per warp.
+  const float bound = OrderedToFloat(lb[si.job]);
+  unsigned keep = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    if (((valid >> t) & 1u) && sc[t] > jb.min_score && sc[t] >= bound) keep |= 1u << t;
+  // slot t = 2*ix + iy
+  const unsigned m00 = __ballot_sync(0xffffffffu, keep & 1u), m10 = __ballot_sync(0xffffffffu, keep & 4u);
+  const unsigned m01 = __ballot_sync(0xffffffffu, keep & 2u), m11 = __ballot_sync(0xffffffffu, keep & 8u);
+  const int row0 = __popc(m00) + __popc(m10), row1 = __popc(m01) + __popc(m11);
+  int base = 0;
+  if (lane == 0 && row0 + row1) base = atomicAdd(next_count, row0 + row1);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const unsigned lt = (1u << lane) - 1u;
+  int p = base + __popc(m00 & lt) + __popc(m10 & lt);
+  if (keep & 1u) {
+    if (p < next_cap) next[p] = Node{nd.scan, nd.xo, nd.yo, sc[0]}; else *overflow = 1;
+    ++p;
+  }
+  if (keep & 4u) {
+    if (p < next_cap) next[p] = Node{nd.scan, nd.xo + s, nd.yo, sc[2]}; else *overflow = 1;
+  }
+  p = base + row0 + __popc(m01 & lt) + __popc(m11 & lt);
+  if (keep & 2u) {
+    if (p < next_cap) next[p] = Node{nd.scan, nd.xo, nd.yo + s, sc[1]}; else *overflow = 1;
+    ++p;
+  }
+  if (keep & 8u) {
+    if (p < next_cap) next[p] = Node{nd.scan, nd.xo + s, nd.yo + s, sc[3]}; else *overflow = 1;
   }
 }
 
@@ -712,19 +954,24 @@ csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, dou
   }
   CSM_CUDA(cudaMalloc(&st->d_levels, total));
   for (int l = 0; l < depth; ++l) h.level[l] = st->d_levels + st->level_off[l];
-  // decimated, 4x byte-shifted copy of the top level (the dense lowest-resolution pass)
+  // decimated, 4x byte-shifted copies of every level (dense lowest-resolution pass
+  // and lattice-based branch steps)
   const int top = depth - 1;
-  {
-    const int s = 1 << top;
-    h.dec_id = (h.wx[top] + s - 1) / s;
-    h.dec_jd = (h.wy[top] + s - 1) / s;
-    h.dec_ids = (h.dec_id + 3) / 4 * 4 + 4;
-    const long long bytes = static_cast<long long>(s) * s * h.dec_jd * h.dec_ids;
+  std::vector<size_t> dec_off(depth);
+  size_t dec_total = 0;
+  for (int l = 0; l < depth; ++l) {
+    const int s = 1 << l;
+    h.dec_id[l] = (h.wx[l] + s - 1) / s;
+    h.dec_jd[l] = (h.wy[l] + s - 1) / s;
+    h.dec_ids[l] = (h.dec_id[l] + 3) / 4 * 4 + 4;
+    const long long bytes = static_cast<long long>(s) * s * h.dec_jd[l] * h.dec_ids[l];
     CSM_REQUIRE(bytes < (1LL << 29), "decimated level too large");
-    h.dec_lpad = static_cast<int>((bytes + 32 + 15) / 16 * 16);
-    CSM_CUDA(cudaMalloc(&st->d_dec, 4 * static_cast<size_t>(h.dec_lpad)));
-    h.dec4 = st->d_dec;
+    h.dec_lpad[l] = static_cast<int>((bytes + 32 + 15) / 16 * 16);
+    dec_off[l] = dec_total;
+    dec_total += 4 * static_cast<size_t>(h.dec_lpad[l]);
   }
+  CSM_CUDA(cudaMalloc(&st->d_dec, dec_total));
+  for (int l = 0; l < depth; ++l) h.dec4[l] = st->d_dec + dec_off[l];
   // upload cells + LUT into scratch
   DevBuf& d_cells = ctx->D("stack_cells");
   DevBuf& d_lut = ctx->D("stack_lut");
@@ -746,10 +993,13 @@ csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, dou
                                                     h.wy[l], 1 << (l - 1));
     CSM_LAUNCH_CHECK();
   }
-  k_stack_decimate4<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-      h.level[top], h.wx[top], h.wy[top], top, st->d_dec, h.dec_lpad, h.dec_id, h.dec_jd,
-      h.dec_ids);
-  CSM_LAUNCH_CHECK();
+  for (int l = 0; l < depth; ++l) {
+    k_stack_decimate4<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+        h.level[l], h.wx[l], h.wy[l], l, st->d_dec + dec_off[l], h.dec_lpad[l], h.dec_id[l],
+        h.dec_jd[l], h.dec_ids[l]);
+    CSM_LAUNCH_CHECK();
+  }
+  (void)top;
   CSM_CUDA(cudaMalloc(&st->d, sizeof(StackDev)));
   CSM_CUDA(cudaMemcpyAsync(st->d, &h, sizeof(StackDev), cudaMemcpyHostToDevice, ctx->stream));
   CSM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1120,7 +1370,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     CSM_REQUIRE(stacks[jobs[j].stack_index]->h.depth == depth_max,
                 "all stacks of one batch must share branch_and_bound_depth");
   const int hmax = depth_max - 1;
-  const int kChunk = 1 << 20;
+  const int kChunk = 1 << 22;
   const int kQueueCap = 4 * kChunk;
   const int kLeafCap = 1 << 22;
   const long long top_cap_ll = std::min<long long>(plan.total_slots, 1LL << 30);
@@ -1133,6 +1383,15 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   CSM_TRY(d_q.Reserve(sizeof(Node) * static_cast<size_t>(kQueueCap) * std::max(1, hmax)));
   CSM_TRY(d_leaves.Reserve(sizeof(Node) * static_cast<size_t>(kLeafCap)));
   CSM_TRY(d_best.Reserve(sizeof(Node) * static_cast<size_t>(kLeafCap)));
+  DevBuf& d_scan_cnt = ctx->D("scan_cnt");
+  DevBuf& d_scan_off = ctx->D("scan_off");
+  DevBuf& d_items = ctx->D("work_items");
+  DevBuf& d_sorted = ctx->D("sorted_nodes");
+  CSM_TRY(d_scan_cnt.Reserve(sizeof(int) * 2 * static_cast<size_t>(total_scans)));
+  CSM_TRY(d_scan_off.Reserve(sizeof(int) * 2 * static_cast<size_t>(total_scans)));
+  CSM_TRY(d_items.Reserve(sizeof(WorkItem) * (static_cast<size_t>(kChunk) / 32 + total_scans + 2)));
+  CSM_TRY(d_sorted.Reserve(sizeof(Node) * static_cast<size_t>(kChunk)));
+  static const bool use_lattice = getenv("CSM_NO_LATTICE") == nullptr;
   auto queue_ptr = [&](int h) -> Node* {
     return h == hmax ? d_qtop.as<Node>() : d_q.as<Node>() + static_cast<size_t>(kQueueCap) * h;
   };
@@ -1188,16 +1447,55 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     const int chunk = std::min(qn[h], kChunk);
     const int start = qn[h] - chunk;
     if (h - 1 >= 1) CSM_CUDA(cudaMemsetAsync(ictr + (h - 1), 0, sizeof(int), s));
-    ProfBegin(ctx);
-    k_expand<<<DivUp(static_cast<long long>(chunk) * 32, 256), 256, 0, s>>>(
-        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), queue_ptr(h) + start,
-        chunk, h, d_lb.as<unsigned>(), h - 1 >= 1 ? queue_ptr(h - 1) : nullptr,
-        ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap, d_leaves.as<Node>(), leaf_count, kLeafCap,
-        overflow, ctr);
-    CSM_LAUNCH_CHECK();
-    if (g_profile_on.load()) {
-      ProfStop(ctx);
-      ProfCommit(ctx, "k_expand", prof_scored());
+    // small frontiers: the warp-per-parent kernel has a 34-iteration critical path,
+    // the lattice kernel a 1081-iteration one
+    if (use_lattice && chunk >= 16384) {
+      // group the chunk's parents by scan (counting sort), then one CTA per <= 128
+      // parents of a scan
+      CSM_CUDA(cudaMemsetAsync(d_scan_cnt.p, 0, sizeof(int) * 2 * total_scans, s));
+      int* scan_cnt = d_scan_cnt.as<int>();
+      int* cursor = scan_cnt + total_scans;
+      int* scan_off = d_scan_off.as<int>();
+      int* item_off = scan_off + total_scans;
+      ProfBegin(ctx);
+      k_q_count<<<DivUp(chunk, 256), 256, 0, s>>>(queue_ptr(h) + start, chunk, scan_cnt);
+      CSM_LAUNCH_CHECK();
+      k_q_offsets<<<1, 1024, 0, s>>>(scan_cnt, total_scans, scan_off, item_off, ictr + 24);
+      CSM_LAUNCH_CHECK();
+      k_q_items<<<DivUp(total_scans, 256), 256, 0, s>>>(scan_cnt, scan_off, item_off,
+                                                        total_scans, d_items.as<WorkItem>());
+      CSM_LAUNCH_CHECK();
+      k_q_scatter<<<DivUp(chunk, 256), 256, 0, s>>>(queue_ptr(h) + start, chunk, scan_off, cursor,
+                                                   d_sorted.as<Node>());
+      CSM_LAUNCH_CHECK();
+      if (g_profile_on.load()) {
+        ProfStop(ctx);
+        ProfCommit(ctx, "k_q_sort", chunk);
+      }
+      const int max_items = chunk / 32 + std::min(chunk, total_scans) + 1;
+      ProfBegin(ctx);
+      k_expand_lattice<<<DivUp(max_items, kLatThreads / 32), kLatThreads, 0, s>>>(
+          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_sorted.as<Node>(),
+          d_items.as<WorkItem>(), ictr + 24, h, d_lb.as<unsigned>(),
+          h - 1 >= 1 ? queue_ptr(h - 1) : nullptr, ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap,
+          d_leaves.as<Node>(), leaf_count, kLeafCap, overflow, ctr);
+      CSM_LAUNCH_CHECK();
+      if (g_profile_on.load()) {
+        ProfStop(ctx);
+        ProfCommit(ctx, "k_expand_lattice", prof_scored());
+      }
+    } else {
+      ProfBegin(ctx);
+      k_expand<<<DivUp(static_cast<long long>(chunk) * 32, 256), 256, 0, s>>>(
+          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), queue_ptr(h) + start,
+          chunk, h, d_lb.as<unsigned>(), h - 1 >= 1 ? queue_ptr(h - 1) : nullptr,
+          ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap, d_leaves.as<Node>(), leaf_count, kLeafCap,
+          overflow, ctr);
+      CSM_LAUNCH_CHECK();
+      if (g_profile_on.load()) {
+        ProfStop(ctx);
+        ProfCommit(ctx, "k_expand", prof_scored());
+      }
     }
     qn[h] -= chunk;
     CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));

@@ -15,7 +15,7 @@ constexpr int kMaxDepth = 12;
 struct StackDev {
   const uint8_t* level[kMaxDepth];
   // Decimated ("phase-major") layout of the lowest-resolution level h = depth-1
-  // for the dense top pass.  With s = 2^h the flat array
+  // for the dense passes.  With s = 2^h the flat array
   //   D[((ay * s + ax) * jd + J) * ids + I] = level[h][(s*J + ay) * wx + s*I + ax]
   // (zero outside the wide grid; every row is followed by >= 4 zero bytes) puts
   // the cells that the candidates of one scan lattice need for one scan point
@@ -23,8 +23,10 @@ struct StackDev {
   // k bytes (copy_k[t] = D[t + k]), each dec_lpad bytes long with index 0 at byte
   // 16, so that any 4 consecutive bytes of D can be fetched with one aligned
   // 32-bit load: word(a) = *(u32*)(dec4 + (a & 3) * dec_lpad + 16 + (a & ~3)).
-  const uint8_t* dec4;
-  int dec_lpad, dec_id, dec_jd, dec_ids;
+  // The same layout exists for EVERY level l (lattice stride 2^l): the children of
+  // branch-and-bound nodes of one scan also sit on that scan's lattice.
+  const uint8_t* dec4[kMaxDepth];
+  int dec_lpad[kMaxDepth], dec_id[kMaxDepth], dec_jd[kMaxDepth], dec_ids[kMaxDepth];
   int wx[kMaxDepth], wy[kMaxDepth];
   int nx, ny, depth;
   double resolution, max_x, max_y;
