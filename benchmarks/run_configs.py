@@ -101,7 +101,7 @@ def cfg4(scale):
             jobs[k]["initial_pose"] = truths[ni] + rng.uniform(-1, 1, 3) * [3.0, 3.0, math.radians(15)]
             jobs[k]["min_score"] = min_score
             k += 1
-    sm.match_batch(matchers, clouds, jobs[:8], lin, ang)
+    sm.match_batch(matchers, clouds, jobs, lin, ang)   # warm-up: sizes the device workspace
     sync()
     t0 = time.perf_counter()
     res, st = sm.match_batch(matchers, clouds, jobs, lin, ang)

@@ -11,6 +11,7 @@
 #include "engine2d.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -457,6 +458,24 @@ __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const Scan
   return 1u | (y2 ? 2u : 0u) | (x2 ? 4u : 0u) | ((x2 && y2) ? 8u : 0u);
 }
 
+// Per-job maximum of the lowest-resolution sums (one warp per scan -> atomicMax).
+__global__ void __launch_bounds__(256)
+k_job_best(const ScanInfo* __restrict__ info, const int* __restrict__ top_sum,
+           const long long* __restrict__ scan_slot_base, int total_scans,
+           int* __restrict__ job_best) {
+  const int lane = threadIdx.x & 31;
+  const int sg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (sg >= total_scans) return;
+  const ScanInfo si = info[sg];
+  const int slots = si.nxc * si.nyc;
+  const int* __restrict__ ts = top_sum + scan_slot_base[sg];
+  int best = 0;
+  for (int s = lane; s < slots; s += 32) best = max(best, ts[s]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (lane == 0) atomicMax(&job_best[si.job], best);
+}
+
 // Greedy dives: one warp per scan starts at the scan's best lowest-resolution
 // candidate and follows the best child down to a leaf.  Every leaf score is a
 // valid lower bound of the job's optimum; the maximum over all scans seeds the
@@ -466,6 +485,7 @@ __global__ void __launch_bounds__(256)
 k_dive(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
        const short2* __restrict__ dscan, const int* __restrict__ top_sum,
        const long long* __restrict__ scan_slot_base, int total_scans,
+       const int* __restrict__ job_best, float dive_ratio,
        unsigned* __restrict__ lb, unsigned long long* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
   const int sg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -487,6 +507,9 @@ k_dive(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
     if (ov > best || (ov == best && os < best_slot)) { best = ov; best_slot = os; }
   }
   if (!(ToScore(st, best, jb.n) > jb.min_score)) return;
+  // only scans whose best bound is close to the job's best bound are worth a dive
+  // (any subset keeps the bound valid; this one keeps it tight at a fraction of the cost)
+  if (static_cast<float>(best) < dive_ratio * static_cast<float>(job_best[si.job])) return;
   int h = st.depth - 1;
   const int i = best_slot / si.nyc, jy = best_slot - i * si.nyc;
   int xo = si.min_x + (i << h), yo = si.min_y + (jy << h);
@@ -1131,6 +1154,17 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
                              bool discretize_only, int32_t* out_dscan, int32_t* out_bounds) {
   CSM_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
+  static const bool timing = getenv("CSM_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(
+                        std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_phase = now();
+  auto phase = [&](const char* name) {
+    if (!timing) return;
+    cudaStreamSynchronize(s);
+    const double t = now();
+    fprintf(stderr, "[csm timing] %-14s %8.3f ms\n", name, t - t_phase);
+    t_phase = t;
+  };
   BatchPlan plan;
   plan.jobs.resize(num_jobs);
   plan.search.resize(num_jobs);
@@ -1225,6 +1259,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     }
   }
 
+  phase("host plan");
   // ---- device buffers ----
   DevBuf& d_trig = ctx->D("trig");
   DevBuf& d_jobs = ctx->D("jobs");
@@ -1291,6 +1326,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     return CSM_OK;
   }
 
+  phase("upload+discr");
   // ---- lowest-resolution pass ----
   CSM_TRY(d_top.Reserve(sizeof(int) * plan.total_slots));
   {
@@ -1341,6 +1377,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
                static_cast<double>(c3));
   }
 
+  phase("top pass");
   // ---- greedy dives seed the per-job bound ----
   unsigned long long prof_c0 = 0;
   auto prof_scored = [&]() -> double {  // candidates scored since the last call
@@ -1352,16 +1389,26 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     return d;
   };
   if (g_profile_on.load()) prof_scored();
+  DevBuf& d_job_best = ctx->D("job_best");
+  CSM_TRY(d_job_best.Reserve(sizeof(int) * num_jobs));
+  CSM_CUDA(cudaMemsetAsync(d_job_best.p, 0, sizeof(int) * num_jobs, s));
+  static const float dive_ratio = getenv("CSM_DIVE_RATIO") ? atof(getenv("CSM_DIVE_RATIO")) : 0.97f;
   ProfBegin(ctx);
+  k_job_best<<<DivUp(static_cast<long long>(total_scans) * 32, 256), 256, 0, s>>>(
+      d_info.as<ScanInfo>(), d_top.as<int>(), d_slot_base.as<long long>(), total_scans,
+      d_job_best.as<int>());
+  CSM_LAUNCH_CHECK();
   k_dive<<<DivUp(static_cast<long long>(total_scans) * 32, 256), 256, 0, s>>>(
       d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
-      d_slot_base.as<long long>(), total_scans, d_lb.as<unsigned>(), ctr);
+      d_slot_base.as<long long>(), total_scans, d_job_best.as<int>(), dive_ratio,
+      d_lb.as<unsigned>(), ctr);
   CSM_LAUNCH_CHECK();
   if (g_profile_on.load()) {
     ProfStop(ctx);
     ProfCommit(ctx, "k_dive", prof_scored());
   }
 
+  phase("dives");
   // ---- branch and bound: per-level queues, deepest level first ----
   int depth_max = 0;
   for (int j = 0; j < num_jobs; ++j)
@@ -1522,6 +1569,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     }
   }
 
+  phase("branch&bound");
   // ---- collect the optimal leaves of every job ----
   CSM_CUDA(cudaMemsetAsync(best_count, 0, sizeof(int), s));
   if (h_leaf > 0) {
@@ -1665,6 +1713,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     std::swap(ties[0], ties[w]);
   }
 
+  phase("collect+ties");
   // ---- results ----
   for (int j = 0; j < num_jobs; ++j) {
     csm_result2d& r = results[j];
