@@ -361,11 +361,12 @@ class CudaExecutor3D:
     """One csm_matcher3d per submap (DispatchScanMatcherConstruction,
     constraint_builder_3d.cc:172-198); jobs run through csm_match3d."""
 
-    def __init__(self, options, device=0):
+    def __init__(self, options, device=0, threads=8):
         from . import scan_matching as sm
         self.sm = sm
         self.options = options
         self.device = device
+        self.threads = threads
         self.matchers = {}
         self.stats = {"candidates_scored": 0, "device_ms": 0.0, "searched": 0}
 
@@ -375,8 +376,12 @@ class CudaExecutor3D:
             m.close()
 
     def run(self, jobs, submaps, nodes):
+        """Matchers are built first (one per submap, like the reference's creation
+        tasks); the matches then run from `threads` host threads at once — the library
+        gives every in-flight call its own CUDA stream (the reference's pool threads
+        call Match concurrently too, constraint_builder_3d.cc:104-113)."""
+        from concurrent.futures import ThreadPoolExecutor
         sm, o = self.sm, self.options
-        out = []
         for j in jobs:
             if j.submap_id not in self.matchers:
                 sub = submaps[j.submap_id]
@@ -389,10 +394,20 @@ class CudaExecutor3D:
                         o.linear_xy_search_window, o.linear_z_search_window,
                         o.angular_search_window),
                     device=self.device, grid_size_in_voxels=sub.grid_size_in_voxels)
-            m = self.matchers[j.submap_id]
-            r = m._match(j.full, j.node_pose, j.submap_pose, nodes[j.node_key], j.min_score)
-            self.stats["candidates_scored"] += m.last_stats["candidates_scored"]
-            self.stats["device_ms"] += m.last_stats["device_ms"]
+
+        def one(j):
+            return self.matchers[j.submap_id].match_raw(j.full, j.node_pose, j.submap_pose,
+                                                        nodes[j.node_key], j.min_score)
+
+        if self.threads > 1 and len(jobs) > 1:
+            with ThreadPoolExecutor(max_workers=self.threads) as pool:
+                pairs = list(pool.map(one, jobs))
+        else:
+            pairs = [one(j) for j in jobs]
+        out = []
+        for r, st in pairs:
+            self.stats["candidates_scored"] += st["candidates_scored"]
+            self.stats["device_ms"] += st["device_ms"]
             self.stats["searched"] += 1
             out.append(r)
         return out

@@ -39,21 +39,76 @@ csm_status GetCtx(int device, Ctx** out) {
   return CSM_OK;
 }
 
+static csm_status NewCtx(int device, std::unique_ptr<Ctx>* out) {
+  std::unique_ptr<Ctx> ctx(new Ctx);
+  ctx->device = device;
+  cudaDeviceProp prop;
+  CSM_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  CSM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CSM_CUDA(cudaEventCreate(&ctx->ev0));
+  CSM_CUDA(cudaEventCreate(&ctx->ev1));
+  *out = std::move(ctx);
+  return CSM_OK;
+}
+
+static std::mutex g_lane_mu;
+static std::map<int, std::vector<std::unique_ptr<Ctx>>> g_lanes;
+static std::atomic<unsigned> g_lane_rr{0};
+constexpr size_t kMaxLanes = 8;
+
+csm_status AcquireLane(int device, LaneGuard* out) {
+  {
+    std::lock_guard<std::mutex> lock(g_lane_mu);
+    std::vector<std::unique_ptr<Ctx>>& lanes = g_lanes[device];
+    for (auto& l : lanes) {
+      std::unique_lock<std::mutex> lk(l->mu, std::try_to_lock);
+      if (lk.owns_lock()) {
+        out->lane = l.get();
+        out->lock = std::move(lk);
+        return CSM_OK;
+      }
+    }
+    if (lanes.size() < kMaxLanes) {
+      int count = 0;
+      CSM_CUDA(cudaGetDeviceCount(&count));
+      CSM_REQUIRE(device >= 0 && device < count, "device index out of range");
+      CSM_CUDA(cudaSetDevice(device));
+      std::unique_ptr<Ctx> ctx;
+      CSM_TRY(NewCtx(device, &ctx));
+      lanes.push_back(std::move(ctx));
+      out->lane = lanes.back().get();
+      out->lock = std::unique_lock<std::mutex>(out->lane->mu);
+      return CSM_OK;
+    }
+  }
+  // all lanes busy: wait for one (round robin)
+  Ctx* l;
+  {
+    std::lock_guard<std::mutex> lock(g_lane_mu);
+    std::vector<std::unique_ptr<Ctx>>& lanes = g_lanes[device];
+    l = lanes[g_lane_rr.fetch_add(1) % lanes.size()].get();
+  }
+  out->lane = l;
+  out->lock = std::unique_lock<std::mutex>(l->mu);
+  return CSM_OK;
+}
+
 std::atomic<int> g_profile_on{0};
 struct ProfEntry { double ms = 0; long long launches = 0; double units = 0; };
 static std::mutex g_prof_mu;
 static std::map<std::string, ProfEntry> g_prof;
-static std::map<int, std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
+static std::map<Ctx*, std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev;
 
 void ProfBegin(Ctx* ctx) {
   if (!g_profile_on.load(std::memory_order_relaxed)) return;
   std::lock_guard<std::mutex> lock(g_prof_mu);
-  auto it = g_prof_ev.find(ctx->device);
+  auto it = g_prof_ev.find(ctx);
   if (it == g_prof_ev.end()) {
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    it = g_prof_ev.emplace(ctx->device, std::make_pair(a, b)).first;
+    it = g_prof_ev.emplace(ctx, std::make_pair(a, b)).first;
   }
   cudaEventRecord(it->second.first, ctx->stream);
 }
@@ -61,7 +116,7 @@ void ProfBegin(Ctx* ctx) {
 void ProfStop(Ctx* ctx) {
   if (!g_profile_on.load(std::memory_order_relaxed)) return;
   std::lock_guard<std::mutex> lock(g_prof_mu);
-  auto it = g_prof_ev.find(ctx->device);
+  auto it = g_prof_ev.find(ctx);
   if (it == g_prof_ev.end()) return;
   cudaEventRecord(it->second.second, ctx->stream);
 }
@@ -69,7 +124,7 @@ void ProfStop(Ctx* ctx) {
 void ProfCommit(Ctx* ctx, const char* name, double units) {
   if (!g_profile_on.load(std::memory_order_relaxed)) return;
   std::lock_guard<std::mutex> lock(g_prof_mu);
-  auto it = g_prof_ev.find(ctx->device);
+  auto it = g_prof_ev.find(ctx);
   if (it == g_prof_ev.end()) return;
   cudaEventSynchronize(it->second.second);
   float ms = 0.f;

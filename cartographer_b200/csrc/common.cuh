@@ -106,11 +106,23 @@ struct Ctx {
 
 csm_status GetCtx(int device, Ctx** out);
 
+// Match calls do not serialise on the device-wide context: each call borrows a
+// "lane" — a Ctx of the same device with its own stream, events and workspace —
+// so that several host threads (the reference's pool threads,
+// constraints/constraint_builder_2d.cc:102-111) keep the GPU busy with concurrent
+// matches.  Handles (stacks, clouds, matchers) are read-only during matches and are
+// shared by all lanes.
+struct LaneGuard {
+  Ctx* lane = nullptr;
+  std::unique_lock<std::mutex> lock;
+};
+csm_status AcquireLane(int device, LaneGuard* out);
+
 // Optional per-kernel timing (csm_profile_enable): CUDA events on the engine's
 // own stream around every launch of a named kernel; bench.py reads the totals
 // to compute the roofline numbers of the dominant kernel.
 extern std::atomic<int> g_profile_on;
-void ProfBegin(Ctx* ctx);
+void ProfBegin(Ctx* ctx);  // per-lane events
 void ProfStop(Ctx* ctx);                                   // records the end event
 void ProfCommit(Ctx* ctx, const char* name, double units);  // waits for it and accumulates
 inline void ProfEnd(Ctx* ctx, const char* name, double units) {

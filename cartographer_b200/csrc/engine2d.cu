@@ -1182,7 +1182,8 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     CSM_REQUIRE(jb.cloud_index >= 0 && jb.cloud_index < num_clouds, "cloud index");
     const csm_stack2d* st = stacks[jb.stack_index];
     const csm_cloud* cl = clouds[jb.cloud_index];
-    CSM_REQUIRE(st && cl && st->ctx == ctx && cl->ctx == ctx, "handles must share one device");
+    CSM_REQUIRE(st && cl && st->ctx->device == ctx->device && cl->ctx->device == ctx->device,
+                "handles must share one device");
     const StackDev& h = st->h;
     double lin = linear_window, ang = angular_window;
     double ix = jb.initial_pose[0], iy = jb.initial_pose[1], ith = jb.initial_pose[2];
@@ -1767,8 +1768,9 @@ csm_status csm_match2d_batch(const csm_stack2d* const* stacks, int32_t num_stack
   CSM_REQUIRE(stacks && clouds && jobs && results, "null pointer");
   CSM_REQUIRE(num_jobs >= 1 && num_stacks >= 1 && num_clouds >= 1, "empty batch");
   CSM_REQUIRE(stacks[0] != nullptr, "null stack");
-  Ctx* ctx = stacks[0]->ctx;
-  std::lock_guard<std::mutex> lock(ctx->mu);
+  LaneGuard guard;
+  CSM_TRY(AcquireLane(stacks[0]->ctx->device, &guard));
+  Ctx* ctx = guard.lane;
   if (total) std::memset(total, 0, sizeof(*total));
   // Split into sub-batches so the discrete-scan buffer stays below ~8 GB.
   const long long kMaxPoints = 1LL << 30;
@@ -1844,9 +1846,11 @@ csm_status csm_discretize2d(const csm_stack2d* stack, const float* xyz, int32_t 
     job.full_submap = full_submap;
     if (initial_pose) std::memcpy(job.initial_pose, initial_pose, sizeof(double) * 3);
     const csm_cloud* cl = cloud;
-    std::lock_guard<std::mutex> lock(stack->ctx->mu);
-    st = RunBatch2D(stack->ctx, &stack, 1, &cl, 1, &job, 1, linear_window, angular_window,
-                    nullptr, nullptr, true, discrete_scans, bounds);
+    LaneGuard guard;
+    st = AcquireLane(stack->ctx->device, &guard);
+    if (st == CSM_OK)
+      st = RunBatch2D(guard.lane, &stack, 1, &cl, 1, &job, 1, linear_window, angular_window,
+                      nullptr, nullptr, true, discrete_scans, bounds);
   }
   csm_cloud_destroy(cloud);
   return st;
@@ -1860,8 +1864,9 @@ csm_status csm_score_candidates2d(const csm_stack2d* stack, int32_t level,
   CSM_REQUIRE(level >= 0 && level < stack->h.depth, "level out of range");
   CSM_REQUIRE(num_scans >= 1 && n >= 1 && num_candidates >= 0, "sizes");
   if (num_candidates == 0) return CSM_OK;
-  Ctx* ctx = stack->ctx;
-  std::lock_guard<std::mutex> lock(ctx->mu);
+  LaneGuard guard;
+  CSM_TRY(AcquireLane(stack->ctx->device, &guard));
+  Ctx* ctx = guard.lane;
   CSM_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   // one synthetic job whose discrete scans are supplied by the caller

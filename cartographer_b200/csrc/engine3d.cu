@@ -840,9 +840,8 @@ csm_status csm_rotational_match3d(const float* submap_hist, const float* hist, i
 
 // GenerateDiscreteScans up to (not including) DiscretizeScan (:246-295): angles,
 // rotational scores (device), surviving scan poses.
-static csm_status PlanScans(const csm_matcher3d* m, const csm_node3d* node, const HostSearch3& sp,
-                            ScanPlan* plan) {
-  Ctx* ctx = m->ctx;
+static csm_status PlanScans(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node,
+                            const HostSearch3& sp, ScanPlan* plan) {
   cudaStream_t s = ctx->stream;
   const float resolution = m->hs.resolution;
   float max_scan_range = 3.f * resolution;
@@ -949,19 +948,19 @@ static csm_status MakeSearch3(const csm_matcher3d* m, const csm_node3d* node,
   return CSM_OK;
 }
 
-static csm_status Run3D(const csm_matcher3d* m, const csm_node3d* node, const double node_pose[7],
+static csm_status Run3D(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node,
+                        const double node_pose[7],
                         const double submap_pose[7], int full, float min_score,
                         csm_result3d* result, csm_stats* stats, bool discretize_only,
                         int32_t* out_num_scans, int32_t* out_cells, float* out_poses,
                         float* out_rot) {
-  Ctx* ctx = m->ctx;
   CSM_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   HostSearch3 sp;
   CSM_TRY(MakeSearch3(m, node, node_pose, submap_pose, full, &sp));
   CSM_CUDA(cudaEventRecord(ctx->ev0, s));
   ScanPlan plan;
-  CSM_TRY(PlanScans(m, node, sp, &plan));
+  CSM_TRY(PlanScans(ctx, m, node, sp, &plan));
   const int S = static_cast<int>(plan.scans.size());
   if (out_num_scans) *out_num_scans = S;
   if (result) {
@@ -1253,9 +1252,10 @@ csm_status csm_match3d(const csm_matcher3d* m, const csm_node3d* node, const dou
   CSM_REQUIRE(node->num_high >= 1 && node->high_resolution_point_cloud, "high-resolution cloud");
   CSM_REQUIRE(node->num_low >= 0 && (node->num_low == 0 || node->low_resolution_point_cloud),
               "low-resolution cloud");
-  std::lock_guard<std::mutex> lock(m->ctx->mu);
-  return Run3D(m, node, node_pose, submap_pose, full, min_score, result, stats, false, nullptr,
-               nullptr, nullptr, nullptr);
+  LaneGuard guard;
+  CSM_TRY(AcquireLane(m->ctx->device, &guard));
+  return Run3D(guard.lane, m, node, node_pose, submap_pose, full, min_score, result, stats, false,
+               nullptr, nullptr, nullptr, nullptr);
 }
 
 csm_status csm_discretize3d(const csm_matcher3d* m, const csm_node3d* node,
@@ -1263,9 +1263,10 @@ csm_status csm_discretize3d(const csm_matcher3d* m, const csm_node3d* node,
                             int32_t* num_scans, int32_t* cells, float* poses, float* rot) {
   CSM_REQUIRE(m && node && node_pose && submap_pose && num_scans, "null pointer");
   CSM_REQUIRE(node->num_high >= 1 && node->high_resolution_point_cloud, "high-resolution cloud");
-  std::lock_guard<std::mutex> lock(m->ctx->mu);
-  return Run3D(m, node, node_pose, submap_pose, full, 0.f, nullptr, nullptr, true, num_scans,
-               cells, poses, rot);
+  LaneGuard guard;
+  CSM_TRY(AcquireLane(m->ctx->device, &guard));
+  return Run3D(guard.lane, m, node, node_pose, submap_pose, full, 0.f, nullptr, nullptr, true,
+               num_scans, cells, poses, rot);
 }
 
 }  // extern "C"

@@ -116,9 +116,9 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
                                      double pose_estimate[3], csm_stats* stats) {
   CSM_REQUIRE(cells && xyz && initial_pose && score && pose_estimate, "null pointer");  // :121
   CSM_REQUIRE(nx >= 1 && ny >= 1 && n >= 1 && resolution > 0., "sizes");
-  Ctx* ctx;
-  CSM_TRY(GetCtx(device, &ctx));
-  std::lock_guard<std::mutex> lock(ctx->mu);
+  LaneGuard guard;
+  CSM_TRY(AcquireLane(device, &guard));
+  Ctx* ctx = guard.lane;
   CSM_CUDA(cudaSetDevice(device));
   cudaStream_t s = ctx->stream;
 

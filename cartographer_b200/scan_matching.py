@@ -305,6 +305,14 @@ class FastCorrelativeScanMatcher3D:
     __del__ = close
 
     def _match(self, full, node_pose, submap_pose, constant_data, min_score):
+        res, self.last_stats = self.match_raw(full, node_pose, submap_pose, constant_data,
+                                              min_score)
+        return res
+
+    def match_raw(self, full, node_pose, submap_pose, constant_data, min_score):
+        """Thread-safe form (no state on self): -> (Result dict or None, stats dict).
+        Like the reference's const Match*, it may be called from several threads at once;
+        concurrent calls run on separate CUDA streams inside the library."""
         holder = _NodeHolder(constant_data)
         npose = np.ascontiguousarray(node_pose, np.float64)
         spose = np.ascontiguousarray(submap_pose, np.float64)
@@ -313,15 +321,13 @@ class FastCorrelativeScanMatcher3D:
         check(lib().csm_match3d(self._h, C.byref(holder.c), ptr(npose, C.c_double),
                                 ptr(spose, C.c_double), C.c_int32(int(full)),
                                 C.c_float(min_score), C.byref(res), C.byref(stats)))
-        self.last_stats = stats.as_dict()
-        self.last_result = res
         if not res.found:
-            return None
+            return None, stats.as_dict()
         return dict(score=np.float32(res.score), pose_estimate=np.array(res.pose_estimate[:]),
                     rotational_score=np.float32(res.rotational_score),
                     low_resolution_score=np.float32(res.low_resolution_score),
                     best_scan_index=res.best_scan_index, best_offset=tuple(res.best_offset[:]),
-                    leaves_tied=res.leaves_tied)
+                    leaves_tied=res.leaves_tied), stats.as_dict()
 
     def Match(self, global_node_pose, global_submap_pose, constant_data, min_score):
         """-> Result dict or None (nullptr), fast_correlative_scan_matcher_3d.cc:127-144.
