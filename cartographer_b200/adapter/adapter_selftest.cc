@@ -42,5 +42,42 @@ int main() {
               pose.translation().x(), pose.translation().y(), pose.rotation().angle());
   if (!found || std::fabs(pose.translation().x()) > 0.051 || std::fabs(pose.translation().y()) > 0.051)
     return 1;
+
+  // ---- 3D: the reference's 12-point axis cloud inserted at a known pose ----
+  mapping::HybridGrid hybrid(0.05f);
+  sensor::PointCloud cloud3;
+  const float tx = 0.2f, ty = -0.15f, tz = 0.1f;
+  for (int axis = 0; axis < 3; ++axis)
+    for (float d = 4.f; d <= 5.5f; d += 0.5f) {
+      float p[3] = {0.f, 0.f, 0.f};
+      p[axis] = d;
+      cloud3.push_back({{{p[0], p[1], p[2]}}});
+      hybrid.Set(static_cast<int>(std::lround((p[0] + tx) / 0.05f)),
+                 static_cast<int>(std::lround((p[1] + ty) / 0.05f)),
+                 static_cast<int>(std::lround((p[2] + tz) / 0.05f)), 24575 /* p ~ 0.7 */);
+    }
+  mapping::scan_matching::proto::FastCorrelativeScanMatcherOptions3D o3;
+  o3.o.branch_and_bound_depth = 6;
+  o3.o.full_resolution_depth = 6;
+  o3.o.min_rotational_score = 0.1;
+  o3.o.min_low_resolution_score = 0.15;
+  o3.o.linear_xy_search_window = 0.8;
+  o3.o.linear_z_search_window = 0.8;
+  o3.o.angular_search_window = 0.3;
+  const std::vector<float> histogram(10, 0.f);
+  mapping::scan_matching::FastCorrelativeScanMatcher3D matcher3(hybrid, &hybrid, &histogram, o3);
+  mapping::TrajectoryNodeData data;
+  data.high_resolution_point_cloud = cloud3;
+  data.low_resolution_point_cloud = cloud3;
+  data.rotational_scan_matcher_histogram = histogram;
+  const auto result = matcher3.Match(transform::Rigid3d(), transform::Rigid3d(), data, 0.1f);
+  if (!result) { std::printf("adapter_selftest: 3D match failed\n"); return 1; }
+  std::printf("adapter_selftest: 3D score=%.4f t=(%.3f, %.3f, %.3f) low=%.3f\n", result->score,
+              result->pose_estimate.translation().x(), result->pose_estimate.translation().y(),
+              result->pose_estimate.translation().z(), result->low_resolution_score);
+  if (std::fabs(result->pose_estimate.translation().x() - tx) > 0.051 ||
+      std::fabs(result->pose_estimate.translation().y() - ty) > 0.051 ||
+      std::fabs(result->pose_estimate.translation().z() - tz) > 0.051)
+    return 1;
   return 0;
 }

@@ -44,6 +44,57 @@ class PointCloud {
 };
 }  // namespace sensor
 
+namespace transform {
+// transform/rigid_transform.h:116-196 (Rigid3<double>) and Eigen::Quaterniond as used
+// in the 3D matcher's signatures.
+struct Quaterniond {
+  double w_, x_, y_, z_;
+  double w() const { return w_; } double x() const { return x_; }
+  double y() const { return y_; } double z() const { return z_; }
+};
+class Rigid3d {
+ public:
+  struct Vector { double v[3]; double x() const { return v[0]; } double y() const { return v[1]; } double z() const { return v[2]; } };
+  Rigid3d() : t_{{0., 0., 0.}}, q_{1., 0., 0., 0.} {}
+  Rigid3d(const Vector& t, const Quaterniond& q) : t_(t), q_(q) {}
+  const Vector& translation() const { return t_; }
+  const Quaterniond& rotation() const { return q_; }
+ private:
+  Vector t_;
+  Quaterniond q_;
+};
+}  // namespace transform
+
+namespace mapping {
+// mapping/3d/hybrid_grid.h:468-526: what the adapter needs is iteration over the
+// non-zero voxels (HybridGrid::Iterator / begin()-end(), :413-460) and resolution().
+class HybridGrid {
+ public:
+  struct Voxel { int x, y, z; uint16_t value; };
+  explicit HybridGrid(float resolution) : resolution_(resolution) {}
+  float resolution() const { return resolution_; }
+  int grid_size() const { return grid_size_; }
+  void Set(int x, int y, int z, uint16_t value) {
+    voxels_.push_back(Voxel{x, y, z, value});
+    while (x < -(grid_size_ >> 1) || x >= (grid_size_ >> 1) || y < -(grid_size_ >> 1) ||
+           y >= (grid_size_ >> 1) || z < -(grid_size_ >> 1) || z >= (grid_size_ >> 1))
+      grid_size_ <<= 1;
+  }
+  const std::vector<Voxel>& voxels() const { return voxels_; }
+ private:
+  float resolution_;
+  int grid_size_ = 128;
+  std::vector<Voxel> voxels_;
+};
+// mapping/trajectory_node.h:45-63 (the fields the 3D matcher reads).
+struct TrajectoryNodeData {
+  transform::Quaterniond gravity_alignment{1., 0., 0., 0.};
+  sensor::PointCloud high_resolution_point_cloud;
+  sensor::PointCloud low_resolution_point_cloud;
+  std::vector<float> rotational_scan_matcher_histogram;   // Eigen::VectorXf
+};
+}  // namespace mapping
+
 namespace mapping {
 // mapping/2d/xy_index.h:34-45, mapping/2d/map_limits.h:40-95.
 struct CellLimits { int num_x_cells = 0; int num_y_cells = 0; };
@@ -105,6 +156,21 @@ class RealTimeCorrelativeScanMatcherOptions {
   void set_rotation_delta_cost_weight(double v) { wr_ = v; }
  private:
   double lin_ = 0., ang_ = 0., wt_ = 0., wr_ = 0.;
+};
+// proto/scan_matching/fast_correlative_scan_matcher_options_3d.proto
+class FastCorrelativeScanMatcherOptions3D {
+ public:
+  int branch_and_bound_depth() const { return o.branch_and_bound_depth; }
+  int full_resolution_depth() const { return o.full_resolution_depth; }
+  double min_rotational_score() const { return o.min_rotational_score; }
+  double min_low_resolution_score() const { return o.min_low_resolution_score; }
+  double linear_xy_search_window() const { return o.linear_xy_search_window; }
+  double linear_z_search_window() const { return o.linear_z_search_window; }
+  double angular_search_window() const { return o.angular_search_window; }
+  struct { int branch_and_bound_depth = 8, full_resolution_depth = 3;
+           double min_rotational_score = 0.77, min_low_resolution_score = 0.55,
+                  linear_xy_search_window = 5., linear_z_search_window = 1.,
+                  angular_search_window = 0.2617993877991494; } o;
 };
 }  // namespace proto
 }  // namespace scan_matching

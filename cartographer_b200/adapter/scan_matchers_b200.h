@@ -17,6 +17,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <vector>
 
 #include "../../include/csm_abi.h"
@@ -142,6 +143,109 @@ class RealTimeCorrelativeScanMatcher2D {
   const proto::RealTimeCorrelativeScanMatcherOptions options_;
   int device_;
 };
+
+#ifndef CSM_ADAPTER_REAL_CARTOGRAPHER
+// fast_correlative_scan_matcher_3d.h:66-101.  (Inside a Cartographer checkout the
+// same body is used with HybridGrid::Iterator for the voxel walk, Eigen::VectorXf
+// for the histograms and TrajectoryNode::Data — see INTEGRATION.md §3.)
+class FastCorrelativeScanMatcher3D {
+ public:
+  struct Result {  // fast_correlative_scan_matcher_3d.h:68-73
+    float score;
+    transform::Rigid3d pose_estimate;
+    float rotational_score;
+    float low_resolution_score;
+  };
+
+  FastCorrelativeScanMatcher3D(const HybridGrid& hybrid_grid,
+                               const HybridGrid* low_resolution_hybrid_grid,
+                               const std::vector<float>* rotational_scan_matcher_histogram,
+                               const proto::FastCorrelativeScanMatcherOptions3D& options,
+                               int device = 0) {
+    std::vector<int32_t> hi_idx, lo_idx;
+    std::vector<uint16_t> hi_val, lo_val;
+    Flatten(hybrid_grid, &hi_idx, &hi_val);
+    Flatten(*low_resolution_hybrid_grid, &lo_idx, &lo_val);
+    csm_options3d o;
+    o.branch_and_bound_depth = options.branch_and_bound_depth();
+    o.full_resolution_depth = options.full_resolution_depth();
+    o.min_rotational_score = options.min_rotational_score();
+    o.min_low_resolution_score = options.min_low_resolution_score();
+    o.linear_xy_search_window = options.linear_xy_search_window();
+    o.linear_z_search_window = options.linear_z_search_window();
+    o.angular_search_window = options.angular_search_window();
+    b200_internal::Check(csm_matcher3d_create(
+        hi_idx.data(), hi_val.data(), static_cast<int64_t>(hi_val.size()),
+        hybrid_grid.resolution(), hybrid_grid.grid_size(), lo_idx.data(), lo_val.data(),
+        static_cast<int64_t>(lo_val.size()), low_resolution_hybrid_grid->resolution(),
+        rotational_scan_matcher_histogram->data(),
+        static_cast<int32_t>(rotational_scan_matcher_histogram->size()), &o, device, &matcher_));
+  }
+  ~FastCorrelativeScanMatcher3D() { csm_matcher3d_destroy(matcher_); }
+  FastCorrelativeScanMatcher3D(const FastCorrelativeScanMatcher3D&) = delete;
+  FastCorrelativeScanMatcher3D& operator=(const FastCorrelativeScanMatcher3D&) = delete;
+
+  std::unique_ptr<Result> Match(const transform::Rigid3d& global_node_pose,
+                                const transform::Rigid3d& global_submap_pose,
+                                const TrajectoryNodeData& constant_data, float min_score) const {
+    return Run(0, global_node_pose, global_submap_pose, constant_data, min_score);
+  }
+  std::unique_ptr<Result> MatchFullSubmap(const transform::Quaterniond& global_node_rotation,
+                                          const transform::Quaterniond& global_submap_rotation,
+                                          const TrajectoryNodeData& constant_data,
+                                          float min_score) const {
+    return Run(1, transform::Rigid3d({{0., 0., 0.}}, global_node_rotation),
+               transform::Rigid3d({{0., 0., 0.}}, global_submap_rotation), constant_data,
+               min_score);
+  }
+
+ private:
+  static void Flatten(const HybridGrid& grid, std::vector<int32_t>* idx,
+                      std::vector<uint16_t>* val) {
+    for (const auto& v : grid.voxels()) {
+      idx->push_back(v.x);
+      idx->push_back(v.y);
+      idx->push_back(v.z);
+      val->push_back(v.value);
+    }
+  }
+  static void Pose7(const transform::Rigid3d& p, double out[7]) {
+    out[0] = p.translation().x(); out[1] = p.translation().y(); out[2] = p.translation().z();
+    out[3] = p.rotation().w(); out[4] = p.rotation().x(); out[5] = p.rotation().y();
+    out[6] = p.rotation().z();
+  }
+  std::unique_ptr<Result> Run(int full, const transform::Rigid3d& node_pose,
+                              const transform::Rigid3d& submap_pose,
+                              const TrajectoryNodeData& data, float min_score) const {
+    const std::vector<float> hi = b200_internal::Flatten(data.high_resolution_point_cloud);
+    const std::vector<float> lo = b200_internal::Flatten(data.low_resolution_point_cloud);
+    csm_node3d node;
+    node.high_resolution_point_cloud = hi.data();
+    node.num_high = static_cast<int32_t>(data.high_resolution_point_cloud.size());
+    node.low_resolution_point_cloud = lo.data();
+    node.num_low = static_cast<int32_t>(data.low_resolution_point_cloud.size());
+    node.rotational_scan_matcher_histogram = data.rotational_scan_matcher_histogram.data();
+    node.histogram_size = static_cast<int32_t>(data.rotational_scan_matcher_histogram.size());
+    node.gravity_alignment[0] = data.gravity_alignment.w();
+    node.gravity_alignment[1] = data.gravity_alignment.x();
+    node.gravity_alignment[2] = data.gravity_alignment.y();
+    node.gravity_alignment[3] = data.gravity_alignment.z();
+    double np[7], sp[7];
+    Pose7(node_pose, np);
+    Pose7(submap_pose, sp);
+    csm_result3d r;
+    b200_internal::Check(csm_match3d(matcher_, &node, np, sp, full, min_score, &r, nullptr));
+    if (!r.found) return nullptr;  // fast_correlative_scan_matcher_3d.cc:197
+    return std::unique_ptr<Result>(new Result{
+        r.score,
+        transform::Rigid3d({{r.pose_estimate[0], r.pose_estimate[1], r.pose_estimate[2]}},
+                           transform::Quaterniond{r.pose_estimate[3], r.pose_estimate[4],
+                                                  r.pose_estimate[5], r.pose_estimate[6]}),
+        r.rotational_score, r.low_resolution_score});
+  }
+  csm_matcher3d* matcher_ = nullptr;
+};
+#endif  // !CSM_ADAPTER_REAL_CARTOGRAPHER
 
 }  // namespace scan_matching
 }  // namespace mapping

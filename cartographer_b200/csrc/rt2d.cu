@@ -17,6 +17,8 @@ namespace csm {
 struct RtParams {
   int nx, ny, n, num_scans, lin, width;  // width = 2 * lin + 1
   float k_scale, cost_bias, max_cost, min_probability;
+  // TSDF variant: value -> tsd / weight (tsd_value_converter.cc:24-34)
+  float tsd_scale, tsd_bias, min_tsd, w_scale, w_bias, truncation;
 };
 
 // mapping/2d/probability_grid.cc:78-82 + probability_values.cc:29-37
@@ -52,6 +54,41 @@ k_rt_score(const uint16_t* __restrict__ cells, const short2* __restrict__ dscan,
   }
   float score = __fdiv_rn(sum, __int2float_rn(P.n));
   // candidate.score *= exp(...): float *= double  (:170-174)
+  score = __double2float_rn(__dmul_rn(static_cast<double>(score), weight[c]));
+  scores[c] = score;
+}
+
+// TSDF variant (:38-59): score = sum(normalized_tsd * weight) / sum(weight), both sums
+// ordered float sums over the scan points.
+__global__ void __launch_bounds__(128)
+k_rt_score_tsdf(const uint16_t* __restrict__ tsd_cells, const uint16_t* __restrict__ w_cells,
+                const short2* __restrict__ dscan, const double* __restrict__ weight, RtParams P,
+                float* __restrict__ scores) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_scan = P.width * P.width;
+  if (c >= P.num_scans * per_scan) return;
+  const int scan = c / per_scan;
+  const int r = c - scan * per_scan;
+  const int xo = -P.lin + r / P.width;
+  const int yo = -P.lin + r % P.width;
+  const short2* __restrict__ pts = dscan + static_cast<size_t>(scan) * P.n;
+  float candidate_score = 0.f, summed_weight = 0.f;
+  for (int p = 0; p < P.n; ++p) {
+    const short2 q = pts[p];
+    const int x = q.x + xo, y = q.y + yo;
+    float tsd = P.min_tsd, w = 0.f;  // outside the limits (tsdf_2d.cc:94-95)
+    if (static_cast<unsigned>(x) < static_cast<unsigned>(P.nx) &&
+        static_cast<unsigned>(y) < static_cast<unsigned>(P.ny)) {
+      const size_t flat = static_cast<size_t>(y) * P.nx + x;
+      const int tv = __ldg(tsd_cells + flat) & 0x7fff, wv = __ldg(w_cells + flat) & 0x7fff;
+      tsd = tv == 0 ? P.min_tsd : __fadd_rn(__fmul_rn(__int2float_rn(tv), P.tsd_scale), P.tsd_bias);
+      w = wv == 0 ? 0.f : __fadd_rn(__fmul_rn(__int2float_rn(wv), P.w_scale), P.w_bias);
+    }
+    const float normalized = __fdiv_rn(__fsub_rn(P.truncation, fabsf(tsd)), P.truncation);
+    candidate_score = __fadd_rn(candidate_score, __fmul_rn(normalized, w));
+    summed_weight = __fadd_rn(summed_weight, w);
+  }
+  float score = summed_weight == 0.f ? 0.f : __fdiv_rn(candidate_score, summed_weight);
   score = __double2float_rn(__dmul_rn(static_cast<double>(score), weight[c]));
   scores[c] = score;
 }
@@ -108,12 +145,12 @@ inline HV3 HRotate(float qw, const HV3& qv, const HV3& v) {
 }
 }  // namespace
 
-extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t ny,
-                                     double resolution, double max_x, double max_y,
-                                     const float* xyz, int32_t n, const double initial_pose[3],
-                                     double linear_window, double angular_window, double w_t,
-                                     double w_r, int32_t device, double* score,
-                                     double pose_estimate[3], csm_stats* stats) {
+static csm_status RtMatch(const uint16_t* cells, const uint16_t* weight_cells, float truncation,
+                          float max_weight, int32_t nx, int32_t ny, double resolution,
+                          double max_x, double max_y, const float* xyz, int32_t n,
+                          const double initial_pose[3], double linear_window,
+                          double angular_window, double w_t, double w_r, int32_t device,
+                          double* score, double pose_estimate[3], csm_stats* stats) {
   CSM_REQUIRE(cells && xyz && initial_pose && score && pose_estimate, "null pointer");  // :121
   CSM_REQUIRE(nx >= 1 && ny >= 1 && n >= 1 && resolution > 0., "sizes");
   LaneGuard guard;
@@ -178,6 +215,7 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
   sd.max_y = max_y;
   DevBuf& d_sd = ctx->D("rt_stack");
   DevBuf& d_cells = ctx->D("rt_cells");
+  DevBuf& d_wcells = ctx->D("rt_wcells");
   DevBuf& d_xyz = ctx->D("rt_xyz");
   DevBuf& d_trig = ctx->D("rt_trig");
   DevBuf& d_w = ctx->D("rt_weight");
@@ -190,6 +228,7 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
   const size_t ncell = static_cast<size_t>(nx) * ny;
   CSM_TRY(d_sd.Reserve(sizeof(StackDev)));
   CSM_TRY(d_cells.Reserve(ncell * 2));
+  if (weight_cells) CSM_TRY(d_wcells.Reserve(ncell * 2));
   CSM_TRY(d_xyz.Reserve(rot.size() * 4));
   CSM_TRY(d_trig.Reserve(trig.size() * 4));
   CSM_TRY(d_w.Reserve(weight.size() * 8));
@@ -215,6 +254,8 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
   CSM_CUDA(cudaEventRecord(ctx->ev0, s));
   CSM_CUDA(cudaMemcpyAsync(d_sd.p, &sd, sizeof(sd), cudaMemcpyHostToDevice, s));
   CSM_CUDA(cudaMemcpyAsync(d_cells.p, cells, ncell * 2, cudaMemcpyHostToDevice, s));
+  if (weight_cells)
+    CSM_CUDA(cudaMemcpyAsync(d_wcells.p, weight_cells, ncell * 2, cudaMemcpyHostToDevice, s));
   CSM_CUDA(cudaMemcpyAsync(d_xyz.p, rot.data(), rot.size() * 4, cudaMemcpyHostToDevice, s));
   CSM_CUDA(cudaMemcpyAsync(d_trig.p, trig.data(), trig.size() * 4, cudaMemcpyHostToDevice, s));
   CSM_CUDA(cudaMemcpyAsync(d_w.p, weight.data(), weight.size() * 8, cudaMemcpyHostToDevice, s));
@@ -242,8 +283,22 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
     P.max_cost = kMaxCost;
     P.min_probability = kMinProbability;
   }
-  k_rt_score<<<static_cast<int>((num_cand + 127) / 128), 128, 0, s>>>(
-      d_cells.as<uint16_t>(), d_dscan.as<short2>(), d_w.as<double>(), P, d_scores.as<float>());
+  if (weight_cells) {
+    // TSDValueConverter tables (tsd_value_converter.cc:24-34, value_conversion_tables.cc:29-37)
+    const float min_tsd = -truncation;
+    P.tsd_scale = (truncation - min_tsd) / 32766.f;
+    P.tsd_bias = min_tsd - P.tsd_scale;
+    P.min_tsd = min_tsd;
+    P.w_scale = (max_weight - 0.f) / 32766.f;
+    P.w_bias = 0.f - P.w_scale;
+    P.truncation = truncation;
+    k_rt_score_tsdf<<<static_cast<int>((num_cand + 127) / 128), 128, 0, s>>>(
+        d_cells.as<uint16_t>(), d_wcells.as<uint16_t>(), d_dscan.as<short2>(), d_w.as<double>(),
+        P, d_scores.as<float>());
+  } else {
+    k_rt_score<<<static_cast<int>((num_cand + 127) / 128), 128, 0, s>>>(
+        d_cells.as<uint16_t>(), d_dscan.as<short2>(), d_w.as<double>(), P, d_scores.as<float>());
+  }
   CSM_LAUNCH_CHECK();
   int* d_best = reinterpret_cast<int*>(d_misc.as<char>() + 32);
   k_first_argmax<<<1, 1024, 0, s>>>(d_scores.as<float>(), static_cast<int>(num_cand), d_best);
@@ -275,3 +330,31 @@ extern "C" csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t 
   }
   return CSM_OK;
 }
+
+extern "C" {
+
+csm_status csm_rt_match2d(const uint16_t* cells, int32_t nx, int32_t ny, double resolution,
+                          double max_x, double max_y, const float* xyz, int32_t n,
+                          const double initial_pose[3], double linear_window,
+                          double angular_window, double w_t, double w_r, int32_t device,
+                          double* score, double pose_estimate[3], csm_stats* stats) {
+  return RtMatch(cells, nullptr, 0.f, 0.f, nx, ny, resolution, max_x, max_y, xyz, n,
+                 initial_pose, linear_window, angular_window, w_t, w_r, device, score,
+                 pose_estimate, stats);
+}
+
+csm_status csm_rt_match2d_tsdf(const uint16_t* tsd_cells, const uint16_t* weight_cells,
+                               int32_t nx, int32_t ny, double resolution, double max_x,
+                               double max_y, float truncation_distance, float max_weight,
+                               const float* xyz, int32_t n, const double initial_pose[3],
+                               double linear_window, double angular_window, double w_t,
+                               double w_r, int32_t device, double* score,
+                               double pose_estimate[3], csm_stats* stats) {
+  CSM_REQUIRE(weight_cells != nullptr, "null weight cells");
+  CSM_REQUIRE(truncation_distance > 0.f && max_weight > 0.f, "TSDF parameters");
+  return RtMatch(tsd_cells, weight_cells, truncation_distance, max_weight, nx, ny, resolution,
+                 max_x, max_y, xyz, n, initial_pose, linear_window, angular_window, w_t, w_r,
+                 device, score, pose_estimate, stats);
+}
+
+}  // extern "C"

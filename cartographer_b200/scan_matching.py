@@ -192,6 +192,43 @@ class RealTimeCorrelativeScanMatcher2D:
         return score.value, pose
 
 
+@dataclass
+class TSDF2DSpec:
+    """Flat record of a TSDF2D grid (mapping/internal/2d/tsdf_2d.h): tsd and weight
+    cells (uint16 [num_y, num_x]) plus the TSDValueConverter parameters."""
+    tsd_cells: np.ndarray
+    weight_cells: np.ndarray
+    resolution: float
+    max_x: float
+    max_y: float
+    truncation_distance: float
+    max_weight: float
+
+
+def _rt_match_tsdf(self, initial_pose_estimate, point_cloud, grid):
+    xyz = _f32(point_cloud)
+    tsd = np.ascontiguousarray(grid.tsd_cells, dtype=np.uint16)
+    wgt = np.ascontiguousarray(grid.weight_cells, dtype=np.uint16)
+    ip = np.ascontiguousarray(initial_pose_estimate, dtype=np.float64)
+    pose = np.zeros(3, np.float64)
+    score = C.c_double(0.0)
+    stats = CsmStats()
+    o = self.options
+    check(lib().csm_rt_match2d_tsdf(
+        ptr(tsd, C.c_uint16), ptr(wgt, C.c_uint16), C.c_int32(tsd.shape[1]),
+        C.c_int32(tsd.shape[0]), C.c_double(grid.resolution), C.c_double(grid.max_x),
+        C.c_double(grid.max_y), C.c_float(grid.truncation_distance), C.c_float(grid.max_weight),
+        ptr(xyz, C.c_float), C.c_int32(len(xyz)), ptr(ip, C.c_double),
+        C.c_double(o.linear_search_window), C.c_double(o.angular_search_window),
+        C.c_double(o.translation_delta_cost_weight), C.c_double(o.rotation_delta_cost_weight),
+        C.c_int32(self.device), C.byref(score), ptr(pose, C.c_double), C.byref(stats)))
+    self.last_stats = stats.as_dict()
+    return score.value, pose
+
+
+RealTimeCorrelativeScanMatcher2D.MatchTSDF = _rt_match_tsdf
+
+
 def kernel_launch_count():
     return int(lib().csm_kernel_launch_count())
 

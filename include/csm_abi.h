@@ -173,6 +173,20 @@ csm_status csm_rt_match2d(const uint16_t* cells, int32_t num_x_cells, int32_t nu
                           double rotation_delta_cost_weight, int32_t device, double* score,
                           double pose_estimate[3], csm_stats* stats /* may be NULL */);
 
+/* Same for a TSDF2D grid (real_time_correlative_scan_matcher_2d.cc:38-59,160-166):
+ * tsd_cells = Grid2D::correspondence_cost_cells(), weight_cells = TSDF2D::weight_cells_
+ * (mapping/internal/2d/tsdf_2d.h), both uint16 with flat index num_x*y + x;
+ * truncation_distance / max_weight are the TSDValueConverter parameters. */
+csm_status csm_rt_match2d_tsdf(const uint16_t* tsd_cells, const uint16_t* weight_cells,
+                               int32_t num_x_cells, int32_t num_y_cells, double resolution,
+                               double max_x, double max_y, float truncation_distance,
+                               float max_weight, const float* xyz, int32_t num_points,
+                               const double initial_pose[3], double linear_search_window,
+                               double angular_search_window,
+                               double translation_delta_cost_weight,
+                               double rotation_delta_cost_weight, int32_t device, double* score,
+                               double pose_estimate[3], csm_stats* stats /* may be NULL */);
+
 /* ==== 3D: FastCorrelativeScanMatcher3D ====================================== */
 /* A HybridGrid crosses the ABI in the flat form of proto::HybridGrid
  * (mapping/proto/hybrid_grid.proto:19-28): voxel indices (n x {x,y,z} int32, origin

@@ -465,4 +465,78 @@ void RealTimeCorrelativeScanMatcher2D::ScoreCandidates(
   }
 }
 
+// ---- TSDF variant ---------------------------------------------------------------
+TSDF2D::TSDF2D(const MapLimits& l, float truncation, float max_w)
+    : limits(l),
+      truncation_distance(truncation),
+      max_weight(max_w),
+      tsd_cells(static_cast<size_t>(l.cell_limits.num_x_cells) * l.cell_limits.num_y_cells, 0),
+      weight_cells(tsd_cells.size(), 0),
+      // tsd_value_converter.cc:31-34: GetConversionTable(min_tsd, min_tsd, max_tsd) and
+      // GetConversionTable(min_weight, min_weight, max_weight)
+      value_to_tsd(PrecomputeValueToBoundedFloat(0, -truncation, -truncation, truncation)),
+      value_to_weight(PrecomputeValueToBoundedFloat(0, 0.f, 0.f, max_w)) {}
+
+// real_time_correlative_scan_matcher_2d.cc:38-59 + :170-174
+void RealTimeCorrelativeScanMatcher2D::ScoreCandidates(
+    const TSDF2D& tsdf, const std::vector<DiscreteScan2D>& discrete_scans,
+    const SearchParameters& /*search_parameters*/,
+    std::vector<Candidate2D>* const candidates) const {
+  for (Candidate2D& candidate : *candidates) {
+    float candidate_score = 0.f;
+    float summed_weight = 0.f;
+    for (const Array2i& xy_index : discrete_scans[candidate.scan_index]) {
+      const Array2i proposed{xy_index.x + candidate.x_index_offset,
+                             xy_index.y + candidate.y_index_offset};
+      const std::pair<float, float> tsd_and_weight = tsdf.GetTSDAndWeight(proposed);
+      const float normalized_tsd_score =
+          (tsdf.GetMaxCorrespondenceCost() - std::abs(tsd_and_weight.first)) /
+          tsdf.GetMaxCorrespondenceCost();
+      const float weight = tsd_and_weight.second;
+      candidate_score += normalized_tsd_score * weight;
+      summed_weight += weight;
+    }
+    if (summed_weight == 0.f) {
+      candidate_score = 0.f;
+    } else {
+      candidate_score /= summed_weight;
+    }
+    candidate.score = candidate_score;
+    candidate.score *= std::exp(-Pow2(std::hypot(candidate.x, candidate.y) *
+                                          options_.translation_delta_cost_weight +
+                                      std::abs(candidate.orientation) *
+                                          options_.rotation_delta_cost_weight));
+  }
+}
+
+double RealTimeCorrelativeScanMatcher2D::Match(const Rigid2d& initial_pose_estimate,
+                                               const PointCloud& point_cloud, const TSDF2D& grid,
+                                               Rigid2d* pose_estimate, MatchStats* stats) const {
+  const double initial_rotation = initial_pose_estimate.theta;
+  const PointCloud rotated_point_cloud =
+      TransformPointCloudRotZ(point_cloud, static_cast<float>(initial_rotation));
+  const SearchParameters search_parameters(options_.linear_search_window,
+                                           options_.angular_search_window,
+                                           rotated_point_cloud, grid.limits.resolution);
+  const std::vector<PointCloud> rotated_scans =
+      GenerateRotatedScans(rotated_point_cloud, search_parameters);
+  const std::vector<DiscreteScan2D> discrete_scans =
+      DiscretizeScans(grid.limits, rotated_scans, static_cast<float>(initial_pose_estimate.x),
+                      static_cast<float>(initial_pose_estimate.y));
+  std::vector<Candidate2D> candidates = GenerateExhaustiveSearchCandidates(search_parameters);
+  ScoreCandidates(grid, discrete_scans, search_parameters, &candidates);
+  const Candidate2D& best_candidate = *std::max_element(candidates.begin(), candidates.end());
+  *pose_estimate = Rigid2d{initial_pose_estimate.x + best_candidate.x,
+                           initial_pose_estimate.y + best_candidate.y,
+                           initial_rotation + best_candidate.orientation};
+  if (stats) {
+    stats->candidates_scored += candidates.size();
+    stats->num_scans = search_parameters.num_scans;
+    stats->best_scan_index = best_candidate.scan_index;
+    stats->best_x_offset = best_candidate.x_index_offset;
+    stats->best_y_offset = best_candidate.y_index_offset;
+  }
+  return best_candidate.score;
+}
+
 }  // namespace oracle

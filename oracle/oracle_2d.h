@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <utility>
 #include <vector>
 
 #include "oracle_common.h"
@@ -68,6 +69,36 @@ struct ProbabilityGrid {
   void SetProbability(const Array2i& c, const float probability) {
     cells[ToFlatIndex(c)] =
         CorrespondenceCostToValue(ProbabilityToCorrespondenceCost(probability));
+  }
+};
+
+// mapping/internal/2d/tsdf_2d.{h,cc} + tsd_value_converter.{h,cc}; read-only subset.
+struct TSDF2D {
+  MapLimits limits;
+  float truncation_distance, max_weight;
+  std::vector<uint16_t> tsd_cells;      // Grid2D::correspondence_cost_cells_
+  std::vector<uint16_t> weight_cells;   // tsdf_2d.h weight_cells_
+  std::vector<float> value_to_tsd, value_to_weight;  // tsd_value_converter.cc:24-34
+
+  TSDF2D(const MapLimits& limits, float truncation_distance, float max_weight);
+  float GetMaxCorrespondenceCost() const { return truncation_distance; }  // tsdf_2d.cc:26-27
+  // tsdf_2d.cc:86-96
+  std::pair<float, float> GetTSDAndWeight(const Array2i& c) const {
+    if (limits.Contains(c)) {
+      const int flat = limits.cell_limits.num_x_cells * c.y + c.x;
+      return std::make_pair(value_to_tsd[tsd_cells[flat]], value_to_weight[weight_cells[flat]]);
+    }
+    return std::make_pair(-truncation_distance, 0.f);
+  }
+  // tsd_value_converter.h:35-52
+  uint16_t TSDToValue(float tsd) const {
+    return static_cast<uint16_t>(
+        RoundToInt((Clamp(tsd, -truncation_distance, truncation_distance) + truncation_distance) *
+                   (32766.f / (truncation_distance - (-truncation_distance)))) + 1);
+  }
+  uint16_t WeightToValue(float w) const {
+    return static_cast<uint16_t>(
+        RoundToInt((Clamp(w, 0.f, max_weight) - 0.f) * (32766.f / (max_weight - 0.f))) + 1);
   }
 };
 
@@ -232,6 +263,12 @@ class RealTimeCorrelativeScanMatcher2D {  // real_time...2d.h:53-85, .cc:77-176
                MatchStats* stats = nullptr) const;
   void ScoreCandidates(const ProbabilityGrid& grid,
                        const std::vector<DiscreteScan2D>& discrete_scans,
+                       const SearchParameters& search_parameters,
+                       std::vector<Candidate2D>* candidates) const;
+  // TSDF grid type (real_time_correlative_scan_matcher_2d.cc:38-59, 160-166)
+  double Match(const Rigid2d& initial_pose_estimate, const PointCloud& point_cloud,
+               const TSDF2D& grid, Rigid2d* pose_estimate, MatchStats* stats = nullptr) const;
+  void ScoreCandidates(const TSDF2D& grid, const std::vector<DiscreteScan2D>& discrete_scans,
                        const SearchParameters& search_parameters,
                        std::vector<Candidate2D>* candidates) const;
   std::vector<Candidate2D> GenerateExhaustiveSearchCandidates(

@@ -267,6 +267,31 @@ double orc_rt2d_match(const uint16_t* cells, int nx, int ny, double res, double 
   return score;
 }
 
+double orc_rt2d_match_tsdf(const uint16_t* tsd, const uint16_t* weight, int nx, int ny,
+                           double res, double max_x, double max_y, float truncation,
+                           float max_weight, const float* xyz, int n, const double* init_pose,
+                           double lin, double ang, double w_t, double w_r, double* pose_out,
+                           int64_t* stats_out) {
+  TSDF2D grid(MapLimits{res, max_x, max_y, CellLimits{nx, ny}}, truncation, max_weight);
+  std::memcpy(grid.tsd_cells.data(), tsd, sizeof(uint16_t) * size_t(nx) * ny);
+  std::memcpy(grid.weight_cells.data(), weight, sizeof(uint16_t) * size_t(nx) * ny);
+  const RealTimeCorrelativeScanMatcher2D matcher(RealTimeOptions{lin, ang, w_t, w_r});
+  MatchStats stats;
+  Rigid2d pose{0, 0, 0};
+  const double score = matcher.Match(Rigid2d{init_pose[0], init_pose[1], init_pose[2]},
+                                     MakeCloud(xyz, n), grid, &pose, &stats);
+  pose_out[0] = pose.x;
+  pose_out[1] = pose.y;
+  pose_out[2] = pose.theta;
+  FillStats(stats, stats_out);
+  return score;
+}
+void orc_tsdf_values(float truncation, float max_weight, float tsd, float w, uint16_t* out2) {
+  const TSDF2D g(MapLimits{1., 0., 0., CellLimits{1, 1}}, truncation, max_weight);
+  out2[0] = g.TSDToValue(tsd);
+  out2[1] = g.WeightToValue(w);
+}
+
 // RT ScoreCandidates over an explicit candidate list (test hook,
 // real_time_correlative_scan_matcher_2d_test.cc:125-198).
 void orc_rt2d_score_candidates(const uint16_t* cells, int nx, int ny, double res, double max_x,

@@ -41,6 +41,7 @@ def lib():
         _lib.orc_frontend2d_step.restype = C.c_double
         _lib.orc_fast2d_create.restype = C.c_void_p
         _lib.orc_rt2d_match.restype = C.c_double
+        _lib.orc_rt2d_match_tsdf.restype = C.c_double
         _lib.orc_fast2d_batch.restype = C.c_double
         _lib.orc_fast3d_create.restype = C.c_void_p
         _lib.orc_hybrid_create.restype = C.c_void_p
@@ -240,6 +241,31 @@ def rt2d_match(grid, xyz, init_pose, lin, ang, w_t, w_r):
                                  _p(xyz, C.c_float), C.c_int(len(xyz)), _p(ip, C.c_double),
                                  C.c_double(lin), C.c_double(ang), C.c_double(w_t),
                                  C.c_double(w_r), _p(pose, C.c_double), _p(stats, C.c_int64))
+    return dict(score=float(score), pose=pose,
+                **{k: int(stats[i]) for i, k in enumerate(STAT_KEYS)})
+
+
+def tsdf_values(truncation, max_weight, tsd, weight):
+    out = np.zeros(2, np.uint16)
+    lib().orc_tsdf_values(C.c_float(truncation), C.c_float(max_weight), C.c_float(tsd),
+                          C.c_float(weight), _p(out, C.c_uint16))
+    return int(out[0]), int(out[1])
+
+
+def rt2d_match_tsdf(tsd_cells, weight_cells, resolution, max_x, max_y, truncation, max_weight,
+                    xyz, init_pose, lin, ang, w_t, w_r):
+    tsd, wgt = _u16(tsd_cells), _u16(weight_cells)
+    ny, nx = tsd.shape
+    xyz = _f32(xyz)
+    ip = np.ascontiguousarray(init_pose, dtype=np.float64)
+    pose = np.zeros(3, np.float64)
+    stats = np.zeros(8, np.int64)
+    score = lib().orc_rt2d_match_tsdf(
+        _p(tsd, C.c_uint16), _p(wgt, C.c_uint16), C.c_int(nx), C.c_int(ny), C.c_double(resolution),
+        C.c_double(max_x), C.c_double(max_y), C.c_float(truncation), C.c_float(max_weight),
+        _p(xyz, C.c_float), C.c_int(len(xyz)), _p(ip, C.c_double), C.c_double(lin),
+        C.c_double(ang), C.c_double(w_t), C.c_double(w_r), _p(pose, C.c_double),
+        _p(stats, C.c_int64))
     return dict(score=float(score), pose=pose,
                 **{k: int(stats[i]) for i, k in enumerate(STAT_KEYS)})
 

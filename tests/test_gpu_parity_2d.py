@@ -289,3 +289,36 @@ def test_rt_match_parity(oracle, sm, seed):
     assert np.float32(score) == np.float32(want["score"])
     np.testing.assert_array_equal(est, want["pose"])
     assert rt.last_stats["candidates_scored"] == want["candidates_scored"]
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_rt_match_tsdf_parity(oracle, sm, seed):
+    """TSDF grid type of the real-time matcher (real_time...2d.cc:38-59): ordered
+    weighted float sums, bit-compared with the oracle on a synthetic TSDF."""
+    grid, occ, pose, scan = worlds.small_world(500 + seed, size_cells=160, beams=241, max_range=5.0)
+    rng = np.random.RandomState(seed)
+    trunc, max_w = 0.3, 10.0
+    # signed distance to the nearest wall cell (coarse, brute force on a small grid)
+    ys, xs = np.nonzero(occ)
+    yy, xx = np.mgrid[0:occ.shape[0], 0:occ.shape[1]]
+    d = np.full(occ.shape, 1e9)
+    for k in range(0, len(ys), 512):
+        d = np.minimum(d, np.sqrt((yy[..., None] - ys[k:k + 512]) ** 2 +
+                                  (xx[..., None] - xs[k:k + 512]) ** 2).min(axis=-1))
+    tsd = np.clip(d * grid.resolution, -trunc, trunc).astype(np.float32)
+    w = rng.uniform(0.0, max_w, occ.shape).astype(np.float32)
+    tv = np.zeros(occ.shape, np.uint16)
+    wv = np.zeros(occ.shape, np.uint16)
+    known = rng.uniform(size=occ.shape) < 0.8
+    for (y, x) in zip(*np.nonzero(known)):
+        tv[y, x], wv[y, x] = oracle.tsdf_values(trunc, max_w, float(tsd[y, x]), float(w[y, x]))
+    init = pose + np.array([0.04, -0.03, 0.02])
+    opts = sm.RealTimeCorrelativeScanMatcherOptions(0.1, math.radians(5.0), 0.1, 0.1)
+    rt = sm.RealTimeCorrelativeScanMatcher2D(opts)
+    spec = sm.TSDF2DSpec(tv, wv, grid.resolution, grid.max_x, grid.max_y, trunc, max_w)
+    score, est = rt.MatchTSDF(init, scan, spec)
+    want = oracle.rt2d_match_tsdf(tv, wv, grid.resolution, grid.max_x, grid.max_y, trunc, max_w,
+                                  scan, init, 0.1, math.radians(5.0), 0.1, 0.1)
+    assert np.float32(score) == np.float32(want["score"])
+    np.testing.assert_array_equal(est, want["pose"])
+    assert 0.0 < score <= 1.0

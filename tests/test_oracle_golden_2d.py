@@ -204,3 +204,29 @@ def test_rt_match_recovers_offset(oracle):
     r = oracle.rt2d_match(grid, TEST_CLOUD_7, (0.0, 0.0, 0.0), 0.6, 0.16, 0.0, 0.0)
     assert r["score"] == pytest.approx(0.7, abs=1e-2)
     assert abs(r["pose"][0]) < 1e-9 and abs(r["pose"][1]) < 1e-9
+
+
+# real_time_correlative_scan_matcher_2d_test.cc:146-160, 180-198 (TSDF grid type): a
+# cloud lying exactly on the zero crossing scores ~1; shifted by one cell it scores
+# between 1 - 4/(7*6) and 1 (3 of 7 points stay on the surface, truncation 0.3 = 6 cells).
+def test_rt_tsdf_score_bands(oracle):
+    trunc, max_w, res = 0.3, 10.0, 0.05
+    nx = ny = 20
+    max_x, max_y = 0.3, 0.5
+    tv = np.zeros((ny, nx), np.uint16)
+    wv = np.zeros((ny, nx), np.uint16)
+    cells = [oracle.get_cell_index(res, max_x, max_y, float(p[0]), float(p[1]))
+             for p in TEST_CLOUD_7]
+    for cy in range(ny):
+        for cx in range(nx):
+            dist = min(math.hypot(cx - a, cy - b) for a, b in cells) * res
+            if dist <= trunc:
+                tv[cy, cx], wv[cy, cx] = oracle.tsdf_values(trunc, max_w, dist, 5.0)
+    perfect = oracle.rt2d_match_tsdf(tv, wv, res, max_x, max_y, trunc, max_w, TEST_CLOUD_7,
+                                     (0.0, 0.0, 0.0), 0.0, 0.0, 0.0, 0.0)
+    assert perfect["score"] > 0.95 and perfect["score"] <= 1.0 + 1e-6
+    shifted = TEST_CLOUD_7.copy()
+    shifted[:, 0] -= 0.05  # one cell along index y
+    part = oracle.rt2d_match_tsdf(tv, wv, res, max_x, max_y, trunc, max_w, shifted,
+                                  (0.0, 0.0, 0.0), 0.0, 0.0, 0.0, 0.0)
+    assert 1.0 - 4.0 / (7.0 * 6.0) - 1e-3 < part["score"] < 1.0
