@@ -66,7 +66,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                  "--format=csv,noheader,nounits", "-lms", "20"],
+                                  "--format=csv,noheader,nounits", "-lms", "50"],
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -221,7 +221,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident leg (value) -------------------------------------------
-    sampler = ClockSampler(local_rank)
+    # clocks: one nvidia-smi poller on rank 0 only (several pollers contend on the
+    # driver and slow every rank), started before the warm-up so that its start-up
+    # cost is outside the timed region; only rows sampled during the timed steps count.
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+    rows0 = 0
     launches0 = sm.kernel_launch_count()
     step_s, cand, found = [], 0, 0
     dev_ms = 0.0
@@ -229,7 +235,7 @@ def main():
         flush.zero_()
         barrier()
         if it == args.warmup:
-            sampler.start()
+            rows0 = len(sampler.rows) if sampler is not None else 0
             launches0 = sm.kernel_launch_count()
         t0 = time.perf_counter()
         res, st = sm.match_batch([matcher], clouds, jobs_for(it), LIN, ANG)
@@ -242,8 +248,10 @@ def main():
             found += int(res["found"].sum())
             dev_ms += st["device_ms"]
     launches = sm.kernel_launch_count() - launches0
-    clocks = sampler.summary() if sampler.is_alive() or sampler.rows else \
-        {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if sampler is not None:
+        sampler.rows = sampler.rows[rows0:] if len(sampler.rows) > rows0 else sampler.rows[-1:]
+        clocks = sampler.summary()
     elapsed = float(sum(step_s))
     t = torch.tensor([elapsed, float(cand), float(found)], dtype=torch.float64, device=dev)
     if dist is not None:

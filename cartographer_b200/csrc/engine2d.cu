@@ -758,11 +758,12 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
                  Node* __restrict__ next, int* __restrict__ next_count, int next_cap,
                  Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
                  int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
-  __shared__ int4 s_all[kLatThreads / 32][kLatChunk];  // {D index of lattice origin, qx, qy, 0}
+  __shared__ int2 s_all[kLatThreads / 32][kLatChunk];  // {D index of lattice origin, qy << 16 | qx}
+  // (8 B per point: a smaller shared-memory carve-out leaves more L1 for the tiles)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * (kLatThreads / 32) + warp;
   if (item >= *num_items) return;
-  int4* s_pt = s_all[warp];
+  int2* s_pt = s_all[warp];
   const WorkItem it = items[item];
   if (it.count < kLatMinParents) {
     // too few parents of this scan to amortise the shared point staging
@@ -794,13 +795,14 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
     __syncwarp();
     for (int t = lane; t < kLatChunk; t += 32) {
       const int p = p0 + t;
-      int4 d = make_int4(0, -(1 << 24), -(1 << 24), 0);
+      int2 d = make_int2(0, static_cast<int>(0x80008000u));  // qx = qy = -32768: never in range
       if (p < jb.n) {
         const short2 c = pts[p];
         const int bx = c.x + si.min_x + s - 1, by = c.y + si.min_y + s - 1;
         const int qx = bx >> lv, qy = by >> lv;
         const int ax = bx & (s - 1), ay = by & (s - 1);
-        d = make_int4(((ay * s + ax) * jd + qy) * ids + qx, qx, qy, 0);
+        if (qx > -32000 && qx < 32000 && qy > -32000 && qy < 32000)
+          d = make_int2(((ay * s + ax) * jd + qy) * ids + qx, (qy << 16) | (qx & 0xffff));
       }
       s_pt[t] = d;
     }
@@ -810,9 +812,9 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
       unsigned r0 = 0, r1 = 0;  // packed u16 pairs: (col I, col I+1) of row J / row J+1
 #pragma unroll 4
       for (int t = 0; t < cnt; ++t) {
-        const int4 d = s_pt[t];
-        const int J = d.z + j0;
-        const int c3 = d.y + i0 + 3;
+        const int2 d = s_pt[t];
+        const int J = (d.y >> 16) + j0;
+        const int c3 = static_cast<short>(d.y & 0xffff) + i0 + 3;
         if (static_cast<unsigned>(c3) < static_cast<unsigned>(id + 3)) {
           const int a = d.x + toff;
           const unsigned k = static_cast<unsigned>(a) & 3u;
@@ -1522,7 +1524,8 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
       }
       const int max_items = chunk / 32 + std::min(chunk, total_scans) + 1;
       ProfBegin(ctx);
-      k_expand_lattice<<<DivUp(max_items, kLatThreads / 32), kLatThreads, 0, s>>>(
+      static const int lat_dyn = getenv("CSM_LAT_DYNSMEM") ? atoi(getenv("CSM_LAT_DYNSMEM")) : 0;
+      k_expand_lattice<<<DivUp(max_items, kLatThreads / 32), kLatThreads, lat_dyn, s>>>(
           d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_sorted.as<Node>(),
           d_items.as<WorkItem>(), ictr + 24, h, d_lb.as<unsigned>(),
           h - 1 >= 1 ? queue_ptr(h - 1) : nullptr, ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap,
