@@ -316,8 +316,16 @@ def main():
         k = kernels[top]
         peak, how = measured_peak_gbs()
         ach = k["units"] * BYTES_PER_CANDIDATE / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
+        traffic = None
+        try:  # DRAM bytes per launch of this kernel from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = json.load(f).get(top)
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak,
-                    "peak_source": how, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": how, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_note": "ncu dram bytes of the largest launch of this kernel; the "
+                                    "working set is L2-resident, so DRAM traffic << algorithmic bytes",
                     "launches": k["launches"],
                     "avg_launch_ms": k["ms"] / max(1, k["launches"]),
                     "share_of_step": k["ms"] / tot_ms if tot_ms else None,

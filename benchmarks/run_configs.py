@@ -215,6 +215,22 @@ def cfg3_5(scale, which):
         ok &= (g is not None) == w["found"]
         if w["found"]:
             ok &= g["score"] == w["score"] and np.array_equal(g["pose_estimate"], w["pose"])
+    # per-kernel device time of ONE match that is found (CUDA events inside the library)
+    import ctypes as C
+    from cartographer_b200._lib import lib
+    prof = {}
+    for ji, r in enumerate(results):
+        if r is not None:
+            lib().csm_profile_enable(1)
+            si, n, init = jobs[ji]
+            ms[si].match_raw(False, init, ident, mk(n), min_score)
+            buf = C.create_string_buffer(8192)
+            lib().csm_profile_read(buf, 8192)
+            lib().csm_profile_enable(0)
+            for ln in buf.value.decode().strip().splitlines():
+                nm, n_l, t_ms, units = ln.split()
+                prof[nm] = {"launches": int(n_l), "ms": round(float(t_ms), 4)}
+            break
     npts = int(np.mean([len(n["cloud"]) for _, n, _ in jobs]))
     b3 = npts * 13 + 20
     return {"config": which, "what": "FastCSM3D %d rings x %d az (~%d pts) vs HybridGrid@10cm + low-res@45cm, "
@@ -223,6 +239,7 @@ def cfg3_5(scale, which):
             "gpu_cand_per_s": cand / gpu_s, "gpu_algorithmic_GBps": cand * b3 / gpu_s / 1e9,
             "gpu_device_ms_per_match": dev_ms / len(jobs), "gpu_wall_ms_per_match": 1e3 * gpu_s / len(jobs),
             "gpu_matcher_build_ms": 1e3 * build_s / n_sub, "gpu_host_threads": threads_gpu,
+            "kernels_of_one_found_match": prof,
             "cpu_sample_matches": len(sample), "cpu_matches_per_s_1thread": len(sample) / t_cpu,
             "cpu_cand_per_s_1thread": ccand / t_cpu, "parity_ok": bool(ok)}
 
