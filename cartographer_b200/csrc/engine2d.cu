@@ -118,6 +118,29 @@ __global__ void k_stack_decimate4(const uint8_t* __restrict__ lvl, int wx, int w
   }
 }
 
+// Child-window layout of parent level h (see StackDev::win): one 32-bit word per
+// (phase, lattice cell) with the four children values of level h-1.
+__global__ void k_stack_window(const uint8_t* __restrict__ lvl, int wx, int wy, int h,
+                               unsigned* __restrict__ win, int jd, int ids) {
+  const int S = 1 << h, s = S >> 1;
+  const long long total = static_cast<long long>(S) * S * jd * ids;
+  for (long long u = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; u < total;
+       u += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int I = static_cast<int>(u % ids) - 1;
+    long long r = u / ids;
+    const int J = static_cast<int>(r % jd) - 1;
+    r /= jd;
+    const int ax = static_cast<int>(r % S);
+    const int ay = static_cast<int>(r / S);
+    const int x = S * I + ax, y = S * J + ay;
+    auto at = [&](int px, int py) -> unsigned {
+      return (px >= 0 && py >= 0 && px < wx && py < wy) ? lvl[static_cast<size_t>(py) * wx + px]
+                                                        : 0u;
+    };
+    win[u] = at(x, y) | (at(x + s, y) << 8) | (at(x, y + s) << 16) | (at(x + s, y + s) << 24);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K2: GenerateRotatedScans + DiscretizeScans + ShrinkToFit
 // ---------------------------------------------------------------------------
@@ -386,6 +409,124 @@ k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ 
   }
 }
 
+// ---- lowest-resolution pass, tile form ------------------------------------------
+// For one scan point the candidates of a scan's lattice that fall inside the grid
+// read exactly one tile of the decimated level: jd rows of ids bytes, contiguous in
+// memory (phase (ax, ay) of StackDev::dec4).  MatchFullSubmap lattices are wider than
+// that tile (most candidate/point pairs lie outside the grid), so instead of every
+// candidate walking all points, ONE WARP walks the points of a scan and adds each
+// point's tile into the lattice:
+//   * lane l owns the tile words f = l - 1 + 32*it (fully coalesced 128 B loads);
+//   * the word offset between tile and lattice, (qx, qy), only changes when the point
+//     moves to another coarse cell; consecutive beams mostly stay in one, so the
+//     lanes accumulate in REGISTERS (packed u16 pairs) across a run of points and add
+//     the run into the 32-bit lattice in shared memory when (qx, qy) changes (or
+//     after 256 points, before the u16 lanes can overflow);
+//   * copy k = qx & 3 of dec4 aligns tile words with lattice quads.
+// Integer sums are order independent, so the result equals k_score_top_dense's.
+template <int kIters>
+__global__ void __launch_bounds__(128)
+k_score_top_tile(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+                 const short2* __restrict__ dscan, int* __restrict__ top_sum,
+                 const long long* __restrict__ scan_slot_base, int total_scans, int lat_ints) {
+  extern __shared__ __align__(16) int s_lat_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* __restrict__ s_lat = s_lat_all + warp * lat_ints;  // [nyc][qr] quads of 4 ints
+  const int nwarps = gridDim.x * 4;
+  for (int sg = blockIdx.x * 4 + warp; sg < total_scans; sg += nwarps) {
+    const ScanInfo si = info[sg];
+    const JobDev& jb = jobs[si.job];
+    const StackDev& st = *jb.stack;
+    const int h = st.depth - 1;
+    const int s1 = (1 << h) - 1;
+    const int id = st.dec_id[h], jd = st.dec_jd[h], ids = st.dec_ids[h];
+    const long long lpad = st.dec_lpad[h];
+    const uint8_t* __restrict__ dec = st.dec4[h] + 16;
+    const int rw = ids >> 2;         // words per tile row
+    const int W = jd * rw + 1;       // tile words incl. the one before the tile (f = -1)
+    const int qr = (si.nxc + 3) >> 2;
+    const int lat_n = qr * 4 * si.nyc;
+    const short2* __restrict__ pts = dscan + jb.dscan_off +
+                                   static_cast<long long>(sg - jb.scan_base) * jb.n;
+    int* __restrict__ out = top_sum + scan_slot_base[sg];
+    for (int t = lane; t < lat_n; t += 32) s_lat[t] = 0;
+    unsigned a02[kIters], a13[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) a02[it] = a13[it] = 0u;
+    int cur_key = 0x7fff7fff;  // (qy << 16) | (qx & 0xffff) of the current run
+    int run = 0;
+    const uint8_t* cur_base = dec;
+    // adds the run's register sums into the lattice
+    auto flush = [&]() {
+      __syncwarp();
+      const int qx = static_cast<short>(cur_key & 0xffff), qy = cur_key >> 16;
+      const int k = qx & 3;
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int f = lane + 32 * it - 1;
+        int r = (f + rw) / rw - 1;           // floor(f / rw) for f >= -1
+        int c0 = ((f - r * rw) << 2) + k;    // tile column of the word's first byte
+        if (c0 + 3 >= ids) { ++r; c0 -= ids; }  // the word continues in the next row
+        const int j = r - qy, i0 = c0 - qx;  // lattice row / first lattice column (multiple of 4)
+        if (f + 1 < W && c0 < id && static_cast<unsigned>(r) < static_cast<unsigned>(jd) &&
+            static_cast<unsigned>(j) < static_cast<unsigned>(si.nyc) &&
+            static_cast<unsigned>(i0) < static_cast<unsigned>(qr << 2)) {
+          int4* cell = reinterpret_cast<int4*>(s_lat) + (j * qr + (i0 >> 2));
+          int4 v = *cell;
+          v.x += static_cast<int>(a02[it] & 0xffffu);
+          v.y += static_cast<int>(a13[it] & 0xffffu);
+          v.z += static_cast<int>(a02[it] >> 16);
+          v.w += static_cast<int>(a13[it] >> 16);
+          *cell = v;
+        }
+        a02[it] = a13[it] = 0u;
+      }
+    };
+    for (int p0 = 0; p0 < jb.n; p0 += 32) {
+      int my_off = 0, my_key = 0x7fff7fff;
+      if (p0 + lane < jb.n) {
+        const short2 c = pts[p0 + lane];
+        const int bx = c.x + si.min_x + s1, by = c.y + si.min_y + s1;
+        const int qx = bx >> h, qy = by >> h;  // floor division
+        if (qx > -32000 && qx < 32000 && qy > -32000 && qy < 32000) {
+          my_off = ((((by & s1) << h) | (bx & s1)) * jd) * ids;
+          my_key = (qy << 16) | (qx & 0xffff);
+        }
+      }
+      const int cnt = min(32, jb.n - p0);
+      for (int t = 0; t < cnt; ++t) {
+        const int key = __shfl_sync(0xffffffffu, my_key, t);
+        const int off = __shfl_sync(0xffffffffu, my_off, t);
+        if (key != cur_key || run == 256) {
+          if (run) flush();
+          cur_key = key;
+          run = 0;
+          cur_base = dec + (key & 3) * lpad - 4 + 4 * lane;
+        }
+        if (key == 0x7fff7fff) continue;  // point cannot hit the grid
+        ++run;
+        const unsigned* __restrict__ q = reinterpret_cast<const unsigned*>(cur_base + off);
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+          if (lane + 32 * it < W) {
+            const unsigned w = __ldg(q + 32 * it);
+            a02[it] += __byte_perm(w, 0u, 0x4240);  // bytes 0 and 2 in u16 lanes
+            a13[it] += __byte_perm(w, 0u, 0x4341);  // bytes 1 and 3
+          }
+        }
+      }
+    }
+    if (run) flush();
+    __syncwarp();
+    const int slots = si.nxc * si.nyc;
+    for (int o = lane; o < slots; o += 32) {
+      const int i = o / si.nyc, j = o - i * si.nyc;
+      out[o] = s_lat[((j * qr + (i >> 2)) << 2) + (i & 3)];
+    }
+    __syncwarp();
+  }
+}
+
 // Generic list scoring (test hook + tie resolution): one warp per candidate.
 struct ListCand { int scan; int xo, yo, level; };
 __global__ void __launch_bounds__(256)
@@ -419,42 +560,59 @@ k_score_list(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
 // Slot t = 2*ix + iy (ix, iy in {0,1}) is the child at offset (ix*half, iy*half);
 // increasing t is the reference's generation order (x offset outer, y offset
 // inner), and a slot is valid unless it is clipped by the scan's max bound
-// (fast...2d.cc:352-367).  Four scan points per lane are in flight per iteration
-// so that 4 point loads + up to 16 cell gathers overlap (the loop is
-// latency-bound otherwise).  Returns the valid mask; sums[t] is 0 if invalid.
+// (fast...2d.cc:352-367).  One aligned word of the child-window layout
+// (StackDev::win) holds all four children values for a scan point; four points per
+// lane are in flight per iteration (the loop is latency-bound otherwise).
+// Returns the valid mask; sums[t] is 0 if invalid.
 __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const ScanInfo& si,
                                                   const short2* __restrict__ pts, int n, int xo,
                                                   int yo, int h, int lane, int sums[4]) {
   const int half = 1 << (h - 1);
   const bool x2 = !(xo + half > si.max_x);
   const bool y2 = !(yo + half > si.max_y);
-  const int lv = h - 1;
-  const int w1 = (1 << lv) - 1;
-  const uint8_t* __restrict__ g = st.level[lv];
-  const int wx = st.wx[lv], wy = st.wy[lv];
+  const int S1 = (1 << h) - 1;
+  const unsigned* __restrict__ win = st.win[h];
+  const int jd = st.win_jd[h], ids = st.win_ids[h];
+  const int bx = xo + half - 1, by = yo + half - 1;
   int s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-  const int bx = xo + w1, by = yo + w1;
   constexpr int kU = 4;
-  for (int p = lane; p < n; p += 32 * kU) {
-    short2 q[kU];
+  for (int p0 = lane; p0 < n; p0 += 32 * kU * 64) {
+    // packed u16 pairs: r0 = (ix 0, ix 1) of iy 0, r1 = same of iy 1; at most
+    // 64 * kU = 256 points per lane between flushes (256 * 255 < 2^16)
+    unsigned r0 = 0, r1 = 0;
+    const int pend = min(n, p0 + 32 * kU * 64);
+    for (int p = p0; p < pend; p += 32 * kU) {
+      short2 q[kU];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int pp = p + 32 * u;
-      q[u] = pp < n ? pts[pp] : make_short2(-32768, -32768);  // reads as 0
-    }
+      for (int u = 0; u < kU; ++u) {
+        const int pp = p + 32 * u;
+        q[u] = pp < pend ? pts[pp] : make_short2(0, 0);
+      }
+      unsigned w[kU];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int lx = q[u].x + bx, ly = q[u].y + by;
-      s00 += GetValue(g, wx, wy, lx, ly);
-      if (y2) s01 += GetValue(g, wx, wy, lx, ly + half);
-      if (x2) s10 += GetValue(g, wx, wy, lx + half, ly);
-      if (x2 && y2) s11 += GetValue(g, wx, wy, lx + half, ly + half);
+      for (int u = 0; u < kU; ++u) {
+        const int lx = q[u].x + bx, ly = q[u].y + by;
+        const int Qx = (lx >> h) + 1, Qy = (ly >> h) + 1;
+        w[u] = 0u;
+        if (p + 32 * u < pend && static_cast<unsigned>(Qx) < static_cast<unsigned>(ids) &&
+            static_cast<unsigned>(Qy) < static_cast<unsigned>(jd))
+          w[u] = __ldg(win + ((static_cast<long long>((ly & S1) << h | (lx & S1)) * jd + Qy) * ids + Qx));
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        r0 += __byte_perm(w[u], 0u, 0x4140);
+        r1 += __byte_perm(w[u], 0u, 0x4342);
+      }
     }
+    s00 += r0 & 0xffffu;
+    s10 += r0 >> 16;
+    s01 += r1 & 0xffffu;
+    s11 += r1 >> 16;
   }
   sums[0] = WarpSum(s00);
-  sums[1] = WarpSum(s01);
-  sums[2] = WarpSum(s10);
-  sums[3] = WarpSum(s11);
+  sums[1] = y2 ? WarpSum(s01) : 0;
+  sums[2] = x2 ? WarpSum(s10) : 0;
+  sums[3] = (x2 && y2) ? WarpSum(s11) : 0;
   return 1u | (y2 ? 2u : 0u) | (x2 ? 4u : 0u) | ((x2 && y2) ? 8u : 0u);
 }
 
@@ -750,6 +908,7 @@ __global__ void k_q_scatter(const Node* __restrict__ nodes, int count,
 constexpr int kLatThreads = 128;   // 4 warps, each working on its own item
 constexpr int kLatChunk = 256;
 constexpr int kLatMinParents = 8;
+template <int kUnroll>
 __global__ void __launch_bounds__(kLatThreads)
 k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
                  const short2* __restrict__ dscan, const Node* __restrict__ sorted,
@@ -776,10 +935,10 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
   const JobDev& jb = jobs[si.job];
   const StackDev& st = *jb.stack;
   const int lv = h - 1;            // level of the children
-  const int s = 1 << lv;           // = half width = lattice stride
-  const int id = st.dec_id[lv], jd = st.dec_jd[lv], ids = st.dec_ids[lv];
-  const unsigned lpad1 = static_cast<unsigned>(st.dec_lpad[lv]) - 1u;
-  const uint8_t* __restrict__ dec = st.dec4[lv] + 16;
+  const int s = 1 << lv;           // children stride = half the parents' stride
+  const int S1 = (1 << h) - 1;
+  const int jd = st.win_jd[h], ids = st.win_ids[h];
+  const unsigned* __restrict__ win = st.win[h];
   const short2* __restrict__ pts = dscan + jb.dscan_off +
                                    static_cast<long long>(it.scan - jb.scan_base) * jb.n;
   const bool active = lane < it.count;
@@ -787,7 +946,7 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
   if (active) nd = sorted[it.start + lane];
   // the bound may have risen since the node was queued
   const bool live = active && nd.score >= OrderedToFloat(lb[si.job]);
-  const int i0 = (nd.xo - si.min_x) >> lv, j0 = (nd.yo - si.min_y) >> lv;  // lattice coords
+  const int i0 = (nd.xo - si.min_x) >> h, j0 = (nd.yo - si.min_y) >> h;  // parent lattice coords
   const int toff = j0 * ids + i0;
   const bool x2 = !(nd.xo + s > si.max_x), y2 = !(nd.yo + s > si.max_y);
   unsigned sum0 = 0, sum1 = 0, sum2 = 0, sum3 = 0;  // slots 2*ix+iy: 00, 01, 10, 11
@@ -795,39 +954,36 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
     __syncwarp();
     for (int t = lane; t < kLatChunk; t += 32) {
       const int p = p0 + t;
-      int2 d = make_int2(0, static_cast<int>(0x80008000u));  // qx = qy = -32768: never in range
+      int2 d = make_int2(0, static_cast<int>(0x80008000u));  // Qx = Qy = -32768: never in range
       if (p < jb.n) {
         const short2 c = pts[p];
         const int bx = c.x + si.min_x + s - 1, by = c.y + si.min_y + s - 1;
-        const int qx = bx >> lv, qy = by >> lv;
-        const int ax = bx & (s - 1), ay = by & (s - 1);
+        const int qx = (bx >> h) + 1, qy = (by >> h) + 1;
+        const int ax = bx & S1, ay = by & S1;
         if (qx > -32000 && qx < 32000 && qy > -32000 && qy < 32000)
-          d = make_int2(((ay * s + ax) * jd + qy) * ids + qx, (qy << 16) | (qx & 0xffff));
+          d = make_int2((((ay << h) | ax) * jd + qy) * ids + qx, (qy << 16) | (qx & 0xffff));
       }
       s_pt[t] = d;
     }
     __syncwarp();
     if (live) {
       const int cnt = min(kLatChunk, jb.n - p0);
-      unsigned r0 = 0, r1 = 0;  // packed u16 pairs: (col I, col I+1) of row J / row J+1
-#pragma unroll 4
+      unsigned r0 = 0, r1 = 0;  // packed u16 pairs: (ix 0, ix 1) of iy 0 / iy 1
+#pragma unroll(kUnroll)
       for (int t = 0; t < cnt; ++t) {
         const int2 d = s_pt[t];
         const int J = (d.y >> 16) + j0;
-        const int c3 = static_cast<short>(d.y & 0xffff) + i0 + 3;
-        if (static_cast<unsigned>(c3) < static_cast<unsigned>(id + 3)) {
-          const int a = d.x + toff;
-          const unsigned k = static_cast<unsigned>(a) & 3u;
-          const uint8_t* q = dec + static_cast<long long>(a) + static_cast<long long>(k * lpad1);
-          if (static_cast<unsigned>(J) < static_cast<unsigned>(jd))
-            r0 += __byte_perm(__ldg(reinterpret_cast<const unsigned*>(q)), 0u, 0x4140);
-          if (static_cast<unsigned>(J + 1) < static_cast<unsigned>(jd))
-            r1 += __byte_perm(__ldg(reinterpret_cast<const unsigned*>(q + ids)), 0u, 0x4140);
+        const int I = static_cast<short>(d.y & 0xffff) + i0;
+        if (static_cast<unsigned>(I) < static_cast<unsigned>(ids) &&
+            static_cast<unsigned>(J) < static_cast<unsigned>(jd)) {
+          const unsigned w = __ldg(win + (d.x + toff));
+          r0 += __byte_perm(w, 0u, 0x4140);
+          r1 += __byte_perm(w, 0u, 0x4342);
         }
       }
-      sum0 += r0 & 0xffffu;   // (ix 0, iy 0): col I,   row J
-      sum2 += r0 >> 16;       // (ix 1, iy 0): col I+1, row J
-      sum1 += r1 & 0xffffu;   // (ix 0, iy 1): col I,   row J+1
+      sum0 += r0 & 0xffffu;   // (ix 0, iy 0)
+      sum2 += r0 >> 16;       // (ix 1, iy 0)
+      sum1 += r1 & 0xffffu;   // (ix 0, iy 1)
       sum3 += r1 >> 16;       // (ix 1, iy 1)
     }
   }
@@ -979,24 +1135,33 @@ csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, dou
   }
   CSM_CUDA(cudaMalloc(&st->d_levels, total));
   for (int l = 0; l < depth; ++l) h.level[l] = st->d_levels + st->level_off[l];
-  // decimated, 4x byte-shifted copies of every level (dense lowest-resolution pass
-  // and lattice-based branch steps)
+  // decimated, 4x byte-shifted copies of the lowest-resolution level (dense pass)
   const int top = depth - 1;
-  std::vector<size_t> dec_off(depth);
-  size_t dec_total = 0;
-  for (int l = 0; l < depth; ++l) {
-    const int s = 1 << l;
-    h.dec_id[l] = (h.wx[l] + s - 1) / s;
-    h.dec_jd[l] = (h.wy[l] + s - 1) / s;
-    h.dec_ids[l] = (h.dec_id[l] + 3) / 4 * 4 + 4;
-    const long long bytes = static_cast<long long>(s) * s * h.dec_jd[l] * h.dec_ids[l];
+  {
+    const int s = 1 << top;
+    h.dec_id[top] = (h.wx[top] + s - 1) / s;
+    h.dec_jd[top] = (h.wy[top] + s - 1) / s;
+    h.dec_ids[top] = (h.dec_id[top] + 3 + 3) / 4 * 4;  // >= 3 zero bytes after every row
+    const long long bytes = static_cast<long long>(s) * s * h.dec_jd[top] * h.dec_ids[top];
     CSM_REQUIRE(bytes < (1LL << 29), "decimated level too large");
-    h.dec_lpad[l] = static_cast<int>((bytes + 32 + 15) / 16 * 16);
-    dec_off[l] = dec_total;
-    dec_total += 4 * static_cast<size_t>(h.dec_lpad[l]);
+    h.dec_lpad[top] = static_cast<int>((bytes + 32 + 15) / 16 * 16);
+    CSM_CUDA(cudaMalloc(&st->d_dec, 4 * static_cast<size_t>(h.dec_lpad[top])));
+    h.dec4[top] = st->d_dec;
   }
-  CSM_CUDA(cudaMalloc(&st->d_dec, dec_total));
-  for (int l = 0; l < depth; ++l) h.dec4[l] = st->d_dec + dec_off[l];
+  // child-window words for every parent level (branch steps and dives)
+  std::vector<size_t> win_off(depth, 0);
+  size_t win_total = 0;
+  for (int l = 1; l < depth; ++l) {
+    const int S = 1 << l;
+    h.win_ids[l] = (h.wx[l - 1] + S - 1) / S + 1;
+    h.win_jd[l] = (h.wy[l - 1] + S - 1) / S + 1;
+    const long long words = static_cast<long long>(S) * S * h.win_jd[l] * h.win_ids[l];
+    CSM_REQUIRE(words < (1LL << 31), "window level too large");
+    win_off[l] = win_total;
+    win_total += (static_cast<size_t>(words) + 63) / 64 * 64;
+  }
+  if (win_total) CSM_CUDA(cudaMalloc(&st->d_win, win_total * sizeof(unsigned)));
+  for (int l = 1; l < depth; ++l) h.win[l] = st->d_win + win_off[l];
   // upload cells + LUT into scratch
   DevBuf& d_cells = ctx->D("stack_cells");
   DevBuf& d_lut = ctx->D("stack_lut");
@@ -1018,13 +1183,16 @@ csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, dou
                                                     h.wy[l], 1 << (l - 1));
     CSM_LAUNCH_CHECK();
   }
-  for (int l = 0; l < depth; ++l) {
-    k_stack_decimate4<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-        h.level[l], h.wx[l], h.wy[l], l, st->d_dec + dec_off[l], h.dec_lpad[l], h.dec_id[l],
-        h.dec_jd[l], h.dec_ids[l]);
+  k_stack_decimate4<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+      h.level[top], h.wx[top], h.wy[top], top, st->d_dec, h.dec_lpad[top], h.dec_id[top],
+      h.dec_jd[top], h.dec_ids[top]);
+  CSM_LAUNCH_CHECK();
+  for (int l = 1; l < depth; ++l) {
+    k_stack_window<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+        h.level[l - 1], h.wx[l - 1], h.wy[l - 1], l, st->d_win + win_off[l], h.win_jd[l],
+        h.win_ids[l]);
     CSM_LAUNCH_CHECK();
   }
-  (void)top;
   CSM_CUDA(cudaMalloc(&st->d, sizeof(StackDev)));
   CSM_CUDA(cudaMemcpyAsync(st->d, &h, sizeof(StackDev), cudaMemcpyHostToDevice, ctx->stream));
   CSM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1039,6 +1207,7 @@ csm_status csm_stack2d_destroy(csm_stack2d* stack) {
   cudaStreamSynchronize(stack->ctx->stream);
   cudaFree(stack->d_levels);
   cudaFree(stack->d_dec);
+  cudaFree(stack->d_win);
   cudaFree(stack->d);
   delete stack;
   return CSM_OK;
@@ -1351,24 +1520,52 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   bool use_gather_top = max_cap < 128;
   if (force && !strcmp(force, "gather")) use_gather_top = true;
   if (force && !strcmp(force, "dense")) use_gather_top = false;
+  // Tile form of the dense pass: needs the whole tile in <= 4 words per lane and the
+  // lattice of one scan per warp in shared memory.
+  int tile_words = 0, lat_ints = 0;
+  for (int j = 0; j < num_jobs; ++j) {
+    const StackDev& sh = stacks[jobs[j].stack_index]->h;
+    const int t = sh.depth - 1;
+    tile_words = std::max(tile_words, sh.dec_jd[t] * (sh.dec_ids[t] / 4) + 1);
+  }
+  lat_ints = (max_cap_x + 3) / 4 * 4 * max_cap_y;
+  bool use_tile_top = !use_gather_top && tile_words <= 128 && lat_ints * 16 <= 96 * 1024;
+  if (force && !strcmp(force, "dense")) use_tile_top = false;
+  if (force && !strcmp(force, "tile"))
+    CSM_REQUIRE(use_tile_top, "CSM_TOP_KERNEL=tile: lattice or tile too large");
+  const char* top_name = use_gather_top ? "k_score_top_gather"
+                         : use_tile_top ? "k_score_top_tile" : "k_score_top_dense";
   ProfBegin(ctx);
   if (use_gather_top) {
     k_score_top_gather<<<DivUp(plan.total_slots * 32, 256), 256, 0, s>>>(
         d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
         d_slot_base.as<long long>(), total_scans, plan.total_slots);
+  } else if (use_tile_top) {
+    const size_t smem = static_cast<size_t>(lat_ints) * 16;  // 4 warps x lat_ints x 4 B
+    const int grid = std::min(DivUp(total_scans, 4), ctx->sm_count * 16);
+#define CSM_TILE(K)                                                                          \
+    do {                                                                                     \
+      if (smem > 48 * 1024)                                                                  \
+        CSM_CUDA(cudaFuncSetAttribute(k_score_top_tile<K>,                                   \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                      static_cast<int>(smem)));                              \
+      k_score_top_tile<K><<<grid, 128, smem, s>>>(                                           \
+          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(), \
+          d_slot_base.as<long long>(), total_scans, lat_ints);                               \
+    } while (0)
+    if (tile_words <= 32) CSM_TILE(1);
+    else if (tile_words <= 64) CSM_TILE(2);
+    else if (tile_words <= 96) CSM_TILE(3);
+    else CSM_TILE(4);
+#undef CSM_TILE
   } else {
-    const int max_quads = (max_cap_x + 3) / 4 * max_cap_y;
     const int grid = std::min(total_scans, ctx->sm_count * 128);
-#define CSM_DENSE(Q)                                                                       \
-    k_score_top_dense<Q><<<grid, kDenseThreads, 0, s>>>(                                   \
-        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),   \
-        d_slot_base.as<long long>(), total_scans)
-    // `max_quads` is an a-priori upper bound (the real lattice is only known on the
-    // device after ShrinkToFit); extra quads per thread would execute predicated-off
-    // work, so one quad per thread and extra passes for larger lattices is faster.
-    (void)max_quads;
-    CSM_DENSE(1);
-#undef CSM_DENSE
+    // one quad per thread and extra passes for larger lattices (the real lattice is
+    // only known on the device after ShrinkToFit; more quads per thread would execute
+    // predicated-off work)
+    k_score_top_dense<1><<<grid, kDenseThreads, 0, s>>>(
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
+        d_slot_base.as<long long>(), total_scans);
   }
   CSM_LAUNCH_CHECK();
   if (g_profile_on.load()) {
@@ -1376,8 +1573,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     ProfStop(ctx);
     CSM_CUDA(cudaStreamSynchronize(s));
     CSM_CUDA(cudaMemcpy(&c3, ctr + 3, sizeof(c3), cudaMemcpyDeviceToHost));
-    ProfCommit(ctx, use_gather_top ? "k_score_top_gather" : "k_score_top_dense",
-               static_cast<double>(c3));
+    ProfCommit(ctx, top_name, static_cast<double>(c3));
   }
 
   phase("top pass");
@@ -1524,12 +1720,17 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
       }
       const int max_items = chunk / 32 + std::min(chunk, total_scans) + 1;
       ProfBegin(ctx);
-      static const int lat_dyn = getenv("CSM_LAT_DYNSMEM") ? atoi(getenv("CSM_LAT_DYNSMEM")) : 0;
-      k_expand_lattice<<<DivUp(max_items, kLatThreads / 32), kLatThreads, lat_dyn, s>>>(
-          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_sorted.as<Node>(),
-          d_items.as<WorkItem>(), ictr + 24, h, d_lb.as<unsigned>(),
-          h - 1 >= 1 ? queue_ptr(h - 1) : nullptr, ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap,
-          d_leaves.as<Node>(), leaf_count, kLeafCap, overflow, ctr);
+      static const int lat_unroll = getenv("CSM_LAT_UNROLL") ? atoi(getenv("CSM_LAT_UNROLL")) : 8;
+#define CSM_LATTICE(U)                                                                          \
+      k_expand_lattice<U><<<DivUp(max_items, kLatThreads / 32), kLatThreads, 0, s>>>(           \
+          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_sorted.as<Node>(), \
+          d_items.as<WorkItem>(), ictr + 24, h, d_lb.as<unsigned>(),                            \
+          h - 1 >= 1 ? queue_ptr(h - 1) : nullptr, ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap, \
+          d_leaves.as<Node>(), leaf_count, kLeafCap, overflow, ctr)
+      if (lat_unroll <= 4) CSM_LATTICE(4);
+      else if (lat_unroll <= 8) CSM_LATTICE(8);
+      else CSM_LATTICE(16);
+#undef CSM_LATTICE
       CSM_LAUNCH_CHECK();
       if (g_profile_on.load()) {
         ProfStop(ctx);

@@ -23,10 +23,21 @@ struct StackDev {
   // k bytes (copy_k[t] = D[t + k]), each dec_lpad bytes long with index 0 at byte
   // 16, so that any 4 consecutive bytes of D can be fetched with one aligned
   // 32-bit load: word(a) = *(u32*)(dec4 + (a & 3) * dec_lpad + 16 + (a & ~3)).
-  // The same layout exists for EVERY level l (lattice stride 2^l): the children of
-  // branch-and-bound nodes of one scan also sit on that scan's lattice.
+  // Only entry depth-1 is populated.
   const uint8_t* dec4[kMaxDepth];
   int dec_lpad[kMaxDepth], dec_id[kMaxDepth], dec_jd[kMaxDepth], dec_ids[kMaxDepth];
+  // Branch layout ("child windows") for parent levels h = 1 .. depth-1.  A node of
+  // level h sits on its scan's lattice of stride S = 2^h; its four children are the
+  // cells of level h-1 at the node's position and s = S/2 further along x and/or y.
+  // With b = (scan point + node offset + s - 1), Q = b >> h and A = b & (S-1) per
+  // axis, ONE aligned 32-bit word holds all four children values:
+  //   win[h][((Ay*S + Ax) * win_jd + Qy + 1) * win_ids + Qx + 1] =
+  //     { L(x, y), L(x+s, y), L(x, y+s), L(x+s, y+s) }   (bytes 0..3, L = level h-1,
+  //       x = S*Qx + Ax, y = S*Qy + Ay, zero outside the wide grid)
+  // for Qx in [-1, win_ids-1), Qy in [-1, win_jd-1); cells outside that range are all
+  // zero.  Lattice neighbours (Qx+1) of the same scan point are neighbouring words.
+  const unsigned* win[kMaxDepth];
+  int win_jd[kMaxDepth], win_ids[kMaxDepth];
   int wx[kMaxDepth], wy[kMaxDepth];
   int nx, ny, depth;
   double resolution, max_x, max_y;
@@ -77,6 +88,7 @@ struct csm_stack2d {
   csm::StackDev* d = nullptr;  // device copy
   uint8_t* d_levels = nullptr;
   uint8_t* d_dec = nullptr;
+  unsigned* d_win = nullptr;
   size_t level_off[csm::kMaxDepth];
   float min_cost = 0.f, max_cost = 0.f;
 };
