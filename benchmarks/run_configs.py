@@ -107,6 +107,18 @@ def cfg4(scale):
     res, st = sm.match_batch(matchers, clouds, jobs, lin, ang)
     sync()
     gpu_s = time.perf_counter() - t0
+    # per-kernel device time of one more batch (CUDA events inside the library)
+    import ctypes as C
+    from cartographer_b200._lib import lib
+    lib().csm_profile_enable(1)
+    sm.match_batch(matchers, clouds, jobs, lin, ang)
+    buf = C.create_string_buffer(8192)
+    lib().csm_profile_read(buf, 8192)
+    lib().csm_profile_enable(0)
+    prof = {}
+    for ln in buf.value.decode().strip().splitlines():
+        nm, n_l, t_ms, units = ln.split()
+        prof[nm] = {"launches": int(n_l), "ms": round(float(t_ms), 4)}
     # CPU: bounded sample on all host threads
     threads = max(1, min(os.cpu_count() or 1, 64))
     sample = np.arange(0, len(jobs), max(1, len(jobs) // (threads * 4)))[:threads * 4]
@@ -136,7 +148,8 @@ def cfg4(scale):
             "host_tie_resolves": st["host_tie_resolves"],
             "cpu_threads": threads, "cpu_sample_jobs": len(sample),
             "cpu_constraints_per_s": len(sample) / secs, "cpu_cand_per_s": float(cs.sum()) / secs,
-            "cpu_stack_build_s_per_submap": cpu_build_s, "parity_ok": bool(ok)}
+            "cpu_stack_build_s_per_submap": cpu_build_s, "parity_ok": bool(ok),
+            "gpu_kernels_one_batch": prof}
 
 
 def cfg3_5(scale, which):

@@ -430,8 +430,12 @@ k_score_top_tile(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
                  const short2* __restrict__ dscan, int* __restrict__ top_sum,
                  const long long* __restrict__ scan_slot_base, int total_scans, int lat_ints) {
   extern __shared__ __align__(16) int s_lat_all[];
+  __shared__ __align__(16) int s_key_all[4][32], s_off_all[4][32];
+  constexpr int kNoKey = 0x7fff7fff;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* __restrict__ s_lat = s_lat_all + warp * lat_ints;  // [nyc][qr] quads of 4 ints
+  int* __restrict__ s_key = s_key_all[warp];
+  int* __restrict__ s_off = s_off_all[warp];
   const int nwarps = gridDim.x * 4;
   for (int sg = blockIdx.x * 4 + warp; sg < total_scans; sg += nwarps) {
     const ScanInfo si = info[sg];
@@ -453,22 +457,30 @@ k_score_top_tile(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
     unsigned a02[kIters], a13[kIters];
 #pragma unroll
     for (int it = 0; it < kIters; ++it) a02[it] = a13[it] = 0u;
-    int cur_key = 0x7fff7fff;  // (qy << 16) | (qx & 0xffff) of the current run
+    int cur_key = kNoKey;      // (qy << 16) | (qx & 0xffff) of the current run
     int run = 0;
     const uint8_t* cur_base = dec;
     // adds the run's register sums into the lattice
+    // tile row and byte column (before the copy shift k) of this lane's words
+    int f_row[kIters], f_col[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int f = lane + 32 * it - 1;
+      f_row[it] = (f + rw) / rw - 1;               // floor(f / rw) for f >= -1
+      f_col[it] = (f - f_row[it] * rw) << 2;
+      if (f + 1 >= W) f_row[it] = -(1 << 20);      // not a tile word: never valid
+    }
     auto flush = [&]() {
       __syncwarp();
       const int qx = static_cast<short>(cur_key & 0xffff), qy = cur_key >> 16;
       const int k = qx & 3;
 #pragma unroll
       for (int it = 0; it < kIters; ++it) {
-        const int f = lane + 32 * it - 1;
-        int r = (f + rw) / rw - 1;           // floor(f / rw) for f >= -1
-        int c0 = ((f - r * rw) << 2) + k;    // tile column of the word's first byte
+        int r = f_row[it];
+        int c0 = f_col[it] + k;                 // tile column of the word's first byte
         if (c0 + 3 >= ids) { ++r; c0 -= ids; }  // the word continues in the next row
-        const int j = r - qy, i0 = c0 - qx;  // lattice row / first lattice column (multiple of 4)
-        if (f + 1 < W && c0 < id && static_cast<unsigned>(r) < static_cast<unsigned>(jd) &&
+        const int j = r - qy, i0 = c0 - qx;     // lattice row / first lattice column (multiple of 4)
+        if (c0 < id && static_cast<unsigned>(r) < static_cast<unsigned>(jd) &&
             static_cast<unsigned>(j) < static_cast<unsigned>(si.nyc) &&
             static_cast<unsigned>(i0) < static_cast<unsigned>(qr << 2)) {
           int4* cell = reinterpret_cast<int4*>(s_lat) + (j * qr + (i0 >> 2));
@@ -483,7 +495,7 @@ k_score_top_tile(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
       }
     };
     for (int p0 = 0; p0 < jb.n; p0 += 32) {
-      int my_off = 0, my_key = 0x7fff7fff;
+      int my_off = 0, my_key = kNoKey;
       if (p0 + lane < jb.n) {
         const short2 c = pts[p0 + lane];
         const int bx = c.x + si.min_x + s1, by = c.y + si.min_y + s1;
@@ -493,25 +505,54 @@ k_score_top_tile(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
           my_key = (qy << 16) | (qx & 0xffff);
         }
       }
-      const int cnt = min(32, jb.n - p0);
-      for (int t = 0; t < cnt; ++t) {
-        const int key = __shfl_sync(0xffffffffu, my_key, t);
-        const int off = __shfl_sync(0xffffffffu, my_off, t);
-        if (key != cur_key || run == 256) {
-          if (run) flush();
-          cur_key = key;
-          run = 0;
-          cur_base = dec + (key & 3) * lpad - 4 + 4 * lane;
-        }
-        if (key == 0x7fff7fff) continue;  // point cannot hit the grid
-        ++run;
-        const unsigned* __restrict__ q = reinterpret_cast<const unsigned*>(cur_base + off);
+      __syncwarp();
+      s_key[lane] = my_key;
+      s_off[lane] = my_off;
+      __syncwarp();
+      for (int t = 0; t < 32; t += 4) {   // points past the end carry kNoKey
+        const int4 key = *reinterpret_cast<const int4*>(s_key + t);
+        const int4 off = *reinterpret_cast<const int4*>(s_off + t);
+        if (key.x == cur_key && key.y == cur_key && key.z == cur_key && key.w == cur_key &&
+            run <= 252 && cur_key != kNoKey) {
+          // four points of the current run: 4 * kIters independent loads in flight
+          run += 4;
+          unsigned w[4][kIters];
 #pragma unroll
-        for (int it = 0; it < kIters; ++it) {
-          if (lane + 32 * it < W) {
-            const unsigned w = __ldg(q + 32 * it);
-            a02[it] += __byte_perm(w, 0u, 0x4240);  // bytes 0 and 2 in u16 lanes
-            a13[it] += __byte_perm(w, 0u, 0x4341);  // bytes 1 and 3
+          for (int it = 0; it < kIters; ++it) {
+            const bool on = lane + 32 * it < W;
+            w[0][it] = on ? __ldg(reinterpret_cast<const unsigned*>(cur_base + off.x) + 32 * it) : 0u;
+            w[1][it] = on ? __ldg(reinterpret_cast<const unsigned*>(cur_base + off.y) + 32 * it) : 0u;
+            w[2][it] = on ? __ldg(reinterpret_cast<const unsigned*>(cur_base + off.z) + 32 * it) : 0u;
+            w[3][it] = on ? __ldg(reinterpret_cast<const unsigned*>(cur_base + off.w) + 32 * it) : 0u;
+          }
+#pragma unroll
+          for (int it = 0; it < kIters; ++it) {
+            a02[it] += (__byte_perm(w[0][it], 0u, 0x4240) + __byte_perm(w[1][it], 0u, 0x4240)) +
+                       (__byte_perm(w[2][it], 0u, 0x4240) + __byte_perm(w[3][it], 0u, 0x4240));
+            a13[it] += (__byte_perm(w[0][it], 0u, 0x4341) + __byte_perm(w[1][it], 0u, 0x4341)) +
+                       (__byte_perm(w[2][it], 0u, 0x4341) + __byte_perm(w[3][it], 0u, 0x4341));
+          }
+          continue;
+        }
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+          const int ku = s_key[t + u], ou = s_off[t + u];
+          if (ku != cur_key || run == 256) {
+            if (run) flush();
+            cur_key = ku;
+            run = 0;
+            cur_base = dec + (cur_key & 3) * lpad - 4 + 4 * lane;
+          }
+          if (ku == kNoKey) continue;  // point cannot hit the grid / past the end
+          ++run;
+          const unsigned* __restrict__ q = reinterpret_cast<const unsigned*>(cur_base + ou);
+#pragma unroll
+          for (int it = 0; it < kIters; ++it) {
+            if (lane + 32 * it < W) {
+              const unsigned w = __ldg(q + 32 * it);
+              a02[it] += __byte_perm(w, 0u, 0x4240);  // bytes 0 and 2 in u16 lanes
+              a13[it] += __byte_perm(w, 0u, 0x4341);  // bytes 1 and 3
+            }
           }
         }
       }
@@ -842,38 +883,55 @@ __global__ void k_q_count(const Node* __restrict__ nodes, int count, int* __rest
 }
 
 // exclusive prefix sums of scan_cnt (node offsets) and of ceil(cnt / 32) (work items);
-// single CTA, 1024 threads, chunks of 1024 scans.  out[0] = number of work items.
+// single CTA of 1024 threads: every thread owns a contiguous segment of scans (sum,
+// block-wide scan of the 1024 segment sums, then the segment's offsets).
+// out[0] = number of work items.
 __global__ void __launch_bounds__(1024)
 k_q_offsets(const int* __restrict__ scan_cnt, int total_scans, int* __restrict__ scan_off,
             int* __restrict__ item_off, int* __restrict__ out) {
-  __shared__ int s_a[1024], s_b[1024];
-  __shared__ int base_a, base_b;
-  if (threadIdx.x == 0) { base_a = 0; base_b = 0; }
-  __syncthreads();
-  for (int c0 = 0; c0 < total_scans; c0 += 1024) {
-    const int i = c0 + threadIdx.x;
-    const int cnt = i < total_scans ? scan_cnt[i] : 0;
-    const int items = (cnt + 31) >> 5;
-    s_a[threadIdx.x] = cnt;
-    s_b[threadIdx.x] = items;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int va = threadIdx.x >= o ? s_a[threadIdx.x - o] : 0;
-      const int vb = threadIdx.x >= o ? s_b[threadIdx.x - o] : 0;
-      __syncthreads();
-      s_a[threadIdx.x] += va;
-      s_b[threadIdx.x] += vb;
-      __syncthreads();
-    }
-    if (i < total_scans) {
-      scan_off[i] = base_a + s_a[threadIdx.x] - cnt;
-      item_off[i] = base_b + s_b[threadIdx.x] - items;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) { base_a += s_a[1023]; base_b += s_b[1023]; }
-    __syncthreads();
+  __shared__ int s_wa[32], s_wb[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = (total_scans + 1023) >> 10;
+  const int lo = min(total_scans, static_cast<int>(threadIdx.x) * seg);
+  const int hi = min(total_scans, lo + seg);
+  int a = 0, b = 0;
+#pragma unroll 8
+  for (int i = lo; i < hi; ++i) {
+    const int cnt = scan_cnt[i];
+    a += cnt;
+    b += (cnt + 31) >> 5;
   }
-  if (threadIdx.x == 0) out[0] = base_b;
+  // inclusive warp scans, then the 32 warp totals
+  int ia = a, ib = b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int va = __shfl_up_sync(0xffffffffu, ia, o), vb = __shfl_up_sync(0xffffffffu, ib, o);
+    if (lane >= o) { ia += va; ib += vb; }
+  }
+  if (lane == 31) { s_wa[warp] = ia; s_wb[warp] = ib; }
+  __syncthreads();
+  if (warp == 0) {
+    int wa = s_wa[lane], wb = s_wb[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int va = __shfl_up_sync(0xffffffffu, wa, o), vb = __shfl_up_sync(0xffffffffu, wb, o);
+      if (lane >= o) { wa += va; wb += vb; }
+    }
+    s_wa[lane] = wa;
+    s_wb[lane] = wb;
+  }
+  __syncthreads();
+  int ea = ia - a + (warp ? s_wa[warp - 1] : 0);  // exclusive prefix of this segment
+  int eb = ib - b + (warp ? s_wb[warp - 1] : 0);
+#pragma unroll 8
+  for (int i = lo; i < hi; ++i) {
+    const int cnt = scan_cnt[i];
+    scan_off[i] = ea;
+    item_off[i] = eb;
+    ea += cnt;
+    eb += (cnt + 31) >> 5;
+  }
+  if (threadIdx.x == 1023) out[0] = s_wb[31];
 }
 
 __global__ void k_q_items(const int* __restrict__ scan_cnt, const int* __restrict__ scan_off,
@@ -917,7 +975,7 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
                  Node* __restrict__ next, int* __restrict__ next_count, int next_cap,
                  Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
                  int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
-  __shared__ int2 s_all[kLatThreads / 32][kLatChunk];  // {D index of lattice origin, qy << 16 | qx}
+  __shared__ __align__(16) int2 s_all[kLatThreads / 32][kLatChunk];  // {window index of lattice origin, Qy << 16 | Qx}
   // (8 B per point: a smaller shared-memory carve-out leaves more L1 for the tiles)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * (kLatThreads / 32) + warp;
@@ -969,14 +1027,21 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
     if (live) {
       const int cnt = min(kLatChunk, jb.n - p0);
       unsigned r0 = 0, r1 = 0;  // packed u16 pairs: (ix 0, ix 1) of iy 0 / iy 1
-#pragma unroll(kUnroll)
-      for (int t = 0; t < cnt; ++t) {
-        const int2 d = s_pt[t];
-        const int J = (d.y >> 16) + j0;
-        const int I = static_cast<short>(d.y & 0xffff) + i0;
-        if (static_cast<unsigned>(I) < static_cast<unsigned>(ids) &&
-            static_cast<unsigned>(J) < static_cast<unsigned>(jd)) {
+      // two staged points per 16-byte shared load (entries past cnt never pass the range test)
+#pragma unroll(kUnroll / 2)
+      for (int t = 0; t < cnt; t += 2) {
+        const int4 d = *reinterpret_cast<const int4*>(s_pt + t);
+        const int Ja = (d.y >> 16) + j0, Ia = static_cast<short>(d.y & 0xffff) + i0;
+        const int Jb = (d.w >> 16) + j0, Ib = static_cast<short>(d.w & 0xffff) + i0;
+        if (static_cast<unsigned>(Ia) < static_cast<unsigned>(ids) &&
+            static_cast<unsigned>(Ja) < static_cast<unsigned>(jd)) {
           const unsigned w = __ldg(win + (d.x + toff));
+          r0 += __byte_perm(w, 0u, 0x4140);
+          r1 += __byte_perm(w, 0u, 0x4342);
+        }
+        if (static_cast<unsigned>(Ib) < static_cast<unsigned>(ids) &&
+            static_cast<unsigned>(Jb) < static_cast<unsigned>(jd)) {
+          const unsigned w = __ldg(win + (d.z + toff));
           r0 += __byte_perm(w, 0u, 0x4140);
           r1 += __byte_perm(w, 0u, 0x4342);
         }
@@ -1542,13 +1607,17 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
         d_slot_base.as<long long>(), total_scans, plan.total_slots);
   } else if (use_tile_top) {
     const size_t smem = static_cast<size_t>(lat_ints) * 16;  // 4 warps x lat_ints x 4 B
-    const int grid = std::min(DivUp(total_scans, 4), ctx->sm_count * 16);
+    // persistent warps: exactly the resident CTAs, every warp walks total_scans / warps scans
 #define CSM_TILE(K)                                                                          \
     do {                                                                                     \
       if (smem > 48 * 1024)                                                                  \
         CSM_CUDA(cudaFuncSetAttribute(k_score_top_tile<K>,                                   \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                       static_cast<int>(smem)));                              \
+      int per_sm = 0;                                                                        \
+      CSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_top_tile<K>,   \
+                                                             128, smem));                    \
+      const int grid = std::min(DivUp(total_scans, 4), ctx->sm_count * std::max(1, per_sm)); \
       k_score_top_tile<K><<<grid, 128, smem, s>>>(                                           \
           d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(), \
           d_slot_base.as<long long>(), total_scans, lat_ints);                               \
