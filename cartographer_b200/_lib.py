@@ -11,7 +11,9 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libcsm_b200.so")
+# CSM_B200_LIB points at an alternative build of the same library (A/B timing of kernel
+# variants); the default is the in-tree product library.
+SO_PATH = os.environ.get("CSM_B200_LIB") or os.path.join(_PKG, "libcsm_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 

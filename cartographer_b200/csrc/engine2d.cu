@@ -308,6 +308,80 @@ k_score_top_gather(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__
   if (lane == 0) top_sum[scan_slot_base[sg] + slot] = sum;
 }
 
+// Lowest-resolution pass, small-lattice form (local search windows: a few dozen
+// candidates per scan).  `lanes` consecutive lanes of a warp share one scan; a lane
+// owns one quad = 4 x-consecutive candidates of one lattice row and fetches their
+// cells for a scan point with ONE aligned 32-bit load from the decimated level
+// (as k_score_top_dense), so a warp works on 32 / lanes scans at once and nearly
+// every lane is busy.  Packed u16 sums are flushed every 256 points.
+__global__ void __launch_bounds__(128)
+k_score_top_small(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
+                  const short2* __restrict__ dscan, int* __restrict__ top_sum,
+                  const long long* __restrict__ scan_slot_base, int total_scans, int lanes) {
+  const int lane = threadIdx.x & 31;
+  const int spw = 32 / lanes;                 // scans per warp
+  const int sub = lane / lanes, ql = lane - sub * lanes;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long sgl = warp * spw + sub;
+  if (sub >= spw || sgl >= total_scans) return;
+  const int sg = static_cast<int>(sgl);
+  const ScanInfo si = info[sg];
+  const int qr = (si.nxc + 3) >> 2;
+  if (ql >= qr * si.nyc) return;
+  const JobDev& jb = jobs[si.job];
+  const StackDev& st = *jb.stack;
+  const int h = st.depth - 1;
+  const int s1 = (1 << h) - 1;
+  const int id = st.dec_id[h], jd = st.dec_jd[h], ids = st.dec_ids[h];
+  const unsigned lpad1 = static_cast<unsigned>(st.dec_lpad[h]) - 1u;
+  const uint8_t* __restrict__ dec = st.dec4[h] + 16;
+  const int jy = ql / qr, i0 = (ql - jy * qr) << 2;
+  const int toff = jy * ids + i0;
+  const int ox = si.min_x + s1, oy = si.min_y + s1;
+  const short2* __restrict__ pts = dscan + jb.dscan_off +
+                                 static_cast<long long>(sg - jb.scan_base) * jb.n;
+  unsigned sum0 = 0, sum1 = 0, sum2 = 0, sum3 = 0;
+  constexpr int kU = 4;
+  for (int p0 = 0; p0 < jb.n; p0 += 256) {
+    const int pend = min(jb.n, p0 + 256);
+    unsigned a02 = 0, a13 = 0;
+    for (int p = p0; p < pend; p += kU) {
+      short2 c[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) c[u] = pts[min(p + u, pend - 1)];
+      unsigned w[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int bx = c[u].x + ox, by = c[u].y + oy;
+        const int qx = bx >> h, qy = by >> h;  // floor division
+        const int J = qy + jy, c3 = qx + i0 + 3;
+        w[u] = 0u;
+        if (p + u < pend && static_cast<unsigned>(J) < static_cast<unsigned>(jd) &&
+            static_cast<unsigned>(c3) < static_cast<unsigned>(id + 3)) {
+          const int a = ((((by & s1) << h) | (bx & s1)) * jd + qy) * ids + qx + toff;
+          const unsigned k = static_cast<unsigned>(a) & 3u;
+          w[u] = __ldg(reinterpret_cast<const unsigned*>(
+              dec + static_cast<long long>(a) + static_cast<long long>(k * lpad1)));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        a02 += __byte_perm(w[u], 0u, 0x4240);  // bytes 0 and 2 in u16 lanes
+        a13 += __byte_perm(w[u], 0u, 0x4341);  // bytes 1 and 3
+      }
+    }
+    sum0 += a02 & 0xffffu;
+    sum2 += a02 >> 16;
+    sum1 += a13 & 0xffffu;
+    sum3 += a13 >> 16;
+  }
+  int* __restrict__ out = top_sum + scan_slot_base[sg];
+  const unsigned sums[4] = {sum0, sum1, sum2, sum3};
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (i0 + e < si.nxc) out[(i0 + e) * si.nyc + jy] = static_cast<int>(sums[e]);
+}
+
 // Lowest-resolution pass, dense form: one CTA per scan.  The candidates of one
 // rotated scan form a lattice of stride s = 2^h, so for a scan point p the cells
 // they read are one contiguous block of the decimated level (StackDev::dec4).
@@ -882,27 +956,12 @@ __global__ void k_q_count(const Node* __restrict__ nodes, int count, int* __rest
   if (i < count) atomicAdd(&scan_cnt[nodes[i].scan], 1);
 }
 
-// exclusive prefix sums of scan_cnt (node offsets) and of ceil(cnt / 32) (work items);
-// single CTA of 1024 threads: every thread owns a contiguous segment of scans (sum,
-// block-wide scan of the 1024 segment sums, then the segment's offsets).
-// out[0] = number of work items.
-__global__ void __launch_bounds__(1024)
-k_q_offsets(const int* __restrict__ scan_cnt, int total_scans, int* __restrict__ scan_off,
-            int* __restrict__ item_off, int* __restrict__ out) {
-  __shared__ int s_wa[32], s_wb[32];
+// Exclusive prefix sums of scan_cnt (node offsets) and of ceil(cnt / 32) (work
+// items) in three steps: sums of 1024-scan blocks, a single-CTA scan of those block
+// sums, and per-block scans that also emit the work items.
+__device__ __forceinline__ void BlockScan2(int& ia, int& ib, int* s_wa, int* s_wb) {
+  // inclusive scan of (ia, ib) over the 1024 threads of the CTA
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int seg = (total_scans + 1023) >> 10;
-  const int lo = min(total_scans, static_cast<int>(threadIdx.x) * seg);
-  const int hi = min(total_scans, lo + seg);
-  int a = 0, b = 0;
-#pragma unroll 8
-  for (int i = lo; i < hi; ++i) {
-    const int cnt = scan_cnt[i];
-    a += cnt;
-    b += (cnt + 31) >> 5;
-  }
-  // inclusive warp scans, then the 32 warp totals
-  int ia = a, ib = b;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int va = __shfl_up_sync(0xffffffffu, ia, o), vb = __shfl_up_sync(0xffffffffu, ib, o);
@@ -921,27 +980,57 @@ k_q_offsets(const int* __restrict__ scan_cnt, int total_scans, int* __restrict__
     s_wb[lane] = wb;
   }
   __syncthreads();
-  int ea = ia - a + (warp ? s_wa[warp - 1] : 0);  // exclusive prefix of this segment
-  int eb = ib - b + (warp ? s_wb[warp - 1] : 0);
-#pragma unroll 8
-  for (int i = lo; i < hi; ++i) {
-    const int cnt = scan_cnt[i];
-    scan_off[i] = ea;
-    item_off[i] = eb;
-    ea += cnt;
-    eb += (cnt + 31) >> 5;
-  }
-  if (threadIdx.x == 1023) out[0] = s_wb[31];
+  if (warp) { ia += s_wa[warp - 1]; ib += s_wb[warp - 1]; }
 }
 
-__global__ void k_q_items(const int* __restrict__ scan_cnt, const int* __restrict__ scan_off,
-                          const int* __restrict__ item_off, int total_scans,
-                          WorkItem* __restrict__ items) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= total_scans) return;
-  const int cnt = scan_cnt[s];
+__global__ void __launch_bounds__(1024)
+k_q_block_sums(const int* __restrict__ scan_cnt, int total_scans, int* __restrict__ part_a,
+               int* __restrict__ part_b) {
+  __shared__ int s_wa[32], s_wb[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int cnt = i < total_scans ? scan_cnt[i] : 0;
+  int ia = cnt, ib = (cnt + 31) >> 5;
+  BlockScan2(ia, ib, s_wa, s_wb);
+  if (threadIdx.x == 1023) { part_a[blockIdx.x] = ia; part_b[blockIdx.x] = ib; }
+}
+
+// in-place exclusive scan of the block sums; single CTA, every thread owns a
+// contiguous segment.  out[0] = total number of work items.
+__global__ void __launch_bounds__(1024)
+k_q_scan_parts(int* __restrict__ part_a, int* __restrict__ part_b, int nb, int* __restrict__ out) {
+  __shared__ int s_wa[32], s_wb[32];
+  const int seg = (nb + 1023) >> 10;
+  const int lo = min(nb, static_cast<int>(threadIdx.x) * seg), hi = min(nb, lo + seg);
+  int a = 0, b = 0;
+  for (int i = lo; i < hi; ++i) { a += part_a[i]; b += part_b[i]; }
+  int ia = a, ib = b;
+  BlockScan2(ia, ib, s_wa, s_wb);
+  int ea = ia - a, eb = ib - b;
+  for (int i = lo; i < hi; ++i) {
+    const int va = part_a[i], vb = part_b[i];
+    part_a[i] = ea;
+    part_b[i] = eb;
+    ea += va;
+    eb += vb;
+  }
+  if (threadIdx.x == 1023) out[0] = ib;
+}
+
+__global__ void __launch_bounds__(1024)
+k_q_finish(const int* __restrict__ scan_cnt, int total_scans, const int* __restrict__ part_a,
+           const int* __restrict__ part_b, int* __restrict__ scan_off,
+           WorkItem* __restrict__ items) {
+  __shared__ int s_wa[32], s_wb[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int cnt = i < total_scans ? scan_cnt[i] : 0;
+  int ia = cnt, ib = (cnt + 31) >> 5;
+  BlockScan2(ia, ib, s_wa, s_wb);
+  if (i >= total_scans) return;
+  const int off = part_a[blockIdx.x] + ia - cnt;
+  const int item0 = part_b[blockIdx.x] + ib - ((cnt + 31) >> 5);
+  scan_off[i] = off;
   for (int k = 0; k * 32 < cnt; ++k)
-    items[item_off[s] + k] = WorkItem{s, scan_off[s] + k * 32, min(32, cnt - k * 32)};
+    items[item0 + k] = WorkItem{i, off + k * 32, min(32, cnt - k * 32)};
 }
 
 // Stable within every 32-node run: lanes holding nodes of the same scan get
@@ -963,11 +1052,13 @@ __global__ void k_q_scatter(const Node* __restrict__ nodes, int count,
   if (ok) sorted[scan_off[nd.scan] + base + __popc(peers & ((1u << lane) - 1))] = nd;
 }
 
+#ifndef CSM_LAT_MINB
+#define CSM_LAT_MINB 9   // CTAs per SM the register allocation aims for
+#endif
 constexpr int kLatThreads = 128;   // 4 warps, each working on its own item
 constexpr int kLatChunk = 256;
-constexpr int kLatMinParents = 8;
 template <int kUnroll>
-__global__ void __launch_bounds__(kLatThreads)
+__global__ void __launch_bounds__(kLatThreads, CSM_LAT_MINB)
 k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
                  const short2* __restrict__ dscan, const Node* __restrict__ sorted,
                  const WorkItem* __restrict__ items, const int* __restrict__ num_items, int h,
@@ -982,13 +1073,12 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
   if (item >= *num_items) return;
   int2* s_pt = s_all[warp];
   const WorkItem it = items[item];
-  if (it.count < kLatMinParents) {
-    // too few parents of this scan to amortise the shared point staging
-    for (int k = 0; k < it.count; ++k)
-      ExpandParentWarp(jobs, info, dscan, sorted[it.start + k], h, lb, next, next_count,
-                       next_cap, leaves, leaf_count, leaf_cap, overflow, counters);
-    return;
-  }
+  // With few parents, G = 2^lg lanes share one parent and split the scan points
+  // (lane = parent * G + sub, sub-lane `sub` takes the point pairs sub, sub + G, ...).
+  int lg = 0;
+  while ((it.count << (lg + 1)) <= 32) ++lg;
+  const int G = 1 << lg;
+  const int pidx = lane >> lg, sub = lane & (G - 1);
   const ScanInfo si = info[it.scan];
   const JobDev& jb = jobs[si.job];
   const StackDev& st = *jb.stack;
@@ -999,9 +1089,9 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
   const unsigned* __restrict__ win = st.win[h];
   const short2* __restrict__ pts = dscan + jb.dscan_off +
                                    static_cast<long long>(it.scan - jb.scan_base) * jb.n;
-  const bool active = lane < it.count;
+  const bool active = pidx < it.count;
   Node nd = Node{it.scan, si.min_x, si.min_y, 0.f};
-  if (active) nd = sorted[it.start + lane];
+  if (active) nd = sorted[it.start + pidx];
   // the bound may have risen since the node was queued
   const bool live = active && nd.score >= OrderedToFloat(lb[si.job]);
   const int i0 = (nd.xo - si.min_x) >> h, j0 = (nd.yo - si.min_y) >> h;  // parent lattice coords
@@ -1029,7 +1119,7 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
       unsigned r0 = 0, r1 = 0;  // packed u16 pairs: (ix 0, ix 1) of iy 0 / iy 1
       // two staged points per 16-byte shared load (entries past cnt never pass the range test)
 #pragma unroll(kUnroll / 2)
-      for (int t = 0; t < cnt; t += 2) {
+      for (int t = 2 * sub; t < cnt; t += 2 * G) {
         const int4 d = *reinterpret_cast<const int4*>(s_pt + t);
         const int Ja = (d.y >> 16) + j0, Ia = static_cast<short>(d.y & 0xffff) + i0;
         const int Jb = (d.w >> 16) + j0, Ib = static_cast<short>(d.w & 0xffff) + i0;
@@ -1052,8 +1142,16 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
       sum3 += r1 >> 16;       // (ix 1, iy 1)
     }
   }
-  const unsigned valid = live ? (1u | (y2 ? 2u : 0u) | (x2 ? 4u : 0u) | ((x2 && y2) ? 8u : 0u)) : 0u;
-  if (live) {
+  // totals of the G sub-lanes (all lanes of the warp take part)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v0 = __shfl_xor_sync(0xffffffffu, sum0, o), v1 = __shfl_xor_sync(0xffffffffu, sum1, o);
+    const unsigned v2 = __shfl_xor_sync(0xffffffffu, sum2, o), v3 = __shfl_xor_sync(0xffffffffu, sum3, o);
+    if (o < G) { sum0 += v0; sum1 += v1; sum2 += v2; sum3 += v3; }
+  }
+  const bool lead = live && sub == 0;   // one lane per parent carries on
+  const unsigned valid = lead ? (1u | (y2 ? 2u : 0u) | (x2 ? 4u : 0u) | ((x2 && y2) ? 8u : 0u)) : 0u;
+  if (lead) {
     atomicAdd(&counters[0], (unsigned long long)__popc(valid));
     atomicAdd(&counters[1], 1ull);
   }
@@ -1063,7 +1161,7 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
 #pragma unroll
   for (int t = 0; t < 4; ++t) sc[t] = ToScore(st, sums[t], jb.n);
   if (lv == 0) {
-    if (!live) return;
+    if (!lead) return;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       if (!((valid >> t) & 1u) || !(sc[t] > jb.min_score)) continue;
@@ -1575,7 +1673,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   }
   // Wide lattices (MatchFullSubmap) take the dense decimated-grid kernel; narrow
   // ones (local windows: a few dozen candidates per scan) the gather kernel.
-  static const char* force = getenv("CSM_TOP_KERNEL");  // "gather" | "dense" (debug)
+  static const char* force = getenv("CSM_TOP_KERNEL");  // "small" | "gather" | "tile" | "dense" (debug)
   int max_cap = 0, max_cap_x = 0, max_cap_y = 0;
   for (const JobDev& d : plan.jobs) {
     max_cap = std::max(max_cap, d.cap);
@@ -1595,13 +1693,25 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   }
   lat_ints = (max_cap_x + 3) / 4 * 4 * max_cap_y;
   bool use_tile_top = !use_gather_top && tile_words <= 128 && lat_ints * 16 <= 96 * 1024;
+  const int small_lanes = (max_cap_x + 3) / 4 * max_cap_y;  // quads per scan, a-priori bound
+  bool use_small_top = small_lanes <= 32;
+  if (force && !strcmp(force, "small"))
+    CSM_REQUIRE(use_small_top, "CSM_TOP_KERNEL=small: more than 32 quads per scan");
+  if (force && strcmp(force, "small")) use_small_top = false;
+  if (use_small_top) use_gather_top = use_tile_top = false;
   if (force && !strcmp(force, "dense")) use_tile_top = false;
   if (force && !strcmp(force, "tile"))
     CSM_REQUIRE(use_tile_top, "CSM_TOP_KERNEL=tile: lattice or tile too large");
-  const char* top_name = use_gather_top ? "k_score_top_gather"
-                         : use_tile_top ? "k_score_top_tile" : "k_score_top_dense";
+  const char* top_name = use_small_top    ? "k_score_top_small"
+                         : use_gather_top ? "k_score_top_gather"
+                         : use_tile_top   ? "k_score_top_tile" : "k_score_top_dense";
   ProfBegin(ctx);
-  if (use_gather_top) {
+  if (use_small_top) {
+    const int spw = 32 / small_lanes;
+    k_score_top_small<<<DivUp(DivUp(total_scans, spw), 4), 128, 0, s>>>(
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
+        d_slot_base.as<long long>(), total_scans, small_lanes);
+  } else if (use_gather_top) {
     k_score_top_gather<<<DivUp(plan.total_slots * 32, 256), 256, 0, s>>>(
         d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
         d_slot_base.as<long long>(), total_scans, plan.total_slots);
@@ -1703,7 +1813,8 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   DevBuf& d_items = ctx->D("work_items");
   DevBuf& d_sorted = ctx->D("sorted_nodes");
   CSM_TRY(d_scan_cnt.Reserve(sizeof(int) * 2 * static_cast<size_t>(total_scans)));
-  CSM_TRY(d_scan_off.Reserve(sizeof(int) * 2 * static_cast<size_t>(total_scans)));
+  CSM_TRY(d_scan_off.Reserve(sizeof(int) * (static_cast<size_t>(total_scans) +
+                                            2 * (static_cast<size_t>(total_scans) / 1024 + 2))));
   CSM_TRY(d_items.Reserve(sizeof(WorkItem) * (static_cast<size_t>(kChunk) / 32 + total_scans + 2)));
   CSM_TRY(d_sorted.Reserve(sizeof(Node) * static_cast<size_t>(kChunk)));
   static const bool use_lattice = getenv("CSM_NO_LATTICE") == nullptr;
@@ -1771,14 +1882,18 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
       int* scan_cnt = d_scan_cnt.as<int>();
       int* cursor = scan_cnt + total_scans;
       int* scan_off = d_scan_off.as<int>();
-      int* item_off = scan_off + total_scans;
+      int* part_a = scan_off + total_scans;   // block sums (DivUp(total_scans, 1024) each)
+      int* part_b = part_a + DivUp(total_scans, 1024);
       ProfBegin(ctx);
       k_q_count<<<DivUp(chunk, 256), 256, 0, s>>>(queue_ptr(h) + start, chunk, scan_cnt);
       CSM_LAUNCH_CHECK();
-      k_q_offsets<<<1, 1024, 0, s>>>(scan_cnt, total_scans, scan_off, item_off, ictr + 24);
+      const int nb = DivUp(total_scans, 1024);
+      k_q_block_sums<<<nb, 1024, 0, s>>>(scan_cnt, total_scans, part_a, part_b);
       CSM_LAUNCH_CHECK();
-      k_q_items<<<DivUp(total_scans, 256), 256, 0, s>>>(scan_cnt, scan_off, item_off,
-                                                        total_scans, d_items.as<WorkItem>());
+      k_q_scan_parts<<<1, 1024, 0, s>>>(part_a, part_b, nb, ictr + 24);
+      CSM_LAUNCH_CHECK();
+      k_q_finish<<<nb, 1024, 0, s>>>(scan_cnt, total_scans, part_a, part_b, scan_off,
+                                     d_items.as<WorkItem>());
       CSM_LAUNCH_CHECK();
       k_q_scatter<<<DivUp(chunk, 256), 256, 0, s>>>(queue_ptr(h) + start, chunk, scan_off, cursor,
                                                    d_sorted.as<Node>());
