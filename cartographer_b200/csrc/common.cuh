@@ -102,6 +102,10 @@ struct Ctx {
   std::map<std::string, PinnedBuf> pin;
   DevBuf& D(const char* name) { return dev[name]; }
   PinnedBuf& P(const char* name) { return pin[name]; }
+  // Recycled device buffers of destroyed point clouds (guarded by `mu`): node scans
+  // come and go at sensor rate, and cudaMalloc / cudaFree serialise the whole device.
+  std::vector<std::pair<void*, size_t>> cloud_pool;
+  size_t cloud_pool_bytes = 0;
 };
 
 csm_status GetCtx(int device, Ctx** out);

@@ -498,20 +498,25 @@ k_score_top_dense(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ 
 //     after 256 points, before the u16 lanes can overflow);
 //   * copy k = qx & 3 of dec4 aligns tile words with lattice quads.
 // Integer sums are order independent, so the result equals k_score_top_dense's.
+#ifndef CSM_TILE_THREADS
+#define CSM_TILE_THREADS 128
+#endif
+constexpr int kTileThreads = CSM_TILE_THREADS;
+constexpr int kTileWarps = kTileThreads / 32;
 template <int kIters>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kTileThreads)
 k_score_top_tile(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
                  const short2* __restrict__ dscan, int* __restrict__ top_sum,
                  const long long* __restrict__ scan_slot_base, int total_scans, int lat_ints) {
   extern __shared__ __align__(16) int s_lat_all[];
-  __shared__ __align__(16) int s_key_all[4][32], s_off_all[4][32];
+  __shared__ __align__(16) int s_key_all[kTileWarps][32], s_off_all[kTileWarps][32];
   constexpr int kNoKey = 0x7fff7fff;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* __restrict__ s_lat = s_lat_all + warp * lat_ints;  // [nyc][qr] quads of 4 ints
   int* __restrict__ s_key = s_key_all[warp];
   int* __restrict__ s_off = s_off_all[warp];
-  const int nwarps = gridDim.x * 4;
-  for (int sg = blockIdx.x * 4 + warp; sg < total_scans; sg += nwarps) {
+  const int nwarps = gridDim.x * kTileWarps;
+  for (int sg = blockIdx.x * kTileWarps + warp; sg < total_scans; sg += nwarps) {
     const ScanInfo si = info[sg];
     const JobDev& jb = jobs[si.job];
     const StackDev& st = *jb.stack;
@@ -1055,7 +1060,10 @@ __global__ void k_q_scatter(const Node* __restrict__ nodes, int count,
 #ifndef CSM_LAT_MINB
 #define CSM_LAT_MINB 9   // CTAs per SM the register allocation aims for
 #endif
-constexpr int kLatThreads = 128;   // 4 warps, each working on its own item
+#ifndef CSM_LAT_THREADS
+#define CSM_LAT_THREADS 128
+#endif
+constexpr int kLatThreads = CSM_LAT_THREADS;   // every warp works on its own item
 constexpr int kLatChunk = 256;
 template <int kUnroll>
 __global__ void __launch_bounds__(kLatThreads, CSM_LAT_MINB)
@@ -1410,9 +1418,22 @@ csm_status csm_cloud_create(const float* xyz, int32_t n, int32_t device, csm_clo
     m = std::max(range, m);
   }
   c->max_norm = m;
-  CSM_CUDA(cudaMalloc(&c->d_xyz, sizeof(float) * 3 * n));
-  CSM_CUDA(cudaMemcpyAsync(c->d_xyz, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice,
-                           ctx->stream));
+  const size_t need = sizeof(float) * 3 * static_cast<size_t>(n);
+  for (size_t i = 0; i < ctx->cloud_pool.size(); ++i) {
+    if (ctx->cloud_pool[i].second >= need && ctx->cloud_pool[i].second <= 2 * need + 4096) {
+      c->d_xyz = static_cast<float*>(ctx->cloud_pool[i].first);
+      c->d_bytes = ctx->cloud_pool[i].second;
+      ctx->cloud_pool_bytes -= c->d_bytes;
+      ctx->cloud_pool[i] = ctx->cloud_pool.back();
+      ctx->cloud_pool.pop_back();
+      break;
+    }
+  }
+  if (!c->d_xyz) {
+    c->d_bytes = (need + 4095) / 4096 * 4096;
+    CSM_CUDA(cudaMalloc(&c->d_xyz, c->d_bytes));
+  }
+  CSM_CUDA(cudaMemcpyAsync(c->d_xyz, xyz, need, cudaMemcpyHostToDevice, ctx->stream));
   CSM_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = c.release();
   return CSM_OK;
@@ -1422,8 +1443,17 @@ csm_status csm_cloud_destroy(csm_cloud* cloud) {
   if (!cloud) return CSM_OK;
   std::lock_guard<std::mutex> lock(cloud->ctx->mu);
   cudaSetDevice(cloud->ctx->device);
-  cudaStreamSynchronize(cloud->ctx->stream);
-  cudaFree(cloud->d_xyz);
+  Ctx* ctx = cloud->ctx;
+  // No match is in flight on this cloud (caller contract), so the buffer can be
+  // handed to the next csm_cloud_create without a device-wide cudaFree.
+  if (cloud->d_xyz && ctx->cloud_pool.size() < 4096 &&
+      ctx->cloud_pool_bytes + cloud->d_bytes <= (256u << 20)) {
+    ctx->cloud_pool.emplace_back(cloud->d_xyz, cloud->d_bytes);
+    ctx->cloud_pool_bytes += cloud->d_bytes;
+  } else {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(cloud->d_xyz);
+  }
   delete cloud;
   return CSM_OK;
 }
@@ -1692,7 +1722,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     tile_words = std::max(tile_words, sh.dec_jd[t] * (sh.dec_ids[t] / 4) + 1);
   }
   lat_ints = (max_cap_x + 3) / 4 * 4 * max_cap_y;
-  bool use_tile_top = !use_gather_top && tile_words <= 128 && lat_ints * 16 <= 96 * 1024;
+  bool use_tile_top = !use_gather_top && tile_words <= 128 && lat_ints * 4 * kTileWarps <= 96 * 1024;
   const int small_lanes = (max_cap_x + 3) / 4 * max_cap_y;  // quads per scan, a-priori bound
   bool use_small_top = small_lanes <= 32;
   if (force && !strcmp(force, "small"))
@@ -1716,7 +1746,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
         d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
         d_slot_base.as<long long>(), total_scans, plan.total_slots);
   } else if (use_tile_top) {
-    const size_t smem = static_cast<size_t>(lat_ints) * 16;  // 4 warps x lat_ints x 4 B
+    const size_t smem = static_cast<size_t>(lat_ints) * 4 * kTileWarps;  // one lattice per warp
     // persistent warps: exactly the resident CTAs, every warp walks total_scans / warps scans
 #define CSM_TILE(K)                                                                          \
     do {                                                                                     \
@@ -1726,9 +1756,9 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
                                       static_cast<int>(smem)));                              \
       int per_sm = 0;                                                                        \
       CSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_top_tile<K>,   \
-                                                             128, smem));                    \
-      const int grid = std::min(DivUp(total_scans, 4), ctx->sm_count * std::max(1, per_sm)); \
-      k_score_top_tile<K><<<grid, 128, smem, s>>>(                                           \
+                                                             kTileThreads, smem));           \
+      const int grid = std::min(DivUp(total_scans, kTileWarps), ctx->sm_count * std::max(1, per_sm)); \
+      k_score_top_tile<K><<<grid, kTileThreads, smem, s>>>(                                  \
           d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(), \
           d_slot_base.as<long long>(), total_scans, lat_ints);                               \
     } while (0)

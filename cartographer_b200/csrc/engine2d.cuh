@@ -97,6 +97,7 @@ struct csm_cloud {
   csm::Ctx* ctx = nullptr;
   int n = 0;
   float* d_xyz = nullptr;
+  size_t d_bytes = 0;   // capacity of d_xyz (buffers are recycled through Ctx::cloud_pool)
   float max_norm = 0.f;  // max_i sqrt(x*x + y*y) in float (correlative_scan_matcher_2d.cc:35-38)
   std::vector<float> h_xyz;
 };
