@@ -191,23 +191,30 @@ def cfg3_5(scale, which):
     mk = lambda n: sm.TrajectoryNodeData3D(n["cloud"], n["low"], n["hist"])
     ms[jobs[0][0]].Match(jobs[0][2], ident, mk(jobs[0][1]), min_score)
     sync()
-    from concurrent.futures import ThreadPoolExecutor
-    threads_gpu = 1 if which == 3 else 8   # config 5 = the ConstraintBuilder3D queue: 8 pool threads
-    if threads_gpu > 1:   # warm-up: every lane (stream + workspace) gets sized once
-        with ThreadPoolExecutor(max_workers=threads_gpu) as pool:
-            list(pool.map(lambda j: ms[j[0]].match_raw(False, j[2], ident, mk(j[1]), min_score), jobs))
-        sync()
-    t0 = time.perf_counter()
+    threads_gpu = 1 if which == 3 else 8   # config 5 = the ConstraintBuilder3D queue: 8 matches in flight
     if threads_gpu > 1:
-        with ThreadPoolExecutor(max_workers=threads_gpu) as pool:
-            pairs = list(pool.map(lambda j: ms[j[0]].match_raw(False, j[2], ident, mk(j[1]), min_score), jobs))
+        # one csm_match3d_batch call for the whole queue
+        nodes_u, node_ix = [], {}
+        for si, n, init in jobs:
+            if id(n) not in node_ix:
+                node_ix[id(n)] = len(nodes_u)
+                nodes_u.append(mk(n))
+        bjobs = [(si, node_ix[id(n)], False, init, ident, min_score) for si, n, init in jobs]
+        sm.match_batch3d(ms, nodes_u, bjobs, max_concurrency=threads_gpu)   # warm-up: sizes every lane
+        sync()
+        t0 = time.perf_counter()
+        results, bst = sm.match_batch3d(ms, nodes_u, bjobs, max_concurrency=threads_gpu)
+        sync()
+        gpu_s = time.perf_counter() - t0
+        cand, dev_ms = bst["candidates_scored"], bst["device_ms"]
     else:
+        t0 = time.perf_counter()
         pairs = [ms[si].match_raw(False, init, ident, mk(n), min_score) for si, n, init in jobs]
-    sync()
-    gpu_s = time.perf_counter() - t0
-    results = [p[0] for p in pairs]
-    cand = sum(p[1]["candidates_scored"] for p in pairs)
-    dev_ms = sum(p[1]["device_ms"] for p in pairs)
+        sync()
+        gpu_s = time.perf_counter() - t0
+        results = [p[0] for p in pairs]
+        cand = sum(p[1]["candidates_scored"] for p in pairs)
+        dev_ms = sum(p[1]["device_ms"] for p in pairs)
     found = sum(r is not None for r in results)
     # CPU oracle on a bounded sample (single thread per match, sequential)
     sample = jobs[:max(1, min(len(jobs), 3))]

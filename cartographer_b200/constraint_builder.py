@@ -359,7 +359,7 @@ class _Job3:
 
 class CudaExecutor3D:
     """One csm_matcher3d per submap (DispatchScanMatcherConstruction,
-    constraint_builder_3d.cc:172-198); jobs run through csm_match3d."""
+    constraint_builder_3d.cc:172-198); jobs run through csm_match3d_batch."""
 
     def __init__(self, options, device=0, threads=8):
         from . import scan_matching as sm
@@ -377,10 +377,7 @@ class CudaExecutor3D:
 
     def run(self, jobs, submaps, nodes):
         """Matchers are built first (one per submap, like the reference's creation
-        tasks); the matches then run from `threads` host threads at once — the library
-        gives every in-flight call its own CUDA stream (the reference's pool threads
-        call Match concurrently too, constraint_builder_3d.cc:104-113)."""
-        from concurrent.futures import ThreadPoolExecutor
+        tasks); the whole queue then goes to the library in one call."""
         sm, o = self.sm, self.options
         for j in jobs:
             if j.submap_id not in self.matchers:
@@ -395,21 +392,21 @@ class CudaExecutor3D:
                         o.angular_search_window),
                     device=self.device, grid_size_in_voxels=sub.grid_size_in_voxels)
 
-        def one(j):
-            return self.matchers[j.submap_id].match_raw(j.full, j.node_pose, j.submap_pose,
-                                                        nodes[j.node_key], j.min_score)
-
-        if self.threads > 1 and len(jobs) > 1:
-            with ThreadPoolExecutor(max_workers=self.threads) as pool:
-                pairs = list(pool.map(one, jobs))
-        else:
-            pairs = [one(j) for j in jobs]
-        out = []
-        for r, st in pairs:
-            self.stats["candidates_scored"] += st["candidates_scored"]
-            self.stats["device_ms"] += st["device_ms"]
-            self.stats["searched"] += 1
-            out.append(r)
+        # one csm_match3d_batch call: the library keeps `threads` matches in flight on
+        # separate CUDA streams (the reference's pool threads call Match concurrently
+        # too, constraint_builder_3d.cc:104-113)
+        sub_ids = sorted({j.submap_id for j in jobs})
+        node_keys = sorted({j.node_key for j in jobs})
+        sub_index = {k: i for i, k in enumerate(sub_ids)}
+        node_index = {k: i for i, k in enumerate(node_keys)}
+        out, st = sm.match_batch3d(
+            [self.matchers[k] for k in sub_ids], [nodes[k] for k in node_keys],
+            [(sub_index[j.submap_id], node_index[j.node_key], j.full, j.node_pose,
+              j.submap_pose, j.min_score) for j in jobs],
+            max_concurrency=self.threads)
+        self.stats["candidates_scored"] += st["candidates_scored"]
+        self.stats["device_ms"] += st["device_ms"]
+        self.stats["searched"] += len(jobs)
         return out
 
 

@@ -16,6 +16,11 @@
 
 #include "common.cuh"
 
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+
 namespace csm {
 
 constexpr int kMaxDepth3 = 12;
@@ -1256,6 +1261,69 @@ csm_status csm_match3d(const csm_matcher3d* m, const csm_node3d* node, const dou
   CSM_TRY(AcquireLane(m->ctx->device, &guard));
   return Run3D(guard.lane, m, node, node_pose, submap_pose, full, min_score, result, stats, false,
                nullptr, nullptr, nullptr, nullptr);
+}
+
+csm_status csm_match3d_batch(const csm_matcher3d* const* matchers, int32_t num_matchers,
+                             const csm_node3d* nodes, int32_t num_nodes, const csm_job3d* jobs,
+                             int32_t num_jobs, int32_t max_concurrency, csm_result3d* results,
+                             csm_stats* stats) {
+  CSM_REQUIRE(num_jobs >= 0 && num_matchers >= 0 && num_nodes >= 0, "negative count");
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (num_jobs == 0) return CSM_OK;
+  CSM_REQUIRE(matchers && nodes && jobs && results, "null pointer");
+  for (int j = 0; j < num_jobs; ++j) {
+    CSM_REQUIRE(jobs[j].matcher_index >= 0 && jobs[j].matcher_index < num_matchers &&
+                    matchers[jobs[j].matcher_index] != nullptr,
+                "matcher_index out of range");
+    CSM_REQUIRE(jobs[j].node_index >= 0 && jobs[j].node_index < num_nodes,
+                "node_index out of range");
+  }
+  // Worker threads stand in for the reference's pool threads: every csm_match3d call
+  // borrows its own lane (stream + workspace), so the matches overlap on the device.
+  const int workers = std::max(1, std::min(num_jobs, max_concurrency > 0 ? max_concurrency : 8));
+  std::atomic<int> next{0};
+  std::atomic<int> failed{0};
+  std::mutex mu;
+  std::string first_error;
+  csm_status first_status = CSM_OK;
+  csm_stats total;
+  std::memset(&total, 0, sizeof(total));
+  auto work = [&]() {
+    for (;;) {
+      const int j = next.fetch_add(1);
+      if (j >= num_jobs || failed.load()) return;
+      const csm_job3d& jb = jobs[j];
+      csm_stats st;
+      std::memset(&st, 0, sizeof(st));
+      const csm_status rc =
+          csm_match3d(matchers[jb.matcher_index], &nodes[jb.node_index], jb.global_node_pose,
+                      jb.global_submap_pose, jb.full_submap, jb.min_score, &results[j], &st);
+      std::lock_guard<std::mutex> lock(mu);
+      if (rc != CSM_OK) {
+        if (!failed.exchange(1)) {
+          first_status = rc;
+          first_error = csm_last_error_string();  // this worker's thread-local message
+        }
+        return;
+      }
+      total.candidates_scored += st.candidates_scored;
+      total.lowest_resolution_candidates += st.lowest_resolution_candidates;
+      total.nodes_expanded += st.nodes_expanded;
+      total.num_scans += st.num_scans;
+      total.host_tie_resolves += st.host_tie_resolves;
+      total.device_ms += st.device_ms;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < workers; ++w) pool.emplace_back(work);
+  work();
+  for (std::thread& t : pool) t.join();
+  if (failed.load()) {
+    SetError("%s", first_error.c_str());
+    return first_status;
+  }
+  if (stats) *stats = total;
+  return CSM_OK;
 }
 
 csm_status csm_discretize3d(const csm_matcher3d* m, const csm_node3d* node,

@@ -358,13 +358,7 @@ class FastCorrelativeScanMatcher3D:
         check(lib().csm_match3d(self._h, C.byref(holder.c), ptr(npose, C.c_double),
                                 ptr(spose, C.c_double), C.c_int32(int(full)),
                                 C.c_float(min_score), C.byref(res), C.byref(stats)))
-        if not res.found:
-            return None, stats.as_dict()
-        return dict(score=np.float32(res.score), pose_estimate=np.array(res.pose_estimate[:]),
-                    rotational_score=np.float32(res.rotational_score),
-                    low_resolution_score=np.float32(res.low_resolution_score),
-                    best_scan_index=res.best_scan_index, best_offset=tuple(res.best_offset[:]),
-                    leaves_tied=res.leaves_tied), stats.as_dict()
+        return _result3d_dict(res), stats.as_dict()
 
     def Match(self, global_node_pose, global_submap_pose, constant_data, min_score):
         """-> Result dict or None (nullptr), fast_correlative_scan_matcher_3d.cc:127-144.
@@ -407,6 +401,46 @@ class FastCorrelativeScanMatcher3D:
             check(lib().csm_discretize3d(*args, ptr(cells, C.c_int32), ptr(poses, C.c_float),
                                          ptr(rot, C.c_float)))
         return cells, poses, rot
+
+
+class CsmJob3D(C.Structure):
+    _fields_ = [("matcher_index", C.c_int32), ("node_index", C.c_int32),
+                ("full_submap", C.c_int32), ("min_score", C.c_float),
+                ("global_node_pose", C.c_double * 7), ("global_submap_pose", C.c_double * 7)]
+
+
+def _result3d_dict(res):
+    if not res.found:
+        return None
+    return dict(score=np.float32(res.score), pose_estimate=np.array(res.pose_estimate[:]),
+                rotational_score=np.float32(res.rotational_score),
+                low_resolution_score=np.float32(res.low_resolution_score),
+                best_scan_index=res.best_scan_index, best_offset=tuple(res.best_offset[:]),
+                leaves_tied=res.leaves_tied)
+
+
+def match_batch3d(matchers, nodes, jobs, max_concurrency=0):
+    """csm_match3d_batch: a queue of ConstraintBuilder3D searches in one call.
+    jobs: iterable of (matcher_index, node_index, full_submap, global_node_pose[7],
+    global_submap_pose[7], min_score).  -> ([Result dict or None per job], stats dict)."""
+    jobs = list(jobs)
+    holders = [_NodeHolder(n) for n in nodes]
+    c_nodes = (CsmNode3D * max(1, len(holders)))(*[h.c for h in holders])
+    c_matchers = (C.c_void_p * max(1, len(matchers)))(*[m._h for m in matchers])
+    c_jobs = (CsmJob3D * max(1, len(jobs)))()
+    for k, (mi, ni, full, npose, spose, min_score) in enumerate(jobs):
+        c_jobs[k].matcher_index = int(mi)
+        c_jobs[k].node_index = int(ni)
+        c_jobs[k].full_submap = int(bool(full))
+        c_jobs[k].min_score = float(min_score)
+        c_jobs[k].global_node_pose = (C.c_double * 7)(*[float(v) for v in npose])
+        c_jobs[k].global_submap_pose = (C.c_double * 7)(*[float(v) for v in spose])
+    c_res = (CsmResult3D * max(1, len(jobs)))()
+    stats = CsmStats()
+    check(lib().csm_match3d_batch(c_matchers, C.c_int32(len(matchers)), c_nodes,
+                                  C.c_int32(len(holders)), c_jobs, C.c_int32(len(jobs)),
+                                  C.c_int32(int(max_concurrency)), c_res, C.byref(stats)))
+    return [_result3d_dict(c_res[k]) for k in range(len(jobs))], stats.as_dict()
 
 
 def rotational_match(submap_histogram, histogram, initial_angle, angles, device=0):

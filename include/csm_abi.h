@@ -259,6 +259,26 @@ csm_status csm_match3d(const csm_matcher3d* matcher, const csm_node3d* node,
                        int32_t full_submap, float min_score, csm_result3d* result,
                        csm_stats* stats /* may be NULL */);
 
+/* A queue of ConstraintBuilder3D::ComputeConstraint searches
+ * (constraints/constraint_builder_3d.cc:220-223 global, :239-241 local) in one call:
+ * job j matches nodes[node_index] against matchers[matcher_index].  The reference
+ * runs these from its thread pool, one Match per task (:107-116); here the library
+ * keeps up to max_concurrency (0 = default 8) matches in flight on separate CUDA
+ * streams.  results[j] is exactly what csm_match3d returns for job j.  `stats`
+ * (may be NULL) sums candidates_scored / nodes_expanded over the jobs. */
+typedef struct csm_job3d {
+  int32_t matcher_index;
+  int32_t node_index;
+  int32_t full_submap;
+  float min_score;
+  double global_node_pose[7];
+  double global_submap_pose[7];
+} csm_job3d;
+csm_status csm_match3d_batch(const csm_matcher3d* const* matchers, int32_t num_matchers,
+                             const csm_node3d* nodes, int32_t num_nodes, const csm_job3d* jobs,
+                             int32_t num_jobs, int32_t max_concurrency, csm_result3d* results,
+                             csm_stats* stats /* may be NULL */);
+
 /* Test hooks: RotationalScanMatcher::Match (rotational_scan_matcher.cc:178-189) and
  * the discrete scans of a match (GenerateDiscreteScans, :246-295): full-resolution
  * cell indices (num_scans x n x 3), scan poses (num_scans x 7 float: t, q wxyz) and

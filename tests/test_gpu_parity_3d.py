@@ -217,3 +217,45 @@ def test_constraint_builder_3d_on_device(oracle, sm):
         assert c.tag == "INTER_SUBMAP" and np.float32(c.score) == want["score"]
         np.testing.assert_array_equal(np.array(c.zbar_ij), want["pose"])
     b.DeleteScanMatcher((0, 0))
+
+
+def test_match_3d_batch_equals_single_calls(sm):
+    """csm_match3d_batch (the ConstraintBuilder3D queue in one call, several matches in
+    flight on separate streams) returns exactly what csm_match3d returns per job."""
+    from cartographer_b200._lib import CsmError
+    od = dict(branch_and_bound_depth=6, full_resolution_depth=3, min_rotational_score=0.3,
+              min_low_resolution_score=0.25, linear_xy_search_window=1.5,
+              linear_z_search_window=0.5, angular_search_window=0.25)
+    matchers, nodes, poses = [], [], []
+    for seed in (11, 12):
+        hi, lo, cloud, low, hn, hs, node_pose = _building_case(seed)
+        matchers.append(sm.FastCorrelativeScanMatcher3D(hi, lo, hs, _opts(sm, od)))
+        nodes.append(sm.TrajectoryNodeData3D(cloud, low, hn, (1.0, 0.0, 0.0, 0.0)))
+        poses.append(node_pose)
+    sub = [0, 0, 0, 1, 0, 0, 0]
+    jobs = []
+    for mi in range(2):
+        for ni in range(2):
+            for rep in range(3):   # more jobs than distinct pairs: lanes get reused
+                init = poses[ni].copy()
+                init[0] += 0.1 * rep
+                jobs.append((mi, ni, False, init, sub, 0.3))
+    jobs.append((0, 0, True, [0, 0, 0] + list(poses[0][3:]), sub, 0.3))
+    got, st = sm.match_batch3d(matchers, nodes, jobs, max_concurrency=4)
+    assert len(got) == len(jobs) and st["candidates_scored"] > 0
+    found = 0
+    for (mi, ni, full, npose, spose, ms), g in zip(jobs, got):
+        want, _ = matchers[mi].match_raw(full, npose, spose, nodes[ni], ms)
+        assert (g is None) == (want is None)
+        if g is not None:
+            found += 1
+            assert g["score"] == want["score"] and g["best_offset"] == want["best_offset"]
+            assert g["best_scan_index"] == want["best_scan_index"]
+            np.testing.assert_array_equal(g["pose_estimate"], want["pose_estimate"])
+            assert g["low_resolution_score"] == want["low_resolution_score"]
+    assert found >= 3
+    assert sm.match_batch3d(matchers, nodes, [])[0] == []
+    with pytest.raises(CsmError):
+        sm.match_batch3d(matchers, nodes, [(5, 0, False, poses[0], sub, 0.3)])
+    for m in matchers:
+        m.close()
