@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 
+#include "constraint_builder_b200.h"
 #include "scan_matchers_b200.h"
 
 using namespace cartographer;
@@ -79,5 +80,75 @@ int main() {
       std::fabs(result->pose_estimate.translation().y() - ty) > 0.051 ||
       std::fabs(result->pose_estimate.translation().z() - tz) > 0.051)
     return 1;
+
+  // ---- ConstraintBuilder2D / 3D: the reference's call cycle (constraint_builder_2d_test.cc:58-112) ----
+  {
+    using mapping::constraints::ConstraintBuilder2D;
+    mapping::constraints::proto::ConstraintBuilderOptions bo;
+    bo.sampling_ratio_ = 1.0;
+    bo.max_constraint_distance_ = 10.0;
+    bo.min_score_ = 0.5;
+    bo.global_localization_min_score_ = 0.4;
+    bo.fast2d_ = options;
+    common::InlineThreadPool pool;
+    ConstraintBuilder2D builder(bo, &pool);
+    const transform::Rigid2d submap_pose({0.1, -0.05}, 0.02);
+    mapping::Submap2D submap(&grid, submap_pose);
+    mapping::TrajectoryNodeData node;
+    node.filtered_gravity_aligned_point_cloud = cloud;
+    const mapping::SubmapId sid{0, 0};
+    // initial pose (map <- node) = submap_pose * relative; ask for the same start as above
+    const transform::Rigid2d relative = submap_pose.inverse() * transform::Rigid2d({0.2, -0.15}, 0.05);
+    builder.MaybeAddConstraint(sid, &submap, mapping::NodeId{0, 0}, &node, relative);
+    builder.MaybeAddConstraint(sid, &submap, mapping::NodeId{0, 1}, &node,
+                               transform::Rigid2d({100., 0.}, 0.));  // beyond max distance: skipped
+    builder.MaybeAddGlobalConstraint(sid, &submap, mapping::NodeId{0, 2}, &node);
+    builder.NotifyEndOfNode();
+    int calls = 0;
+    ConstraintBuilder2D::Result got;
+    builder.WhenDone([&](const ConstraintBuilder2D::Result& r) { ++calls; got = r; });
+    std::printf("adapter_selftest: ConstraintBuilder2D %d callback(s), %zu constraints, finished nodes %d, %lld candidates\n",
+                calls, got.size(), builder.GetNumFinishedNodes(),
+                static_cast<long long>(builder.last_stats().candidates_scored));
+    if (calls != 1 || got.size() != 2 || builder.GetNumFinishedNodes() != 1) return 1;
+    for (const auto& c : got) {
+      // zbar_ij = submap_pose^-1 * pose_estimate, pose_estimate ~ identity
+      const transform::Rigid2d want = submap_pose.inverse();
+      if (c.tag != ConstraintBuilder2D::Constraint::INTER_SUBMAP ||
+          std::fabs(c.pose.zbar_ij.translation().x() - want.translation().x()) > 0.051 ||
+          std::fabs(c.pose.zbar_ij.translation().y() - want.translation().y()) > 0.051)
+        return 1;
+    }
+    if (got[0].node_id.node_index != 0 || got[1].node_id.node_index != 2) return 1;
+    builder.DeleteScanMatcher(sid);
+  }
+  {
+    using mapping::constraints::ConstraintBuilder3D;
+    mapping::constraints::proto::ConstraintBuilderOptions bo;
+    bo.sampling_ratio_ = 1.0;
+    bo.min_score_ = 0.1;
+    bo.global_localization_min_score_ = 0.1;
+    bo.fast3d_ = o3;
+    common::InlineThreadPool pool;
+    ConstraintBuilder3D builder(bo, &pool);
+    mapping::Submap3D submap(&hybrid, &hybrid, &histogram);
+    const mapping::SubmapId sid{0, 0};
+    builder.MaybeAddConstraint(sid, &submap, mapping::NodeId{0, 0}, &data, transform::Rigid3d(),
+                               transform::Rigid3d());
+    builder.MaybeAddGlobalConstraint(sid, &submap, mapping::NodeId{0, 1}, &data,
+                                     transform::Quaterniond{1., 0., 0., 0.},
+                                     transform::Quaterniond{1., 0., 0., 0.});
+    builder.NotifyEndOfNode();
+    ConstraintBuilder3D::Result got;
+    builder.WhenDone([&](const ConstraintBuilder3D::Result& r) { got = r; });
+    std::printf("adapter_selftest: ConstraintBuilder3D %zu constraints, finished nodes %d\n",
+                got.size(), builder.GetNumFinishedNodes());
+    if (got.empty() || builder.GetNumFinishedNodes() != 1) return 1;
+    if (std::fabs(got[0].pose.zbar_ij.translation().x() - tx) > 0.051 ||
+        std::fabs(got[0].pose.zbar_ij.translation().y() - ty) > 0.051 ||
+        std::fabs(got[0].pose.zbar_ij.translation().z() - tz) > 0.051)
+      return 1;
+    builder.DeleteScanMatcher(sid);
+  }
   return 0;
 }

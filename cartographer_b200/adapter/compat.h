@@ -9,7 +9,10 @@
 #ifndef CSM_ADAPTER_COMPAT_H_
 #define CSM_ADAPTER_COMPAT_H_
 
+#include <cmath>
 #include <cstdint>
+#include <functional>
+#include <memory>
 #include <vector>
 
 namespace cartographer {
@@ -18,13 +21,28 @@ namespace transform {
 // transform/rigid_transform.h:34-103 (Rigid2<double>): translation + Rotation2D angle.
 class Rigid2d {
  public:
-  struct Vector { double x_, y_; double x() const { return x_; } double y() const { return y_; } };
+  struct Vector {
+    double x_, y_;
+    double x() const { return x_; }
+    double y() const { return y_; }
+    double norm() const { return std::sqrt(x_ * x_ + y_ * y_); }
+  };
   struct Rotation2D { double angle_; double angle() const { return angle_; } };
   Rigid2d() : t_{0., 0.}, r_{0.} {}
   Rigid2d(const Vector& t, double rotation) : t_(t), r_{rotation} {}
   static Rigid2d Identity() { return Rigid2d(); }
   const Vector& translation() const { return t_; }
   Rotation2D rotation() const { return r_; }
+  // rigid_transform.h:76-80 and :93-99
+  Rigid2d inverse() const {
+    const double c = std::cos(-r_.angle_), s = std::sin(-r_.angle_);
+    return Rigid2d({-(c * t_.x_ - s * t_.y_), -(s * t_.x_ + c * t_.y_)}, -r_.angle_);
+  }
+  friend Rigid2d operator*(const Rigid2d& a, const Rigid2d& b) {
+    const double c = std::cos(a.r_.angle_), s = std::sin(a.r_.angle_);
+    return Rigid2d({c * b.t_.x_ - s * b.t_.y_ + a.t_.x_, s * b.t_.x_ + c * b.t_.y_ + a.t_.y_},
+                   a.r_.angle_ + b.r_.angle_);
+  }
  private:
   Vector t_;
   Rotation2D r_;
@@ -89,6 +107,7 @@ class HybridGrid {
 // mapping/trajectory_node.h:45-63 (the fields the 3D matcher reads).
 struct TrajectoryNodeData {
   transform::Quaterniond gravity_alignment{1., 0., 0., 0.};
+  sensor::PointCloud filtered_gravity_aligned_point_cloud;   // 2D
   sensor::PointCloud high_resolution_point_cloud;
   sensor::PointCloud low_resolution_point_cloud;
   std::vector<float> rotational_scan_matcher_histogram;   // Eigen::VectorXf
@@ -174,6 +193,129 @@ class FastCorrelativeScanMatcherOptions3D {
 };
 }  // namespace proto
 }  // namespace scan_matching
+}  // namespace mapping
+}  // namespace cartographer
+
+// ---- stand-ins for the ConstraintBuilder's surroundings --------------------------
+namespace cartographer {
+namespace common {
+// common/task.h:36-80 and common/thread_pool.h:35-49, reduced to what the builders use.
+class Task {
+ public:
+  void SetWorkItem(const std::function<void()>& work_item) { work_item_ = work_item; }
+  void Execute() { if (work_item_) work_item_(); }
+ private:
+  std::function<void()> work_item_;
+};
+class ThreadPoolInterface {
+ public:
+  virtual ~ThreadPoolInterface() {}
+  virtual std::weak_ptr<Task> Schedule(std::unique_ptr<Task> task) = 0;
+};
+// Runs every task at once on the calling thread (enough for the self-test; a checkout
+// uses common::ThreadPool).
+class InlineThreadPool : public ThreadPoolInterface {
+ public:
+  std::weak_ptr<Task> Schedule(std::unique_ptr<Task> task) override {
+    std::shared_ptr<Task> shared(std::move(task));
+    shared->Execute();
+    return shared;
+  }
+};
+// common/fixed_ratio_sampler.cc:23-39
+class FixedRatioSampler {
+ public:
+  explicit FixedRatioSampler(double ratio) : ratio_(ratio) {}
+  bool Pulse() {
+    ++num_pulses_;
+    if (static_cast<double>(num_samples_) / num_pulses_ < ratio_) {
+      ++num_samples_;
+      return true;
+    }
+    return false;
+  }
+ private:
+  const double ratio_;
+  int64_t num_pulses_ = 0, num_samples_ = 0;
+};
+}  // namespace common
+
+namespace mapping {
+// mapping/id.h:43-82
+struct SubmapId {
+  int trajectory_id, submap_index;
+  bool operator<(const SubmapId& o) const {
+    return trajectory_id != o.trajectory_id ? trajectory_id < o.trajectory_id
+                                            : submap_index < o.submap_index;
+  }
+};
+struct NodeId {
+  int trajectory_id, node_index;
+  bool operator<(const NodeId& o) const {
+    return trajectory_id != o.trajectory_id ? trajectory_id < o.trajectory_id
+                                            : node_index < o.node_index;
+  }
+};
+// mapping/2d/submap_2d.h:43-73 / mapping/3d/submap_3d.h:41-83: what the builders read.
+class Submap2D {
+ public:
+  Submap2D(const Grid2D* grid, const transform::Rigid2d& local_pose_2d)
+      : grid_(grid), local_pose_2d_(local_pose_2d) {}
+  const Grid2D* grid() const { return grid_; }
+  // stands for transform::Project2D(local_pose()) = ComputeSubmapPose (submap_2d.h, constraint_builder_2d.cc:48-50)
+  const transform::Rigid2d& local_pose_2d() const { return local_pose_2d_; }
+ private:
+  const Grid2D* grid_;
+  transform::Rigid2d local_pose_2d_;
+};
+class Submap3D {
+ public:
+  Submap3D(const HybridGrid* high, const HybridGrid* low, const std::vector<float>* histogram)
+      : high_(high), low_(low), histogram_(histogram) {}
+  const HybridGrid& high_resolution_hybrid_grid() const { return *high_; }
+  const HybridGrid& low_resolution_hybrid_grid() const { return *low_; }
+  const std::vector<float>& rotational_scan_matcher_histogram() const { return *histogram_; }
+ private:
+  const HybridGrid* high_;
+  const HybridGrid* low_;
+  const std::vector<float>* histogram_;
+};
+// mapping/pose_graph_interface.h:36-53
+struct PoseGraphInterface {
+  struct Constraint {
+    struct Pose {
+      transform::Rigid3d zbar_ij;
+      double translation_weight;
+      double rotation_weight;
+    };
+    SubmapId submap_id;
+    NodeId node_id;
+    Pose pose;
+    enum Tag { INTRA_SUBMAP, INTER_SUBMAP } tag;
+  };
+};
+namespace constraints {
+namespace proto {
+// constraints/proto/constraint_builder_options.proto (fields on the path)
+struct ConstraintBuilderOptions {
+  double sampling_ratio_ = 0.3, max_constraint_distance_ = 15., min_score_ = 0.55,
+         global_localization_min_score_ = 0.6, loop_closure_translation_weight_ = 1.1e4,
+         loop_closure_rotation_weight_ = 1e5;
+  scan_matching::proto::FastCorrelativeScanMatcherOptions2D fast2d_;
+  scan_matching::proto::FastCorrelativeScanMatcherOptions3D fast3d_;
+  double sampling_ratio() const { return sampling_ratio_; }
+  double max_constraint_distance() const { return max_constraint_distance_; }
+  double min_score() const { return min_score_; }
+  double global_localization_min_score() const { return global_localization_min_score_; }
+  double loop_closure_translation_weight() const { return loop_closure_translation_weight_; }
+  double loop_closure_rotation_weight() const { return loop_closure_rotation_weight_; }
+  const scan_matching::proto::FastCorrelativeScanMatcherOptions2D&
+  fast_correlative_scan_matcher_options() const { return fast2d_; }
+  const scan_matching::proto::FastCorrelativeScanMatcherOptions3D&
+  fast_correlative_scan_matcher_options_3d() const { return fast3d_; }
+};
+}  // namespace proto
+}  // namespace constraints
 }  // namespace mapping
 }  // namespace cartographer
 
