@@ -318,16 +318,15 @@ __global__ void __launch_bounds__(128)
 k_score_top_small(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
                   const short2* __restrict__ dscan, int* __restrict__ top_sum,
                   const long long* __restrict__ scan_slot_base, int total_scans, int lanes) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) int2 s_small[];  // [warp][scan of the warp][32 points]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int spw = 32 / lanes;                 // scans per warp
   const int sub = lane / lanes, ql = lane - sub * lanes;
-  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long sgl = warp * spw + sub;
-  if (sub >= spw || sgl >= total_scans) return;
-  const int sg = static_cast<int>(sgl);
+  const long long gwarp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long sgl = gwarp * spw + sub;
+  const bool has_scan = sub < spw && sgl < total_scans;
+  const int sg = has_scan ? static_cast<int>(sgl) : 0;
   const ScanInfo si = info[sg];
-  const int qr = (si.nxc + 3) >> 2;
-  if (ql >= qr * si.nyc) return;
   const JobDev& jb = jobs[si.job];
   const StackDev& st = *jb.stack;
   const int h = st.depth - 1;
@@ -335,46 +334,74 @@ k_score_top_small(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ 
   const int id = st.dec_id[h], jd = st.dec_jd[h], ids = st.dec_ids[h];
   const unsigned lpad1 = static_cast<unsigned>(st.dec_lpad[h]) - 1u;
   const uint8_t* __restrict__ dec = st.dec4[h] + 16;
+  const int qr = (si.nxc + 3) >> 2;
+  const bool owns = has_scan && ql < qr * si.nyc;   // this lane scores a quad
   const int jy = ql / qr, i0 = (ql - jy * qr) << 2;
   const int toff = jy * ids + i0;
   const int ox = si.min_x + s1, oy = si.min_y + s1;
   const short2* __restrict__ pts = dscan + jb.dscan_off +
                                  static_cast<long long>(sg - jb.scan_base) * jb.n;
+  int2* __restrict__ s_pt = s_small + (warp * spw + (sub < spw ? sub : 0)) * 32;
+  // all jobs of a batch have the same point count only per job: the warp walks the
+  // longest of its scans, lanes of shorter scans idle
+  int n_max = has_scan ? jb.n : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
   unsigned sum0 = 0, sum1 = 0, sum2 = 0, sum3 = 0;
-  constexpr int kU = 4;
-  for (int p0 = 0; p0 < jb.n; p0 += 256) {
-    const int pend = min(jb.n, p0 + 256);
-    unsigned a02 = 0, a13 = 0;
-    for (int p = p0; p < pend; p += kU) {
-      short2 c[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) c[u] = pts[min(p + u, pend - 1)];
-      unsigned w[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int bx = c[u].x + ox, by = c[u].y + oy;
-        const int qx = bx >> h, qy = by >> h;  // floor division
-        const int J = qy + jy, c3 = qx + i0 + 3;
-        w[u] = 0u;
-        if (p + u < pend && static_cast<unsigned>(J) < static_cast<unsigned>(jd) &&
-            static_cast<unsigned>(c3) < static_cast<unsigned>(id + 3)) {
-          const int a = ((((by & s1) << h) | (bx & s1)) * jd + qy) * ids + qx + toff;
-          const unsigned k = static_cast<unsigned>(a) & 3u;
-          w[u] = __ldg(reinterpret_cast<const unsigned*>(
-              dec + static_cast<long long>(a) + static_cast<long long>(k * lpad1)));
+  unsigned a02 = 0, a13 = 0;
+  for (int p0 = 0; p0 < n_max; p0 += 32) {
+    // the scan's lanes stage {D index of the lattice origin, qy << 16 | qx} of 32 points
+    __syncwarp();
+    if (has_scan) {
+      for (int t = ql; t < 32; t += lanes) {
+        int2 d = make_int2(0, static_cast<int>(0x80008000u));  // never in range
+        if (p0 + t < jb.n) {
+          const short2 c = pts[p0 + t];
+          const int bx = c.x + ox, by = c.y + oy;
+          const int qx = bx >> h, qy = by >> h;  // floor division
+          if (qx > -32000 && qx < 32000 && qy > -32000 && qy < 32000)
+            d = make_int2(((((by & s1) << h) | (bx & s1)) * jd + qy) * ids + qx,
+                          (qy << 16) | (qx & 0xffff));
         }
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        a02 += __byte_perm(w[u], 0u, 0x4240);  // bytes 0 and 2 in u16 lanes
-        a13 += __byte_perm(w[u], 0u, 0x4341);  // bytes 1 and 3
+        s_pt[t] = d;
       }
     }
-    sum0 += a02 & 0xffffu;
-    sum2 += a02 >> 16;
-    sum1 += a13 & 0xffffu;
-    sum3 += a13 >> 16;
+    __syncwarp();
+    if (owns) {
+#pragma unroll 8
+      for (int t = 0; t < 32; t += 2) {
+        const int4 d = *reinterpret_cast<const int4*>(s_pt + t);
+        const int Ja = (d.y >> 16) + jy, ca = static_cast<short>(d.y & 0xffff) + i0 + 3;
+        const int Jb = (d.w >> 16) + jy, cb = static_cast<short>(d.w & 0xffff) + i0 + 3;
+        if (static_cast<unsigned>(Ja) < static_cast<unsigned>(jd) &&
+            static_cast<unsigned>(ca) < static_cast<unsigned>(id + 3)) {
+          const int a = d.x + toff;
+          const unsigned k = static_cast<unsigned>(a) & 3u;
+          const unsigned w = __ldg(reinterpret_cast<const unsigned*>(
+              dec + static_cast<long long>(a) + static_cast<long long>(k * lpad1)));
+          a02 += __byte_perm(w, 0u, 0x4240);  // bytes 0 and 2 in u16 lanes
+          a13 += __byte_perm(w, 0u, 0x4341);  // bytes 1 and 3
+        }
+        if (static_cast<unsigned>(Jb) < static_cast<unsigned>(jd) &&
+            static_cast<unsigned>(cb) < static_cast<unsigned>(id + 3)) {
+          const int a = d.z + toff;
+          const unsigned k = static_cast<unsigned>(a) & 3u;
+          const unsigned w = __ldg(reinterpret_cast<const unsigned*>(
+              dec + static_cast<long long>(a) + static_cast<long long>(k * lpad1)));
+          a02 += __byte_perm(w, 0u, 0x4240);
+          a13 += __byte_perm(w, 0u, 0x4341);
+        }
+      }
+    }
+    if (((p0 + 32) & 255) == 0 || p0 + 32 >= n_max) {  // flush the packed u16 sums
+      sum0 += a02 & 0xffffu;
+      sum2 += a02 >> 16;
+      sum1 += a13 & 0xffffu;
+      sum3 += a13 >> 16;
+      a02 = a13 = 0u;
+    }
   }
+  if (!owns) return;
   int* __restrict__ out = top_sum + scan_slot_base[sg];
   const unsigned sums[4] = {sum0, sum1, sum2, sum3};
 #pragma unroll
@@ -1738,7 +1765,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   ProfBegin(ctx);
   if (use_small_top) {
     const int spw = 32 / small_lanes;
-    k_score_top_small<<<DivUp(DivUp(total_scans, spw), 4), 128, 0, s>>>(
+    k_score_top_small<<<DivUp(DivUp(total_scans, spw), 4), 128, 4 * spw * 32 * sizeof(int2), s>>>(
         d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_top.as<int>(),
         d_slot_base.as<long long>(), total_scans, small_lanes);
   } else if (use_gather_top) {
