@@ -763,6 +763,16 @@ __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const Scan
   return 1u | (y2 ? 2u : 0u) | (x2 ? 4u : 0u) | ((x2 && y2) ? 8u : 0u);
 }
 
+// scan -> job and scan -> first lowest-resolution slot, one CTA per job.
+__global__ void k_scan_tables(const JobDev* __restrict__ jobs, int* __restrict__ scan_job,
+                              long long* __restrict__ scan_slot_base) {
+  const JobDev& d = jobs[blockIdx.x];
+  for (int k = threadIdx.x; k < d.num_scans; k += blockDim.x) {
+    scan_job[d.scan_base + k] = blockIdx.x;
+    scan_slot_base[d.scan_base + k] = d.top_off + static_cast<long long>(k) * d.cap;
+  }
+}
+
 // Per-job maximum of the lowest-resolution sums (one warp per scan -> atomicMax).
 __global__ void __launch_bounds__(256)
 k_job_best(const ScanInfo* __restrict__ info, const int* __restrict__ top_sum,
@@ -973,14 +983,13 @@ k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
 }
 
 // ---- scan-grouped branch step ------------------------------------------------
-// The children of all frontier nodes of ONE rotated scan lie on that scan's
-// lattice of stride s = 2^(h-1), so — exactly like the lowest-resolution pass —
-// the cells they need for one scan point are neighbouring bytes of one tile of the
-// decimated level h-1.  Parents are first grouped by scan (counting sort), then one
-// CTA handles up to 128 parents of a scan: point descriptors are staged once in
-// shared memory and every thread fetches the 2 x 2 children of its parent with two
-// aligned 32-bit loads per point (vs. four scattered byte gathers + a point load
-// in the warp-per-parent form).
+// The frontier nodes of ONE rotated scan lie on that scan's lattice of stride
+// S = 2^h, so for one scan point the child-window words (StackDev::win) of lattice
+// neighbours are neighbouring words of one phase tile.  Parents are first grouped by
+// scan (counting sort), then one WARP handles a work item of up to 32 parents of a
+// scan: point descriptors are staged once per item in shared memory and every lane
+// fetches the 2 x 2 children of its parent with ONE aligned 32-bit load per point (vs.
+// a point load + a scattered word per lane in the warp-per-parent form).
 struct WorkItem { int scan, start, count; };
 
 __global__ void k_q_count(const Node* __restrict__ nodes, int count, int* __restrict__ scan_cnt) {
@@ -1104,9 +1113,12 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
   __shared__ __align__(16) int2 s_all[kLatThreads / 32][kLatChunk];  // {window index of lattice origin, Qy << 16 | Qx}
   // (8 B per point: a smaller shared-memory carve-out leaves more L1 for the tiles)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * (kLatThreads / 32) + warp;
-  if (item >= *num_items) return;
   int2* s_pt = s_all[warp];
+  const int n_items = *num_items;
+  // the grid is capped (the exact item count is only known on the device): every warp
+  // walks items warp, warp + total warps, ...
+  for (int item = blockIdx.x * (kLatThreads / 32) + warp; item < n_items;
+       item += gridDim.x * (kLatThreads / 32)) {
   const WorkItem it = items[item];
   // With few parents, G = 2^lg lanes share one parent and split the scan points
   // (lane = parent * G + sub, sub-lane `sub` takes the point pairs sub, sub + G, ...).
@@ -1196,7 +1208,7 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
 #pragma unroll
   for (int t = 0; t < 4; ++t) sc[t] = ToScore(st, sums[t], jb.n);
   if (lv == 0) {
-    if (!lead) return;
+    if (!lead) continue;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       if (!((valid >> t) & 1u) || !(sc[t] > jb.min_score)) continue;
@@ -1210,7 +1222,7 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
           *overflow = 1;
       }
     }
-    return;
+    continue;
   }
   // Survivors are appended row by row (all lanes' children of lattice row 2*j0, then
   // row 2*j0+1; within a row in lane order, x ascending) with one atomic per warp.
@@ -1243,6 +1255,7 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
   if (keep & 8u) {
     if (p < next_cap) next[p] = Node{nd.scan, nd.xo + s, nd.yo + s, sc[3]}; else *overflow = 1;
   }
+  }  // items
 }
 
 // Keeps the leaves whose score equals their job's final optimum.
@@ -1527,8 +1540,6 @@ struct BatchPlan {
   std::vector<JobDev> jobs;
   std::vector<HostSearch> search;
   std::vector<double> init_x, init_y, init_theta;
-  std::vector<int> scan_job;
-  std::vector<long long> scan_slot_base;
   long long total_scans = 0, total_points = 0, total_slots = 0;
 };
 
@@ -1641,15 +1652,14 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     plan.total_slots += static_cast<long long>(sp.num_scans) * d.cap;
     CSM_REQUIRE(plan.total_scans < (1LL << 30), "too many scans in one batch");
   }
-  plan.scan_job.resize(plan.total_scans);
-  plan.scan_slot_base.resize(plan.total_scans);
-  for (int j = 0; j < num_jobs; ++j) {
-    const JobDev& d = plan.jobs[j];
-    for (int k = 0; k < d.num_scans; ++k) {
-      plan.scan_job[d.scan_base + k] = j;
-      plan.scan_slot_base[d.scan_base + k] = d.top_off + static_cast<long long>(k) * d.cap;
-    }
-  }
+  // scan -> job on the host (few lookups: optimal leaves only); the per-scan tables
+  // themselves are written on the device (k_scan_tables)
+  std::vector<int> scan_bases(num_jobs);
+  for (int j = 0; j < num_jobs; ++j) scan_bases[j] = plan.jobs[j].scan_base;
+  auto job_of_scan = [&](int scan) {
+    return static_cast<int>(std::upper_bound(scan_bases.begin(), scan_bases.end(), scan) -
+                            scan_bases.begin()) - 1;
+  };
 
   phase("host plan");
   // ---- device buffers ----
@@ -1677,10 +1687,9 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
                            cudaMemcpyHostToDevice, s));
   CSM_CUDA(cudaMemcpyAsync(d_jobs.p, plan.jobs.data(), sizeof(JobDev) * num_jobs,
                            cudaMemcpyHostToDevice, s));
-  CSM_CUDA(cudaMemcpyAsync(d_scan_job.p, plan.scan_job.data(), sizeof(int) * plan.total_scans,
-                           cudaMemcpyHostToDevice, s));
-  CSM_CUDA(cudaMemcpyAsync(d_slot_base.p, plan.scan_slot_base.data(),
-                           sizeof(long long) * plan.total_scans, cudaMemcpyHostToDevice, s));
+  k_scan_tables<<<num_jobs, 256, 0, s>>>(d_jobs.as<JobDev>(), d_scan_job.as<int>(),
+                                         d_slot_base.as<long long>());
+  CSM_LAUNCH_CHECK();
   CSM_CUDA(cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 8 + sizeof(int) * 32, s));
   unsigned long long* ctr = d_ctr.as<unsigned long long>();
   int* ictr = reinterpret_cast<int*>(ctr + 8);  // [0..15] queue counts, [16] leaf, [17] best, [20] overflow
@@ -1915,9 +1924,10 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     CSM_CUDA(cudaMemcpy(tmp.data(), d_leaves.p, sizeof(Node) * qn[0], cudaMemcpyDeviceToHost));
     std::vector<unsigned> lbh(num_jobs);
     CSM_CUDA(cudaMemcpy(lbh.data(), d_lb.p, sizeof(unsigned) * num_jobs, cudaMemcpyDeviceToHost));
-    std::vector<int> sj(plan.scan_job);
-    for (const Node& nd : tmp)
-      lbh[sj[nd.scan]] = std::max(lbh[sj[nd.scan]], HostFloatToOrdered(nd.score));
+    for (const Node& nd : tmp) {
+      const int j = job_of_scan(nd.scan);
+      lbh[j] = std::max(lbh[j], HostFloatToOrdered(nd.score));
+    }
     CSM_CUDA(cudaMemcpy(d_lb.p, lbh.data(), sizeof(unsigned) * num_jobs, cudaMemcpyHostToDevice));
     qn[0] = 0;
   }
@@ -1960,10 +1970,11 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
         ProfCommit(ctx, "k_q_sort", chunk);
       }
       const int max_items = chunk / 32 + std::min(chunk, total_scans) + 1;
+      const int lat_grid = std::min(DivUp(max_items, kLatThreads / 32), ctx->sm_count * 64);
       ProfBegin(ctx);
       static const int lat_unroll = getenv("CSM_LAT_UNROLL") ? atoi(getenv("CSM_LAT_UNROLL")) : 8;
 #define CSM_LATTICE(U)                                                                          \
-      k_expand_lattice<U><<<DivUp(max_items, kLatThreads / 32), kLatThreads, 0, s>>>(           \
+      k_expand_lattice<U><<<lat_grid, kLatThreads, 0, s>>>(                                     \
           d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_sorted.as<Node>(), \
           d_items.as<WorkItem>(), ictr + 24, h, d_lb.as<unsigned>(),                            \
           h - 1 >= 1 ? queue_ptr(h - 1) : nullptr, ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap, \
@@ -2049,7 +2060,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
 
   // group optimal leaves by job
   std::vector<std::vector<TieLeaf>> per_job(num_jobs);
-  for (const Node& nd : best) per_job[plan.scan_job[nd.scan]].push_back(TieLeaf{nd.scan, nd.xo, nd.yo});
+  for (const Node& nd : best) per_job[job_of_scan(nd.scan)].push_back(TieLeaf{nd.scan, nd.xo, nd.yo});
 
   // ---- tie resolution: the reference returns the first optimal leaf in DFS order ----
   int host_resolves = 0;
