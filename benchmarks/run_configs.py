@@ -218,6 +218,8 @@ def cfg3_5(scale, which):
     found = sum(r is not None for r in results)
     # CPU oracle on a bounded sample (single thread per match, sequential)
     sample = jobs[:max(1, min(len(jobs), 3))]
+    if os.environ.get("CSM_SKIP_CPU"):   # A/B timing of kernel variants: no oracle leg
+        sample = []
     ccand, ok = 0, True
     t_cpu = 0.0
     for ji, (si, n, init) in enumerate(sample):
@@ -260,8 +262,9 @@ def cfg3_5(scale, which):
             "gpu_device_ms_per_match": dev_ms / len(jobs), "gpu_wall_ms_per_match": 1e3 * gpu_s / len(jobs),
             "gpu_matcher_build_ms": 1e3 * build_s / n_sub, "gpu_host_threads": threads_gpu,
             "kernels_of_one_found_match": prof,
-            "cpu_sample_matches": len(sample), "cpu_matches_per_s_1thread": len(sample) / t_cpu,
-            "cpu_cand_per_s_1thread": ccand / t_cpu, "parity_ok": bool(ok)}
+            "cpu_sample_matches": len(sample),
+            "cpu_matches_per_s_1thread": len(sample) / t_cpu if t_cpu else None,
+            "cpu_cand_per_s_1thread": ccand / t_cpu if t_cpu else None, "parity_ok": bool(ok)}
 
 
 def main():

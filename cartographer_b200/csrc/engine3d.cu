@@ -226,7 +226,10 @@ __global__ void k3_discretize(Job3 jb) {
 // base + half * {ix, iy, iz}, slot t = 4*iz + 2*iy + ix (the reference's child
 // generation order: z outer, y, x inner, :412-430).  `mask` selects the slots.
 // All threads of the CTA take part; sums[] is valid in thread 0 only.
-constexpr int kT3 = 256;
+#ifndef CSM_T3
+#define CSM_T3 512   // 256: 0.57 ms dive, 512: 0.33 ms, 1024: 0.24 ms but one CTA per SM
+#endif
+constexpr int kT3 = CSM_T3;   // threads per CTA of the 3D scoring kernels
 __device__ __forceinline__ void ScoreOct(const Job3& jb, int scan, int depth, int bx, int by,
                                          int bz, int half, unsigned mask, int sums[8],
                                          int* s_red) {
