@@ -10,7 +10,47 @@
 
 using namespace cartographer;
 
+// Host-only part (runs everywhere): the builder's gating and WhenDone cycle when no
+// pair survives the gates — nothing reaches the device — and the sampler's sequence
+// (common/fixed_ratio_sampler_test.cc).
+static int HostOnlyChecks() {
+  using mapping::constraints::ConstraintBuilder2D;
+  common::FixedRatioSampler half(0.5);
+  const bool want[6] = {true, false, true, false, true, false};
+  for (bool w : want)
+    if (half.Pulse() != w) return 1;
+  mapping::constraints::proto::ConstraintBuilderOptions bo;
+  bo.sampling_ratio_ = 1.0;
+  bo.max_constraint_distance_ = 1.0;
+  common::InlineThreadPool pool;
+  ConstraintBuilder2D builder(bo, &pool);
+  const std::vector<uint16_t> cells(16, 0);
+  mapping::Grid2D grid(mapping::MapLimits(0.05, 0.2, 0.2, mapping::CellLimits{4, 4}), 0.1f, 0.9f,
+                       cells);
+  mapping::Submap2D submap(&grid, transform::Rigid2d());
+  mapping::TrajectoryNodeData node;
+  builder.MaybeAddConstraint(mapping::SubmapId{0, 0}, &submap, mapping::NodeId{0, 0}, &node,
+                             transform::Rigid2d({5., 0.}, 0.));  // beyond max_constraint_distance
+  builder.NotifyEndOfNode();
+  int calls = 0;
+  size_t constraints = 99;
+  builder.WhenDone([&](const ConstraintBuilder2D::Result& r) { ++calls; constraints = r.size(); });
+  if (calls != 1 || constraints != 0 || builder.GetNumFinishedNodes() != 1) return 1;
+  // Rigid2d algebra used for the constraint transform
+  const transform::Rigid2d a({1., 2.}, 0.3);
+  const transform::Rigid2d id = a.inverse() * a;
+  if (std::fabs(id.translation().x()) > 1e-12 || std::fabs(id.translation().y()) > 1e-12 ||
+      std::fabs(id.rotation().angle()) > 1e-12)
+    return 1;
+  std::printf("adapter_selftest: host-only checks passed\n");
+  return 0;
+}
+
 int main() {
+  if (HostOnlyChecks() != 0) {
+    std::printf("adapter_selftest: host-only checks FAILED\n");
+    return 1;
+  }
   int32_t devices = 0;
   if (csm_device_count(&devices) != CSM_OK || devices == 0) {
     std::printf("adapter_selftest: no CUDA device (%s) — link check only\n",

@@ -29,3 +29,5 @@ def test_adapter_headers_compile_and_link():
     out = subprocess.run([os.path.join(ADAPTER, "adapter_selftest")], capture_output=True,
                          text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
+    # the builder's gating / WhenDone cycle and the sampler sequence run without a device
+    assert "host-only checks passed" in out.stdout
