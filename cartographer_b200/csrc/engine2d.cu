@@ -1414,11 +1414,7 @@ csm_status csm_stack2d_destroy(csm_stack2d* stack) {
   std::lock_guard<std::mutex> lock(stack->ctx->mu);
   cudaSetDevice(stack->ctx->device);
   cudaStreamSynchronize(stack->ctx->stream);
-  cudaFree(stack->d_levels);
-  cudaFree(stack->d_dec);
-  cudaFree(stack->d_win);
-  cudaFree(stack->d);
-  delete stack;
+  delete stack;  // the destructor frees the device buffers
   return CSM_OK;
 }
 
@@ -1488,11 +1484,11 @@ csm_status csm_cloud_destroy(csm_cloud* cloud) {
       ctx->cloud_pool_bytes + cloud->d_bytes <= (256u << 20)) {
     ctx->cloud_pool.emplace_back(cloud->d_xyz, cloud->d_bytes);
     ctx->cloud_pool_bytes += cloud->d_bytes;
+    cloud->d_xyz = nullptr;  // now owned by the pool
   } else {
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(cloud->d_xyz);
   }
-  delete cloud;
+  delete cloud;  // frees d_xyz unless it was pooled
   return CSM_OK;
 }
 

@@ -91,6 +91,13 @@ struct csm_stack2d {
   unsigned* d_win = nullptr;
   size_t level_off[csm::kMaxDepth];
   float min_cost = 0.f, max_cost = 0.f;
+  // also runs when csm_stack2d_create fails half-way (cudaFree(nullptr) is a no-op)
+  ~csm_stack2d() {
+    cudaFree(d_levels);
+    cudaFree(d_dec);
+    cudaFree(d_win);
+    cudaFree(d);
+  }
 };
 
 struct csm_cloud {
@@ -100,6 +107,7 @@ struct csm_cloud {
   size_t d_bytes = 0;   // capacity of d_xyz (buffers are recycled through Ctx::cloud_pool)
   float max_norm = 0.f;  // max_i sqrt(x*x + y*y) in float (correlative_scan_matcher_2d.cc:35-38)
   std::vector<float> h_xyz;
+  ~csm_cloud() { cudaFree(d_xyz); }  // nullptr once the buffer went back to the pool
 };
 
 #endif  // CSM_ENGINE2D_CUH_

@@ -533,6 +533,14 @@ struct csm_matcher3d {
   std::vector<float> hist;
   csm_options3d opt;
   int grid_size = 0;
+  // also runs when csm_matcher3d_create fails half-way (cudaFree(nullptr) is a no-op)
+  ~csm_matcher3d() {
+    cudaFree(d_levels);
+    cudaFree(d_lowvol);
+    cudaFree(d_stack);
+    cudaFree(d_low);
+    cudaFree(d_hist);
+  }
 };
 
 namespace {
@@ -781,12 +789,7 @@ csm_status csm_matcher3d_destroy(csm_matcher3d* m) {
   std::lock_guard<std::mutex> lock(m->ctx->mu);
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
-  cudaFree(m->d_levels);
-  cudaFree(m->d_lowvol);
-  cudaFree(m->d_stack);
-  cudaFree(m->d_low);
-  cudaFree(m->d_hist);
-  delete m;
+  delete m;  // the destructor frees the device buffers
   return CSM_OK;
 }
 
