@@ -131,10 +131,13 @@ class MapLimits {
   CellLimits cell_limits_;
 };
 // mapping/2d/grid_2d.h:37-141 — the read-only accessors the matcher ctor uses.
+enum class GridType { PROBABILITY_GRID, TSDF };  // mapping/2d/grid_2d.h:35
 class Grid2D {
  public:
   Grid2D(const MapLimits& limits, float min_cost, float max_cost, std::vector<uint16_t> cells)
       : limits_(limits), min_(min_cost), max_(max_cost), cells_(std::move(cells)) {}
+  virtual ~Grid2D() {}
+  virtual GridType GetGridType() const { return GridType::PROBABILITY_GRID; }
   const MapLimits& limits() const { return limits_; }
   float GetMinCorrespondenceCost() const { return min_; }
   float GetMaxCorrespondenceCost() const { return max_; }
@@ -145,6 +148,25 @@ class Grid2D {
   MapLimits limits_;
   float min_, max_;
   std::vector<uint16_t> cells_;
+};
+
+// mapping/2d/tsdf_2d.h:32-80 — what the real-time matcher's TSDF branch reads: the TSD
+// cells (Grid2D::correspondence_cost_cells), the weight cells and the TSDValueConverter
+// parameters (mapping/internal/2d/tsd_value_converter.h:32-43).
+class TSDF2D : public Grid2D {
+ public:
+  TSDF2D(const MapLimits& limits, float truncation_distance, float max_weight,
+         std::vector<uint16_t> tsd_cells, std::vector<uint16_t> weight_cells)
+      : Grid2D(limits, -truncation_distance, truncation_distance, std::move(tsd_cells)),
+        truncation_distance_(truncation_distance), max_weight_(max_weight),
+        weight_cells_(std::move(weight_cells)) {}
+  GridType GetGridType() const override { return GridType::TSDF; }
+  float truncation_distance() const { return truncation_distance_; }
+  float max_weight() const { return max_weight_; }
+  const std::vector<uint16_t>& weight_cells() const { return weight_cells_; }
+ private:
+  float truncation_distance_, max_weight_;
+  std::vector<uint16_t> weight_cells_;
 };
 
 namespace scan_matching {

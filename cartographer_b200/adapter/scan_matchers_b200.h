@@ -112,7 +112,7 @@ class FastCorrelativeScanMatcher2D {
   csm_stack2d* stack_ = nullptr;
 };
 
-// real_time_correlative_scan_matcher_2d.h:53-85 (ProbabilityGrid path)
+// real_time_correlative_scan_matcher_2d.h:53-85 (ProbabilityGrid and TSDF grids)
 class RealTimeCorrelativeScanMatcher2D {
  public:
   explicit RealTimeCorrelativeScanMatcher2D(
@@ -129,6 +129,20 @@ class RealTimeCorrelativeScanMatcher2D {
                             initial_pose_estimate.translation().y(),
                             initial_pose_estimate.rotation().angle()};
     double score = 0., pose[3] = {0., 0., 0.};
+#ifndef CSM_ADAPTER_REAL_CARTOGRAPHER
+    if (grid.GetGridType() == GridType::TSDF) {  // real_time…2d.cc:160-166
+      const TSDF2D& tsdf = static_cast<const TSDF2D&>(grid);
+      b200_internal::Check(csm_rt_match2d_tsdf(
+          tsdf.correspondence_cost_cells().data(), tsdf.weight_cells().data(),
+          l.cell_limits().num_x_cells, l.cell_limits().num_y_cells, l.resolution(), l.max().x(),
+          l.max().y(), tsdf.truncation_distance(), tsdf.max_weight(), xyz.data(),
+          static_cast<int32_t>(point_cloud.size()), init, options_.linear_search_window(),
+          options_.angular_search_window(), options_.translation_delta_cost_weight(),
+          options_.rotation_delta_cost_weight(), device_, &score, pose, nullptr));
+      *pose_estimate = transform::Rigid2d({pose[0], pose[1]}, pose[2]);
+      return score;
+    }
+#endif
     b200_internal::Check(csm_rt_match2d(
         grid.correspondence_cost_cells().data(), l.cell_limits().num_x_cells,
         l.cell_limits().num_y_cells, l.resolution(), l.max().x(), l.max().y(), xyz.data(),
