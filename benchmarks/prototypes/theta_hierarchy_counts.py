@@ -46,17 +46,15 @@ def score(pg, off, pts, xo, yo):
     return out
 
 
-def main():
-    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-    grid, scans = bench.make_world(seed, 1)
-    cloud = scans[0]
+def study(grid, cloud, init, full, lin, ang, depth, min_score, schedules, verbose=True):
     og = oracle.Grid2D(grid.cells, grid.resolution, grid.max_x, grid.max_y)
-    depth = bench.DEPTH
-    om = oracle.FastCorrelativeScanMatcher2D(og, bench.LIN, bench.ANG, depth)
-    want = om.match_full_submap(cloud, bench.MIN_SCORE)
+    om = oracle.FastCorrelativeScanMatcher2D(og, lin, ang, depth)
+    want = om.match_full_submap(cloud, min_score) if full else om.match(init, cloud, min_score)
+    if not want["found"]:
+        return None
     n = len(cloud)
     # integer threshold equivalent to score >= S*
-    fe = oracle.frontend2d(og, cloud, (0, 0, 0), full=True)
+    fe = oracle.frontend2d(og, cloud, init, full=full, lin=lin, ang=ang)
     ds = fe["discrete_scans"].astype(np.int64)     # (S, n, 2)
     bounds = fe["bounds"].astype(np.int64)         # (S, 4) min_x max_x min_y max_y
     S = len(ds)
@@ -64,8 +62,9 @@ def main():
     # find S* as an integer sum: best leaf sum over the whole window is what the oracle found
     k, bx, by = want["best_scan_index"], want["best_x_offset"], want["best_y_offset"]
     s_star = int(score(levels[0][0], levels[0][1], ds[k], np.array([bx]), np.array([by]))[0])
-    print("match: scans %d, points %d, S* sum %d (score %.4f), found %s" %
-          (S, n, s_star, want["score"], want["found"]))
+    if verbose:
+        print("match: scans %d, points %d, S* sum %d (score %.4f), found %s" %
+              (S, n, s_star, want["score"], want["found"]))
     t0 = time.time()
 
     # ---- today's tree: per scan, top lattice at h = depth-1, expand nodes with bound >= S* ----
@@ -107,9 +106,12 @@ def main():
         evals_now[h - 1] = cnt
         fk, fx, fy = np.concatenate(nk), np.concatenate(nx), np.concatenate(ny)
     leaves_now = set(zip(fk.tolist(), fx.tolist(), fy.tolist()))
-    print("today's tree   : evaluations per level (top..0):",
-          [evals_now[h] for h in range(top, -1, -1)], "total", sum(evals_now.values()),
-          "optimal leaves", len(fk), "[%.0f s]" % (time.time() - t0))
+    if verbose:
+        print("today's tree   : evaluations per level (top..0):",
+              [evals_now[h] for h in range(top, -1, -1)], "total", sum(evals_now.values()),
+              "optimal leaves", len(fk), "[%.0f s]" % (time.time() - t0))
+    # the oracle's answer is one of the optimal leaves
+    assert (want["best_scan_index"], want["best_x_offset"], want["best_y_offset"]) in leaves_now
 
     # ---- joint trees: a schedule of (g, h) node types, g = log2(rotations per node) ----
     def run_schedule(schedule):
@@ -177,18 +179,48 @@ def main():
             g, h = g2, h2
         return evals, set(zip(fk.tolist(), fx.tolist(), fy.tolist()))
 
+    out = {}
+    for name, sch in schedules.items():
+        t0 = time.time()
+        ev, leaves = run_schedule(sch)
+        out[name] = (sum(ev.values()), leaves == leaves_now)
+        if verbose:
+            print("%-26s total %8d  same leaves %s  per (g,h): %s  [%.0f s]" %
+                  (name, sum(ev.values()), leaves == leaves_now, ev, time.time() - t0))
+    return out
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--check":
+        # exactness check on many small worlds (local and full-submap searches, depth 5)
+        from tests import worlds
+        sch = {"reference order": [(0, 4), (0, 3), (0, 2), (0, 1), (0, 0)],
+               "joint": [(3, 4), (2, 3), (1, 2), (0, 1), (0, 0)],
+               "theta first": [(3, 4), (1, 4), (0, 4), (0, 3), (0, 2), (0, 1), (0, 0)]}
+        bad = 0
+        for seed in range(int(sys.argv[2])):
+            grid, occ, pose, scan = worlds.small_world(seed, size_cells=120 + 10 * (seed % 5))
+            rng = np.random.RandomState(seed)
+            full = seed % 3 == 0
+            init = np.array(pose) + rng.uniform(-1, 1, 3) * [0.5, 0.5, 0.2]
+            r = study(grid, scan, init, full, 1.5, 0.4, 5, 0.2, sch, verbose=False)
+            if r is None:
+                continue
+            ok = all(v[1] for v in r.values())
+            bad += not ok
+            print("seed %3d %s %s" % (seed, "full " if full else "local",
+                                      {k: v[0] for k, v in r.items()}), "OK" if ok else "MISMATCH")
+        print("mismatches:", bad)
+        return
+    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    grid, scans = bench.make_world(seed, 1)
     schedules = {
         "reference order": [(0, 6), (0, 5), (0, 4), (0, 3), (0, 2), (0, 1), (0, 0)],
         "joint, g-1/h-1": [(5, 6), (4, 5), (3, 4), (2, 3), (1, 2), (0, 1), (0, 0)],
         "theta first at the top": [(5, 6), (2, 6), (0, 6), (0, 5), (0, 4), (0, 3), (0, 2), (0, 1), (0, 0)],
-        "theta first, two levels": [(5, 6), (3, 6), (3, 5), (1, 5), (0, 5), (0, 4), (0, 3), (0, 2), (0, 1), (0, 0)],
-        "coarse then exact": [(5, 6), (3, 5), (1, 4), (0, 4), (0, 3), (0, 2), (0, 1), (0, 0)],
     }
-    for name, sch in schedules.items():
-        t0 = time.time()
-        ev, leaves = run_schedule(sch)
-        print("%-26s total %8d  same leaves %s  per (g,h): %s  [%.0f s]" %
-              (name, sum(ev.values()), leaves == leaves_now, ev, time.time() - t0))
+    study(grid, scans[0], (0, 0, 0), True, bench.LIN, bench.ANG, bench.DEPTH, bench.MIN_SCORE,
+          schedules)
 
 
 if __name__ == "__main__":
