@@ -3,13 +3,15 @@
 // CPU restatement of the reference algorithm (cartographer-project/cartographer
 // @ 877157a0) for the correlative scan-matching hot path.  It is the parity
 // checker for the CUDA engine in cartographer_b200/ and the CPU baseline that
-// bench.py times (`cpu_baseline`, `--impl reference`).  Only tests/,
-// __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may use
-// anything in this directory.  The product path (libcsm_b200.so) never links,
-// loads or calls it.
+// bench.py times (`cpu_baseline`, `--impl reference`).  Only tests/ (incl. the
+// fixture generator tests/golden/make_golden.py), __graft_entry__.smoke() and the
+// measurement scripts' CPU-baseline / checker legs (bench.py, benchmarks/) may use
+// anything in this directory.  The product path (cartographer_b200/, libcsm_b200.so)
+// never links, loads or calls it (tests/test_abi_cpu.py enforces that).
 //
 // Parity pin status: pinned against the reference's own known-answer tests
-// (tests/test_oracle_golden.py lists every vector and its file:line).  The real
+// (tests/test_oracle_golden_2d.py / _3d.py list every vector and its file:line) and
+// frozen by the committed fixtures tests/golden/golden_v1.npz.  The real
 // reference cannot be compiled in this image (Eigen, glog, abseil, protobuf,
 // Ceres, Lua are absent and its headers need protoc-generated code), so there
 // is no oracle/_ref; see DESIGN.md "Oracle".
