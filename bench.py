@@ -31,7 +31,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from cartographer_b200 import synthetic  # noqa: E402
+from benchmarks import synthetic  # noqa: E402
 
 BYTES_PER_CANDIDATE = 1081 * (8 + 1) + 16  # N*(8+1)+16 @ N=1081
 MATCHES_PER_STEP = 16
@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                  "--format=csv,noheader,nounits", "-lms", "50"],
+                                  "--format=csv,noheader,nounits", "-lms", "100"],
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -229,37 +229,32 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident leg (value) -------------------------------------------
-    # clocks: one nvidia-smi poller on rank 0 only (several pollers contend on the
-    # driver and slow every rank), started before the warm-up so that its start-up
-    # cost is outside the timed region; only rows sampled during the timed steps count.
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler is not None:
-        sampler.start()
-    rows0 = 0
+    # No poller runs during the timed legs (an nvidia-smi loop contends on the driver
+    # lock with kernel launches); the clocks are sampled in a separate pass that repeats
+    # the same steps right after the timed ones (see `clocks.note`).
     launches0 = sm.kernel_launch_count()
     step_s, cand, found = [], 0, 0
     dev_ms = 0.0
+    host_syncs = 0
+    results_by_step = []
     for it in range(total_steps):
         flush.zero_()
         barrier()
         if it == args.warmup:
-            rows0 = len(sampler.rows) if sampler is not None else 0
             launches0 = sm.kernel_launch_count()
         t0 = time.perf_counter()
         res, st = sm.match_batch([matcher], clouds, jobs_for(it), LIN, ANG)
         allgather_results(res)
         finish()
         dt = time.perf_counter() - t0
+        results_by_step.append(res.copy())
         if it >= args.warmup:
             step_s.append(dt)
             cand += st["candidates_scored"]
             found += int(res["found"].sum())
             dev_ms += st["device_ms"]
+            host_syncs = max(host_syncs, st["host_syncs"])
     launches = sm.kernel_launch_count() - launches0
-    clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-    if sampler is not None:
-        sampler.rows = sampler.rows[rows0:] if len(sampler.rows) > rows0 else sampler.rows[-1:]
-        clocks = sampler.summary()
     elapsed = float(sum(step_s))
     t = torch.tensor([elapsed, float(cand), float(found)], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -306,6 +301,21 @@ def main():
     h2d = MATCHES_PER_STEP * 1081 * 12
     d2h = MATCHES_PER_STEP * sm.RESULT2D_DTYPE.itemsize
 
+    # ---- clocks under load (separate pass over the same steps, rank 0's GPU) -------
+    clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if rank == 0:
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        t_end = time.perf_counter() + 1.5
+        it = 0
+        while time.perf_counter() < t_end or it < args.steps:
+            sm.match_batch([matcher], clouds, jobs_for(args.warmup + it % max(1, args.steps)), LIN, ANG)
+            it += 1
+        clocks = sampler.summary()
+        clocks["note"] = ("sampled with nvidia-smi -lms 100 while the same steps ran again right "
+                          "after the timed region (no poller inside the timed legs)")
+    barrier()
+
     # ---- roofline of the dominant kernel (CUDA events on the engine's stream) ----
     import ctypes as C
     roofline = None
@@ -343,15 +353,27 @@ def main():
 
     # ---- CPU baseline (oracle on the host cores, bounded sample) -----------------
     cpu = None
+    parity_checked = parity_failed = 0
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle as oracle
         oracle.build()
         threads = max(1, min(os.cpu_count() or 1, 64))
         og = oracle.Grid2D(grid.cells, grid.resolution, grid.max_x, grid.max_y)
         om = oracle.FastCorrelativeScanMatcher2D(og, LIN, ANG, DEPTH)
-        secs, c_cpu, m_cpu, _ = cpu_reference_step(oracle, om, scans[:threads] if
-                                                   len(scans) >= threads else
-                                                   (scans * threads)[:threads], threads)
+        sample = scans[:threads] if len(scans) >= threads else (scans * threads)[:threads]
+        secs, found_c, scores_c, poses_c, cs_c = oracle.fast2d_batch(
+            [om], [0] * len(sample), list(range(len(sample))), np.zeros((len(sample), 3)), sample,
+            True, MIN_SCORE, threads)
+        c_cpu, m_cpu = int(cs_c.sum()), len(sample)
+        # the same scans went through the engine in the timed steps: compare bit for bit
+        for k in range(min(len(sample), len(scans), total_steps * MATCHES_PER_STEP)):
+            g = results_by_step[k // MATCHES_PER_STEP][k % MATCHES_PER_STEP]
+            ok = bool(g["found"]) == bool(found_c[k])
+            if ok and found_c[k]:
+                ok = (np.float32(g["score"]) == scores_c[k] and
+                      np.array_equal(g["pose_estimate"], poses_c[k]))
+            parity_checked += 1
+            parity_failed += 0 if ok else 1
         cpu = {"value": c_cpu / secs, "unit": "candidates/s", "cores": threads, "kind": "port",
                "constraints_per_sec": m_cpu / secs,
                "sample": "%d MatchFullSubmap (one per host thread) of the same workload, "
@@ -372,7 +394,8 @@ def main():
             "device_ms_per_step": dev_ms / max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "host_syncs_per_batch": host_syncs, "clocks": clocks,
+            "parity_checked": parity_checked, "parity_failed": parity_failed,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

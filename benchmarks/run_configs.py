@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from cartographer_b200 import scan_matching as sm  # noqa: E402
-from cartographer_b200 import synthetic  # noqa: E402
+from benchmarks import synthetic  # noqa: E402
 from oracle import pyoracle as oracle  # noqa: E402  (baseline + spot checks only)
 
 B2 = 1081 * 9 + 16

@@ -22,7 +22,7 @@ class CsmStats(C.Structure):
                 ("nodes_expanded", C.c_int64), ("leaves_tied", C.c_int64),
                 ("num_scans", C.c_int32), ("best_scan_index", C.c_int32),
                 ("best_x_offset", C.c_int32), ("best_y_offset", C.c_int32),
-                ("host_tie_resolves", C.c_int32), ("reserved", C.c_int32),
+                ("host_tie_resolves", C.c_int32), ("host_syncs", C.c_int32),
                 ("device_ms", C.c_float), ("reserved_f", C.c_float)]
 
     def as_dict(self):

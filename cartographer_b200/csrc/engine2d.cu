@@ -251,6 +251,11 @@ k_discretize(const JobDev* __restrict__ jobs, const int* __restrict__ scan_job,
     si.nxc = (si.max_x - si.min_x + step) / step;
     si.nyc = (si.max_y - si.min_y + step) / step;
     si.pad = 0;
+    if (shrink && (si.nyc > jb.cap_y || static_cast<long long>(si.nxc) * jb.cap_y > jb.cap)) {
+      // the host's a-priori slot bound must cover the lattice (reported as an error)
+      counters[6] = 1ull;
+      si.nxc = si.nyc = 0;
+    }
     info[sg] = si;
     const unsigned long long slots = static_cast<unsigned long long>(si.nxc) * si.nyc;
     atomicAdd(&counters[0], slots);  // every lowest-resolution candidate gets scored
@@ -765,8 +770,14 @@ __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const Scan
 
 // scan -> job and scan -> first lowest-resolution slot, one CTA per job.
 __global__ void k_scan_tables(const JobDev* __restrict__ jobs, int* __restrict__ scan_job,
-                              long long* __restrict__ scan_slot_base) {
+                              long long* __restrict__ scan_slot_base, unsigned* __restrict__ lb,
+                              int* __restrict__ job_best) {
   const JobDev& d = jobs[blockIdx.x];
+  if (threadIdx.x == 0) {
+    // the bound starts at min_score: only scores > min_score are ever accepted (fast...2d.cc:253)
+    lb[blockIdx.x] = FloatToOrdered(d.min_score);
+    job_best[blockIdx.x] = 0;
+  }
   for (int k = threadIdx.x; k < d.num_scans; k += blockDim.x) {
     scan_job[d.scan_base + k] = blockIdx.x;
     scan_slot_base[d.scan_base + k] = d.top_off + static_cast<long long>(k) * d.cap;
@@ -908,6 +919,23 @@ k_filter_top(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
   }
 }
 
+// ---- device-resident control of the level loop ---------------------------------
+// The branch-and-bound frontier sizes never visit the host between levels: every
+// kernel of a level reads its chunk [start, start + n) of queue[h] and the kernel
+// form (`mode`) from this block, which k_level_begin fills from the device-side queue
+// counts.  Launch grids are sized for the worst case (or grid-stride), so a whole
+// match batch is ONE stream of launches followed by ONE synchronisation.
+enum : int {
+  kCtlLeaf = 16,      // leaves recorded so far
+  kCtlBest = 17,      // optimal leaves after compaction
+  kCtlOverflow = 20,  // a queue / leaf buffer was too small
+  kCtlItems = 24,     // work items of the current lattice launch
+  kCtlStart = 25,     // first node of the current chunk in queue[h]
+  kCtlCount = 26,     // nodes of the current chunk
+  kCtlMode = 27,      // 0 = nothing to do, 1 = warp per parent, 2 = scan-grouped lattice
+  kCtlInts = 32
+};
+
 // Branch step: one warp per parent node of level h.  Scores its children at
 // level h-1, then either pushes the survivors to the next queue (h-1 >= 1) or,
 // at h-1 == 0, raises the job's bound and records the leaf.
@@ -972,14 +1000,18 @@ __device__ __forceinline__ void ExpandParentWarp(
 
 __global__ void __launch_bounds__(256)
 k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
-         const short2* __restrict__ dscan, const Node* __restrict__ parents, int count, int h,
+         const short2* __restrict__ dscan, const Node* __restrict__ queue,
+         const int* __restrict__ ctl, int h,
          unsigned* __restrict__ lb, Node* __restrict__ next, int* __restrict__ next_count,
          int next_cap, Node* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
          int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= count) return;
-  ExpandParentWarp(jobs, info, dscan, parents[warp], h, lb, next, next_count, next_cap, leaves,
-                   leaf_count, leaf_cap, overflow, counters);
+  if (ctl[kCtlMode] != 1) return;
+  const int count = ctl[kCtlCount];
+  const Node* __restrict__ parents = queue + ctl[kCtlStart];
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < count; warp += warps)
+    ExpandParentWarp(jobs, info, dscan, parents[warp], h, lb, next, next_count, next_cap, leaves,
+                     leaf_count, leaf_cap, overflow, counters);
 }
 
 // ---- scan-grouped branch step ------------------------------------------------
@@ -992,9 +1024,25 @@ k_expand(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ info,
 // a point load + a scattered word per lane in the warp-per-parent form).
 struct WorkItem { int scan, start, count; };
 
-__global__ void k_q_count(const Node* __restrict__ nodes, int count, int* __restrict__ scan_cnt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) atomicAdd(&scan_cnt[nodes[i].scan], 1);
+__global__ void k_level_begin(int* __restrict__ ctl, int h, int chunk_cap, int lattice_min) {
+  if (threadIdx.x != 0) return;
+  const int have = ctl[h];
+  const int n = min(have, chunk_cap);
+  ctl[h] = have - n;          // the chunk is taken from the END of the queue
+  ctl[kCtlStart] = have - n;
+  ctl[kCtlCount] = n;
+  ctl[kCtlItems] = 0;
+  ctl[kCtlMode] = n == 0 ? 0 : (n >= lattice_min ? 2 : 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_q_count(const Node* __restrict__ queue, const int* __restrict__ ctl,
+          int* __restrict__ scan_cnt) {
+  if (ctl[kCtlMode] != 2) return;
+  const Node* __restrict__ nodes = queue + ctl[kCtlStart];
+  const int count = ctl[kCtlCount];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    atomicAdd(&scan_cnt[nodes[i].scan], 1);
 }
 
 // Exclusive prefix sums of scan_cnt (node offsets) and of ceil(cnt / 32) (work
@@ -1025,9 +1073,10 @@ __device__ __forceinline__ void BlockScan2(int& ia, int& ib, int* s_wa, int* s_w
 }
 
 __global__ void __launch_bounds__(1024)
-k_q_block_sums(const int* __restrict__ scan_cnt, int total_scans, int* __restrict__ part_a,
-               int* __restrict__ part_b) {
+k_q_block_sums(const int* __restrict__ ctl, const int* __restrict__ scan_cnt, int total_scans,
+               int* __restrict__ part_a, int* __restrict__ part_b) {
   __shared__ int s_wa[32], s_wb[32];
+  if (ctl[kCtlMode] != 2) return;
   const int i = blockIdx.x * 1024 + threadIdx.x;
   const int cnt = i < total_scans ? scan_cnt[i] : 0;
   int ia = cnt, ib = (cnt + 31) >> 5;
@@ -1038,8 +1087,10 @@ k_q_block_sums(const int* __restrict__ scan_cnt, int total_scans, int* __restric
 // in-place exclusive scan of the block sums; single CTA, every thread owns a
 // contiguous segment.  out[0] = total number of work items.
 __global__ void __launch_bounds__(1024)
-k_q_scan_parts(int* __restrict__ part_a, int* __restrict__ part_b, int nb, int* __restrict__ out) {
+k_q_scan_parts(const int* __restrict__ ctl, int* __restrict__ part_a, int* __restrict__ part_b,
+               int nb, int* __restrict__ out) {
   __shared__ int s_wa[32], s_wb[32];
+  if (ctl[kCtlMode] != 2) return;
   const int seg = (nb + 1023) >> 10;
   const int lo = min(nb, static_cast<int>(threadIdx.x) * seg), hi = min(nb, lo + seg);
   int a = 0, b = 0;
@@ -1058,10 +1109,11 @@ k_q_scan_parts(int* __restrict__ part_a, int* __restrict__ part_b, int nb, int* 
 }
 
 __global__ void __launch_bounds__(1024)
-k_q_finish(const int* __restrict__ scan_cnt, int total_scans, const int* __restrict__ part_a,
-           const int* __restrict__ part_b, int* __restrict__ scan_off,
-           WorkItem* __restrict__ items) {
+k_q_finish(const int* __restrict__ ctl, const int* __restrict__ scan_cnt, int total_scans,
+           const int* __restrict__ part_a, const int* __restrict__ part_b,
+           int* __restrict__ scan_off, WorkItem* __restrict__ items) {
   __shared__ int s_wa[32], s_wb[32];
+  if (ctl[kCtlMode] != 2) return;
   const int i = blockIdx.x * 1024 + threadIdx.x;
   const int cnt = i < total_scans ? scan_cnt[i] : 0;
   int ia = cnt, ib = (cnt + 31) >> 5;
@@ -1077,20 +1129,26 @@ k_q_finish(const int* __restrict__ scan_cnt, int total_scans, const int* __restr
 // Stable within every 32-node run: lanes holding nodes of the same scan get
 // consecutive slots in lane order (one atomic per scan per warp), so the x-ordered
 // runs produced by the push code survive the grouping.
-__global__ void k_q_scatter(const Node* __restrict__ nodes, int count,
-                            const int* __restrict__ scan_off, int* __restrict__ cursor,
-                            Node* __restrict__ sorted) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_q_scatter(const Node* __restrict__ queue, const int* __restrict__ ctl,
+            const int* __restrict__ scan_off, int* __restrict__ cursor,
+            Node* __restrict__ sorted) {
+  if (ctl[kCtlMode] != 2) return;
+  const Node* __restrict__ nodes = queue + ctl[kCtlStart];
+  const int count = ctl[kCtlCount];
   const int lane = threadIdx.x & 31;
-  const bool ok = i < count;
-  Node nd = Node{-1 - lane, 0, 0, 0.f};
-  if (ok) nd = nodes[i];
-  const unsigned peers = __match_any_sync(0xffffffffu, nd.scan);
-  const int leader = __ffs(peers) - 1;
-  int base = 0;
-  if (ok && lane == leader) base = atomicAdd(&cursor[nd.scan], __popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (ok) sorted[scan_off[nd.scan] + base + __popc(peers & ((1u << lane) - 1))] = nd;
+  const int rounded = (count + 31) & ~31;  // whole warps take part in the match
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+    const bool ok = i < count;
+    Node nd = Node{-1 - lane, 0, 0, 0.f};
+    if (ok) nd = nodes[i];
+    const unsigned peers = __match_any_sync(0xffffffffu, nd.scan);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (ok && lane == leader) base = atomicAdd(&cursor[nd.scan], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ok) sorted[scan_off[nd.scan] + base + __popc(peers & ((1u << lane) - 1))] = nd;
+  }
 }
 
 #ifndef CSM_LAT_MINB
@@ -1256,19 +1314,38 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
   }
 }
 
-// Keeps the leaves whose score equals their job's final optimum.
-__global__ void k_compact_leaves(const ScanInfo* __restrict__ info, const Node* __restrict__ in,
-                                 int count, const unsigned* __restrict__ lb,
-                                 Node* __restrict__ out, int* __restrict__ out_count, int cap,
-                                 int* __restrict__ overflow) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const Node nd = in[i];
-  if (FloatToOrdered(nd.score) >= lb[info[nd.scan].job]) {
-    const int idx = atomicAdd(out_count, 1);
-    if (idx < cap) out[idx] = nd;
-    else *overflow = 1;
+// Keeps the leaves whose score equals their job's final optimum.  The leaf count is
+// read on the device (grid-stride).
+__global__ void __launch_bounds__(256)
+k_compact_leaves(const ScanInfo* __restrict__ info, const Node* __restrict__ in,
+                 const int* __restrict__ count_ptr, int cap_in, const unsigned* __restrict__ lb,
+                 Node* __restrict__ out, int* __restrict__ out_count, int cap,
+                 int* __restrict__ overflow) {
+  const int count = min(*count_ptr, cap_in);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const Node nd = in[i];
+    if (FloatToOrdered(nd.score) >= lb[info[nd.scan].job]) {
+      const int idx = atomicAdd(out_count, 1);
+      if (idx < cap) out[idx] = nd;
+      else *overflow = 1;
+    }
   }
+}
+
+// depth 1: the lowest resolution IS the leaf level (fast...2d.cc:339-343): every queued
+// candidate raises its job's bound and becomes a leaf.
+__global__ void __launch_bounds__(256)
+k_top_as_leaves(const ScanInfo* __restrict__ info, const Node* __restrict__ queue,
+                int* __restrict__ ctl, unsigned* __restrict__ lb, Node* __restrict__ leaves,
+                int leaf_cap) {
+  const int count = ctl[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const Node nd = queue[i];
+    atomicMax(&lb[info[nd.scan].job], FloatToOrdered(nd.score));
+    if (i < leaf_cap) leaves[i] = nd;
+    else ctl[kCtlOverflow] = 1;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl[kCtlLeaf] = min(count, leaf_cap);
 }
 
 }  // namespace csm
@@ -1631,11 +1708,15 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     d.ty = static_cast<float>(iy);
     d.min_score = jb.min_score;
     // upper bound of lowest-resolution candidates per axis after ShrinkToFit:
-    // window <= min(2*lin, cells - 1 + scan extent)
+    // window <= min(2*lin, max(cells - 1 + scan extent, lin))
     const int step = 1 << (h.depth - 1);
     const long long extent = 2LL * static_cast<long long>(std::ceil(cl->max_norm / h.resolution)) + 4;
-    const long long span_x = std::min<long long>(2LL * sp.lin, h.nx - 1 + extent);
-    const long long span_y = std::min<long long>(2LL * sp.lin, h.ny - 1 + extent);
+    // (a scan wholly outside the grid on one axis keeps a window of min(lin, distance),
+    // which can exceed cells - 1 + extent: hence the max with lin)
+    const long long span_x =
+        std::min<long long>(2LL * sp.lin, std::max<long long>(h.nx - 1 + extent, sp.lin));
+    const long long span_y =
+        std::min<long long>(2LL * sp.lin, std::max<long long>(h.ny - 1 + extent, sp.lin));
     const long long cx = (span_x + step) / step, cy = (span_y + step) / step;
     d.cap_y = static_cast<int>(cy);
     d.cap = static_cast<int>(cx * cy);
@@ -1673,20 +1754,31 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   CSM_TRY(d_info.Reserve(sizeof(ScanInfo) * plan.total_scans));
   CSM_TRY(d_dscan.Reserve(sizeof(short2) * plan.total_points));
   CSM_TRY(d_lb.Reserve(sizeof(unsigned) * num_jobs));
-  CSM_TRY(d_ctr.Reserve(sizeof(unsigned long long) * 8 + sizeof(int) * 32));
+  CSM_TRY(d_ctr.Reserve(sizeof(unsigned long long) * 8 + sizeof(int) * kCtlInts));
+  DevBuf& d_job_best = ctx->D("job_best");
+  CSM_TRY(d_job_best.Reserve(sizeof(int) * num_jobs));
   for (int j = 0; j < num_jobs; ++j) plan.jobs[j].trig = d_trig.as<float2>() + trig_off[j];
 
+  // uploads go through pinned staging so that they are truly asynchronous (the
+  // previous call on this lane has completed: every call ends with a synchronise)
+  PinnedBuf& up = ctx->P("upload");
+  const size_t up_trig = trig.size() * sizeof(float);
+  const size_t up_jobs_off = (up_trig + 255) / 256 * 256;
+  CSM_TRY(up.Reserve(up_jobs_off + sizeof(JobDev) * num_jobs));
+  if (up_trig) std::memcpy(up.as<char>(), trig.data(), up_trig);
+  std::memcpy(up.as<char>() + up_jobs_off, plan.jobs.data(), sizeof(JobDev) * num_jobs);
   CSM_CUDA(cudaEventRecord(ctx->ev0, s));
-  CSM_CUDA(cudaMemcpyAsync(d_trig.p, trig.data(), trig.size() * sizeof(float),
-                           cudaMemcpyHostToDevice, s));
-  CSM_CUDA(cudaMemcpyAsync(d_jobs.p, plan.jobs.data(), sizeof(JobDev) * num_jobs,
+  if (up_trig)
+    CSM_CUDA(cudaMemcpyAsync(d_trig.p, up.as<char>(), up_trig, cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemcpyAsync(d_jobs.p, up.as<char>() + up_jobs_off, sizeof(JobDev) * num_jobs,
                            cudaMemcpyHostToDevice, s));
   k_scan_tables<<<num_jobs, 256, 0, s>>>(d_jobs.as<JobDev>(), d_scan_job.as<int>(),
-                                         d_slot_base.as<long long>());
+                                         d_slot_base.as<long long>(), d_lb.as<unsigned>(),
+                                         d_job_best.as<int>());
   CSM_LAUNCH_CHECK();
-  CSM_CUDA(cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 8 + sizeof(int) * 32, s));
+  CSM_CUDA(cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 8 + sizeof(int) * kCtlInts, s));
   unsigned long long* ctr = d_ctr.as<unsigned long long>();
-  int* ictr = reinterpret_cast<int*>(ctr + 8);  // [0..15] queue counts, [16] leaf, [17] best, [20] overflow
+  int* ictr = reinterpret_cast<int*>(ctr + 8);  // the level-loop control block (kCtl*)
 
   const int total_scans = static_cast<int>(plan.total_scans);
   ProfBegin(ctx);
@@ -1724,13 +1816,6 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   phase("upload+discr");
   // ---- lowest-resolution pass ----
   CSM_TRY(d_top.Reserve(sizeof(int) * plan.total_slots));
-  {
-    std::vector<unsigned> lb0(num_jobs);
-    for (int j = 0; j < num_jobs; ++j) lb0[j] = HostFloatToOrdered(jobs[j].min_score);
-    CSM_CUDA(cudaMemcpyAsync(d_lb.p, lb0.data(), sizeof(unsigned) * num_jobs,
-                             cudaMemcpyHostToDevice, s));
-    CSM_CUDA(cudaStreamSynchronize(s));  // lb0 is a local
-  }
   // Wide lattices (MatchFullSubmap) take the dense decimated-grid kernel; narrow
   // ones (local windows: a few dozen candidates per scan) the gather kernel.
   static const char* force = getenv("CSM_TOP_KERNEL");  // "small" | "gather" | "tile" | "dense" (debug)
@@ -1827,9 +1912,6 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     return d;
   };
   if (g_profile_on.load()) prof_scored();
-  DevBuf& d_job_best = ctx->D("job_best");
-  CSM_TRY(d_job_best.Reserve(sizeof(int) * num_jobs));
-  CSM_CUDA(cudaMemsetAsync(d_job_best.p, 0, sizeof(int) * num_jobs, s));
   static const float dive_ratio = getenv("CSM_DIVE_RATIO") ? atof(getenv("CSM_DIVE_RATIO")) : 0.97f;
   ProfBegin(ctx);
   k_job_best<<<DivUp(static_cast<long long>(total_scans) * 32, 256), 256, 0, s>>>(
@@ -1847,17 +1929,26 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   }
 
   phase("dives");
-  // ---- branch and bound: per-level queues, deepest level first ----
+  // ---- branch and bound: per-level queues, device-driven level loop ----
+  // The first sweep hmax -> 1 is a static stream of launches: every level takes a chunk of
+  // <= kChunk nodes from the end of its queue (k_level_begin), picks the kernel form on the
+  // device and appends the survivors to the next queue; nothing is read back in between.
+  // A queue below the top starts the sweep empty and receives <= 4 * kChunk children, so it
+  // cannot overflow.  Only if a level held more than one chunk (frontiers > 4 M nodes) does
+  // the host continue, deepest non-empty level first, with one read-back per extra chunk.
   int depth_max = 0;
   for (int j = 0; j < num_jobs; ++j)
     depth_max = std::max(depth_max, stacks[jobs[j].stack_index]->h.depth);
   for (int j = 0; j < num_jobs; ++j)
     CSM_REQUIRE(stacks[jobs[j].stack_index]->h.depth == depth_max,
-                "all stacks of one batch must share branch_and_bound_depth");
+                "internal: sub-batches are grouped by branch_and_bound_depth");
   const int hmax = depth_max - 1;
   const int kChunk = 1 << 22;
   const int kQueueCap = 4 * kChunk;
   const int kLeafCap = 1 << 22;
+  const int kLatticeMin = 16384;  // smaller frontiers: the warp-per-parent kernel has a
+                                  // 34-iteration critical path, the lattice kernel a 1081-iteration one
+  const int kInlineBest = 4096;   // optimal leaves read back with the first (usually only) sync
   const long long top_cap_ll = std::min<long long>(plan.total_slots, 1LL << 30);
   const int top_cap = static_cast<int>(top_cap_ll);
   DevBuf& d_qtop = ctx->D("queue_top");
@@ -1882,174 +1973,160 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     return h == hmax ? d_qtop.as<Node>() : d_q.as<Node>() + static_cast<size_t>(kQueueCap) * h;
   };
   auto queue_cap = [&](int h) { return h == hmax ? top_cap : kQueueCap; };
-  int* overflow = ictr + 20;
-  int* leaf_count = ictr + 16;
-  int* best_count = ictr + 17;
+  int* overflow = ictr + kCtlOverflow;
+  int* leaf_count = ictr + kCtlLeaf;
+  int* best_count = ictr + kCtlBest;
 
-  std::vector<int> qn(hmax + 1, 0);
-  int h_leaf = 0, h_over = 0;
+  // read-back area (pinned): control block | counters | per-job bound | first optimal leaves
   PinnedBuf& pin = ctx->P("readback");
-  CSM_TRY(pin.Reserve(sizeof(int) * 32));
+  const size_t rb_ctr = sizeof(int) * kCtlInts;
+  const size_t rb_lb = rb_ctr + sizeof(unsigned long long) * 8;
+  const size_t rb_best = (rb_lb + sizeof(unsigned) * num_jobs + 15) / 16 * 16;
+  CSM_TRY(pin.Reserve(rb_best + sizeof(Node) * kInlineBest));
   int* hp = pin.as<int>();
+  const unsigned long long* hctr = reinterpret_cast<const unsigned long long*>(pin.as<char>() + rb_ctr);
+  const unsigned* lbh = reinterpret_cast<const unsigned*>(pin.as<char>() + rb_lb);
+  const Node* best_inline = reinterpret_cast<const Node*>(pin.as<char>() + rb_best);
+  int host_syncs = 0;
 
-  if (hmax == 0) {
-    // depth 1: the lowest resolution IS the leaf level (fast...2d.cc:339-343).
-    // Treat every top candidate as a leaf via the filter + a copy to `leaves`.
-  }
   k_filter_top<<<std::min(total_scans, ctx->sm_count * 16), 256, 0, s>>>(
       d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_top.as<int>(), d_slot_base.as<long long>(),
       total_scans, d_lb.as<unsigned>(), queue_ptr(hmax), ictr + hmax, queue_cap(hmax), overflow);
   CSM_LAUNCH_CHECK();
-  CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
-  CSM_CUDA(cudaStreamSynchronize(s));
-  qn[hmax] = hp[hmax];
-  if (hp[20]) { SetError("top-level queue overflow"); return CSM_E_CAPACITY; }
 
   if (hmax == 0) {
-    // every queued node is already a leaf
-    CSM_CUDA(cudaMemcpyAsync(d_leaves.p, queue_ptr(0), sizeof(Node) * qn[0],
-                             cudaMemcpyDeviceToDevice, s));
-    CSM_CUDA(cudaMemcpyAsync(leaf_count, &qn[0], sizeof(int), cudaMemcpyHostToDevice, s));
-    CSM_CUDA(cudaStreamSynchronize(s));
-    h_leaf = qn[0];
-    // bound = max score: computed by a tiny expand-less pass below (compact uses lb),
-    // so raise lb on the host side from the leaves
-    std::vector<Node> tmp(qn[0]);
-    CSM_CUDA(cudaMemcpy(tmp.data(), d_leaves.p, sizeof(Node) * qn[0], cudaMemcpyDeviceToHost));
-    std::vector<unsigned> lbh(num_jobs);
-    CSM_CUDA(cudaMemcpy(lbh.data(), d_lb.p, sizeof(unsigned) * num_jobs, cudaMemcpyDeviceToHost));
-    for (const Node& nd : tmp) {
-      const int j = job_of_scan(nd.scan);
-      lbh[j] = std::max(lbh[j], HostFloatToOrdered(nd.score));
-    }
-    CSM_CUDA(cudaMemcpy(d_lb.p, lbh.data(), sizeof(unsigned) * num_jobs, cudaMemcpyHostToDevice));
-    qn[0] = 0;
+    k_top_as_leaves<<<ctx->sm_count * 4, 256, 0, s>>>(d_info.as<ScanInfo>(), queue_ptr(0), ictr,
+                                                      d_lb.as<unsigned>(), d_leaves.as<Node>(),
+                                                      kLeafCap);
+    CSM_LAUNCH_CHECK();
   }
 
+  // One level step: chunk bookkeeping, grouping by scan, both kernel forms predicated on
+  // the device-side mode.
+  const int nb = DivUp(total_scans, 1024);
+  const int sort_grid = ctx->sm_count * 8;
+  const int max_items = kChunk / 32 + std::min(kChunk, total_scans) + 1;
+  static const int lat_unroll = getenv("CSM_LAT_UNROLL") ? atoi(getenv("CSM_LAT_UNROLL")) : 8;
+  auto level_step = [&](int h) -> csm_status {
+    int* scan_cnt = d_scan_cnt.as<int>();
+    int* cursor = scan_cnt + total_scans;
+    int* scan_off = d_scan_off.as<int>();
+    int* part_a = scan_off + total_scans;   // block sums (DivUp(total_scans, 1024) each)
+    int* part_b = part_a + nb;
+    Node* next = h - 1 >= 1 ? queue_ptr(h - 1) : nullptr;
+    int* next_count = ictr + (h - 1 >= 1 ? h - 1 : 31);
+    k_level_begin<<<1, 32, 0, s>>>(ictr, h, kChunk, use_lattice ? kLatticeMin : INT_MAX);
+    CSM_LAUNCH_CHECK();
+    CSM_CUDA(cudaMemsetAsync(d_scan_cnt.p, 0, sizeof(int) * 2 * total_scans, s));
+    ProfBegin(ctx);
+    k_q_count<<<sort_grid, 256, 0, s>>>(queue_ptr(h), ictr, scan_cnt);
+    CSM_LAUNCH_CHECK();
+    k_q_block_sums<<<nb, 1024, 0, s>>>(ictr, scan_cnt, total_scans, part_a, part_b);
+    CSM_LAUNCH_CHECK();
+    k_q_scan_parts<<<1, 1024, 0, s>>>(ictr, part_a, part_b, nb, ictr + kCtlItems);
+    CSM_LAUNCH_CHECK();
+    k_q_finish<<<nb, 1024, 0, s>>>(ictr, scan_cnt, total_scans, part_a, part_b, scan_off,
+                                   d_items.as<WorkItem>());
+    CSM_LAUNCH_CHECK();
+    k_q_scatter<<<sort_grid, 256, 0, s>>>(queue_ptr(h), ictr, scan_off, cursor,
+                                          d_sorted.as<Node>());
+    CSM_LAUNCH_CHECK();
+    if (g_profile_on.load()) {
+      ProfStop(ctx);
+      ProfCommit(ctx, "k_q_sort", 0.);
+    }
+    ProfBegin(ctx);
+#define CSM_LATTICE(U)                                                                          \
+    k_expand_lattice<U><<<DivUp(max_items, kLatThreads / 32), kLatThreads, 0, s>>>(             \
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_sorted.as<Node>(),  \
+        d_items.as<WorkItem>(), ictr + kCtlItems, h, d_lb.as<unsigned>(), next, next_count,     \
+        kQueueCap, d_leaves.as<Node>(), leaf_count, kLeafCap, overflow, ctr)
+    if (lat_unroll <= 4) CSM_LATTICE(4);
+    else if (lat_unroll <= 8) CSM_LATTICE(8);
+    else CSM_LATTICE(16);
+#undef CSM_LATTICE
+    CSM_LAUNCH_CHECK();
+    if (g_profile_on.load()) {
+      ProfStop(ctx);
+      const double c = prof_scored();
+      if (c > 0.) ProfCommit(ctx, "k_expand_lattice", c);
+    }
+    ProfBegin(ctx);
+    k_expand<<<kLatticeMin * 32 / 256, 256, 0, s>>>(
+        d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), queue_ptr(h), ictr, h,
+        d_lb.as<unsigned>(), next, next_count, kQueueCap, d_leaves.as<Node>(), leaf_count,
+        kLeafCap, overflow, ctr);
+    CSM_LAUNCH_CHECK();
+    if (g_profile_on.load()) {
+      ProfStop(ctx);
+      const double c = prof_scored();
+      if (c > 0.) ProfCommit(ctx, "k_expand", c);
+    }
+    return CSM_OK;
+  };
+  // compaction of the optimal leaves + read-back of everything the host needs
+  auto collect = [&]() -> csm_status {
+    CSM_CUDA(cudaMemsetAsync(best_count, 0, sizeof(int), s));
+    k_compact_leaves<<<ctx->sm_count * 4, 256, 0, s>>>(
+        d_info.as<ScanInfo>(), d_leaves.as<Node>(), leaf_count, kLeafCap, d_lb.as<unsigned>(),
+        d_best.as<Node>(), best_count, kLeafCap, overflow);
+    CSM_LAUNCH_CHECK();
+    CSM_CUDA(cudaEventRecord(ctx->ev1, s));
+    CSM_CUDA(cudaMemcpyAsync(pin.as<char>(), ictr, rb_ctr, cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaMemcpyAsync(pin.as<char>() + rb_ctr, ctr, sizeof(unsigned long long) * 8,
+                             cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaMemcpyAsync(pin.as<char>() + rb_lb, d_lb.p, sizeof(unsigned) * num_jobs,
+                             cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaMemcpyAsync(pin.as<char>() + rb_best, d_best.p, sizeof(Node) * kInlineBest,
+                             cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaStreamSynchronize(s));
+    ++host_syncs;
+    return CSM_OK;
+  };
+
+  for (int h = hmax; h >= 1; --h) CSM_TRY(level_step(h));
+  CSM_TRY(collect());
+  // frontiers larger than one chunk (rare): continue deepest non-empty level first
   for (;;) {
+    if (hp[kCtlOverflow]) {
+      SetError("branch-and-bound queue overflow (more than 2^22 tied optimal leaves, or more "
+               "than 2^30 lowest-resolution candidates in one batch)");
+      return CSM_E_CAPACITY;
+    }
     int h = -1;
     for (int l = 1; l <= hmax; ++l)
-      if (qn[l] > 0) { h = l; break; }
+      if (hp[l] > 0) { h = l; break; }
     if (h < 0) break;
-    const int chunk = std::min(qn[h], kChunk);
-    const int start = qn[h] - chunk;
-    if (h - 1 >= 1) CSM_CUDA(cudaMemsetAsync(ictr + (h - 1), 0, sizeof(int), s));
-    // small frontiers: the warp-per-parent kernel has a 34-iteration critical path,
-    // the lattice kernel a 1081-iteration one
-    if (use_lattice && chunk >= 16384) {
-      // group the chunk's parents by scan (counting sort), then one CTA per <= 128
-      // parents of a scan
-      CSM_CUDA(cudaMemsetAsync(d_scan_cnt.p, 0, sizeof(int) * 2 * total_scans, s));
-      int* scan_cnt = d_scan_cnt.as<int>();
-      int* cursor = scan_cnt + total_scans;
-      int* scan_off = d_scan_off.as<int>();
-      int* part_a = scan_off + total_scans;   // block sums (DivUp(total_scans, 1024) each)
-      int* part_b = part_a + DivUp(total_scans, 1024);
-      ProfBegin(ctx);
-      k_q_count<<<DivUp(chunk, 256), 256, 0, s>>>(queue_ptr(h) + start, chunk, scan_cnt);
-      CSM_LAUNCH_CHECK();
-      const int nb = DivUp(total_scans, 1024);
-      k_q_block_sums<<<nb, 1024, 0, s>>>(scan_cnt, total_scans, part_a, part_b);
-      CSM_LAUNCH_CHECK();
-      k_q_scan_parts<<<1, 1024, 0, s>>>(part_a, part_b, nb, ictr + 24);
-      CSM_LAUNCH_CHECK();
-      k_q_finish<<<nb, 1024, 0, s>>>(scan_cnt, total_scans, part_a, part_b, scan_off,
-                                     d_items.as<WorkItem>());
-      CSM_LAUNCH_CHECK();
-      k_q_scatter<<<DivUp(chunk, 256), 256, 0, s>>>(queue_ptr(h) + start, chunk, scan_off, cursor,
-                                                   d_sorted.as<Node>());
-      CSM_LAUNCH_CHECK();
-      if (g_profile_on.load()) {
-        ProfStop(ctx);
-        ProfCommit(ctx, "k_q_sort", chunk);
-      }
-      const int max_items = chunk / 32 + std::min(chunk, total_scans) + 1;
-      ProfBegin(ctx);
-      static const int lat_unroll = getenv("CSM_LAT_UNROLL") ? atoi(getenv("CSM_LAT_UNROLL")) : 8;
-#define CSM_LATTICE(U)                                                                          \
-      k_expand_lattice<U><<<DivUp(max_items, kLatThreads / 32), kLatThreads, 0, s>>>(           \
-          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), d_sorted.as<Node>(), \
-          d_items.as<WorkItem>(), ictr + 24, h, d_lb.as<unsigned>(),                            \
-          h - 1 >= 1 ? queue_ptr(h - 1) : nullptr, ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap, \
-          d_leaves.as<Node>(), leaf_count, kLeafCap, overflow, ctr)
-      if (lat_unroll <= 4) CSM_LATTICE(4);
-      else if (lat_unroll <= 8) CSM_LATTICE(8);
-      else CSM_LATTICE(16);
-#undef CSM_LATTICE
-      CSM_LAUNCH_CHECK();
-      if (g_profile_on.load()) {
-        ProfStop(ctx);
-        ProfCommit(ctx, "k_expand_lattice", prof_scored());
-      }
-    } else {
-      ProfBegin(ctx);
-      k_expand<<<DivUp(static_cast<long long>(chunk) * 32, 256), 256, 0, s>>>(
-          d_jobs.as<JobDev>(), d_info.as<ScanInfo>(), d_dscan.as<short2>(), queue_ptr(h) + start,
-          chunk, h, d_lb.as<unsigned>(), h - 1 >= 1 ? queue_ptr(h - 1) : nullptr,
-          ictr + (h - 1 >= 1 ? h - 1 : 31), kQueueCap, d_leaves.as<Node>(), leaf_count, kLeafCap,
-          overflow, ctr);
-      CSM_LAUNCH_CHECK();
-      if (g_profile_on.load()) {
-        ProfStop(ctx);
-        ProfCommit(ctx, "k_expand", prof_scored());
-      }
-    }
-    qn[h] -= chunk;
-    CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
-    CSM_CUDA(cudaStreamSynchronize(s));
-    if (h - 1 >= 1) qn[h - 1] = hp[h - 1];
-    h_leaf = hp[16];
-    h_over = hp[20];
-    if (h_over) { SetError("branch-and-bound queue overflow"); return CSM_E_CAPACITY; }
-    if (h_leaf > kLeafCap / 2) {
-      // drop leaves that are already below their job's bound
-      CSM_CUDA(cudaMemsetAsync(best_count, 0, sizeof(int), s));
-      k_compact_leaves<<<DivUp(h_leaf, 256), 256, 0, s>>>(
-          d_info.as<ScanInfo>(), d_leaves.as<Node>(), h_leaf, d_lb.as<unsigned>(),
-          d_best.as<Node>(), best_count, kLeafCap, overflow);
-      CSM_LAUNCH_CHECK();
-      CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
-      CSM_CUDA(cudaStreamSynchronize(s));
-      h_leaf = hp[17];
-      if (h_leaf > kLeafCap / 2) { SetError("too many tied leaves"); return CSM_E_CAPACITY; }
-      CSM_CUDA(cudaMemcpyAsync(d_leaves.p, d_best.p, sizeof(Node) * h_leaf,
+    if (hp[kCtlLeaf] > kLeafCap / 2) {
+      // drop the leaves that are already below their job's bound (d_best holds them
+      // after collect()); more than kLeafCap / 2 exactly tied optima are not supported
+      if (hp[kCtlBest] > kLeafCap / 2) { SetError("too many tied leaves"); return CSM_E_CAPACITY; }
+      CSM_CUDA(cudaMemcpyAsync(d_leaves.p, d_best.p, sizeof(Node) * hp[kCtlBest],
                                cudaMemcpyDeviceToDevice, s));
-      CSM_CUDA(cudaMemcpyAsync(leaf_count, &hp[17], sizeof(int), cudaMemcpyHostToDevice, s));
-      CSM_CUDA(cudaStreamSynchronize(s));
+      CSM_CUDA(cudaMemcpyAsync(leaf_count, best_count, sizeof(int), cudaMemcpyDeviceToDevice, s));
     }
+    CSM_TRY(level_step(h));
+    for (int l = h - 1; l >= 1; --l) CSM_TRY(level_step(l));  // its children fit one chunk each
+    CSM_TRY(collect());
   }
 
   phase("branch&bound");
-  // ---- collect the optimal leaves of every job ----
-  CSM_CUDA(cudaMemsetAsync(best_count, 0, sizeof(int), s));
-  if (h_leaf > 0) {
-    k_compact_leaves<<<DivUp(h_leaf, 256), 256, 0, s>>>(
-        d_info.as<ScanInfo>(), d_leaves.as<Node>(), h_leaf, d_lb.as<unsigned>(),
-        d_best.as<Node>(), best_count, kLeafCap, overflow);
-    CSM_LAUNCH_CHECK();
+  const int n_best = hp[kCtlBest];
+  if (hctr[7]) {
+    SetError("a scan point lies more than 30000 cells from the grid origin (int16 cell indices)");
+    return CSM_E_CAPACITY;
   }
-  CSM_CUDA(cudaEventRecord(ctx->ev1, s));
-  CSM_CUDA(cudaMemcpyAsync(hp, ictr, sizeof(int) * 32, cudaMemcpyDeviceToHost, s));
-  CSM_CUDA(cudaStreamSynchronize(s));
-  const int n_best = hp[17];
-  {
-    unsigned long long clamp_flag = 0;
-    CSM_CUDA(cudaMemcpy(&clamp_flag, ctr + 7, sizeof(clamp_flag), cudaMemcpyDeviceToHost));
-    if (clamp_flag) {
-      SetError("a scan point lies more than 30000 cells from the grid origin (int16 cell indices)");
-      return CSM_E_CAPACITY;
-    }
+  if (hctr[6]) {
+    SetError("internal: a scan's lowest-resolution lattice exceeds its reserved slots");
+    return CSM_E_CAPACITY;
   }
-  std::vector<Node> best(n_best);
-  std::vector<unsigned> lbh(num_jobs);
-  unsigned long long hctr[8];
-  if (n_best)
-    CSM_CUDA(cudaMemcpyAsync(best.data(), d_best.p, sizeof(Node) * n_best,
-                             cudaMemcpyDeviceToHost, s));
-  CSM_CUDA(cudaMemcpyAsync(lbh.data(), d_lb.p, sizeof(unsigned) * num_jobs,
-                           cudaMemcpyDeviceToHost, s));
-  CSM_CUDA(cudaMemcpyAsync(hctr, ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
-  CSM_CUDA(cudaStreamSynchronize(s));
+  std::vector<Node> best(best_inline, best_inline + std::min(n_best, kInlineBest));
+  if (n_best > kInlineBest) {  // many exactly tied optima
+    best.resize(n_best);
+    CSM_CUDA(cudaMemcpyAsync(best.data(), d_best.p, sizeof(Node) * n_best, cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaStreamSynchronize(s));
+    ++host_syncs;
+  }
 
   // group optimal leaves by job
   std::vector<std::vector<TieLeaf>> per_job(num_jobs);
@@ -2196,6 +2273,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     total->nodes_expanded += static_cast<int64_t>(hctr[1]);
     total->lowest_resolution_candidates += lowest_total;
     total->host_tie_resolves += host_resolves;
+    total->host_syncs += host_syncs;
     total->device_ms += ms;
     if (num_jobs == 1) {
       total->num_scans = plan.search[0].num_scans;
@@ -2217,35 +2295,56 @@ csm_status csm_match2d_batch(const csm_stack2d* const* stacks, int32_t num_stack
   CSM_REQUIRE(stacks && clouds && jobs && results, "null pointer");
   CSM_REQUIRE(num_jobs >= 1 && num_stacks >= 1 && num_clouds >= 1, "empty batch");
   CSM_REQUIRE(stacks[0] != nullptr, "null stack");
+  bool one_depth = true;
+  for (int j = 0; j < num_jobs; ++j) {
+    const csm_job2d& jb = jobs[j];
+    CSM_REQUIRE(jb.stack_index >= 0 && jb.stack_index < num_stacks, "stack index");
+    CSM_REQUIRE(jb.cloud_index >= 0 && jb.cloud_index < num_clouds, "cloud index");
+    CSM_REQUIRE(stacks[jb.stack_index] && clouds[jb.cloud_index], "null handle");
+    one_depth = one_depth &&
+                stacks[jb.stack_index]->h.depth == stacks[jobs[0].stack_index]->h.depth;
+  }
   LaneGuard guard;
   CSM_TRY(AcquireLane(stacks[0]->ctx->device, &guard));
   Ctx* ctx = guard.lane;
   if (total) std::memset(total, 0, sizeof(*total));
-  // Split into sub-batches so the discrete-scan buffer stays below ~8 GB.
-  const long long kMaxPoints = 1LL << 30;
-  int j0 = 0;
-  while (j0 < num_jobs) {
-    long long pts = 0;
-    int j1 = j0;
-    while (j1 < num_jobs) {
-      const csm_job2d& jb = jobs[j1];
-      CSM_REQUIRE(jb.stack_index >= 0 && jb.stack_index < num_stacks, "stack index");
-      CSM_REQUIRE(jb.cloud_index >= 0 && jb.cloud_index < num_clouds, "cloud index");
-      const csm_stack2d* st = stacks[jb.stack_index];
-      const csm_cloud* cl = clouds[jb.cloud_index];
-      CSM_REQUIRE(st && cl, "null handle");
-      const double ang = jb.full_submap ? M_PI : angular_window;
-      const double lin = jb.full_submap ? 1e6 * st->h.resolution : linear_window;
-      const HostSearch sp = MakeSearch(lin, ang, cl->max_norm, st->h.resolution);
-      const long long add = static_cast<long long>(sp.num_scans) * cl->n;
-      if (j1 > j0 && pts + add > kMaxPoints) break;
-      pts += add;
-      ++j1;
+  // Runs jobs[0..n) (one branch_and_bound_depth) in sub-batches whose discrete-scan buffer
+  // stays below ~4 GB.
+  auto run = [&](const csm_job2d* js, int n, csm_result2d* rs) -> csm_status {
+    const long long kMaxPoints = 1LL << 30;
+    int j0 = 0;
+    while (j0 < n) {
+      long long pts = 0;
+      int j1 = j0;
+      while (j1 < n) {
+        const csm_stack2d* st = stacks[js[j1].stack_index];
+        const csm_cloud* cl = clouds[js[j1].cloud_index];
+        const double ang = js[j1].full_submap ? M_PI : angular_window;
+        const double lin = js[j1].full_submap ? 1e6 * st->h.resolution : linear_window;
+        const HostSearch sp = MakeSearch(lin, ang, cl->max_norm, st->h.resolution);
+        const long long add = static_cast<long long>(sp.num_scans) * cl->n;
+        if (j1 > j0 && pts + add > kMaxPoints) break;
+        pts += add;
+        ++j1;
+      }
+      CSM_TRY(RunBatch2D(ctx, stacks, num_stacks, clouds, num_clouds, js + j0, j1 - j0,
+                         linear_window, angular_window, rs + j0, total, false, nullptr, nullptr));
+      j0 = j1;
     }
-    CSM_TRY(RunBatch2D(ctx, stacks, num_stacks, clouds, num_clouds, jobs + j0, j1 - j0,
-                       linear_window, angular_window, results + j0, total, false, nullptr,
-                       nullptr));
-    j0 = j1;
+    return CSM_OK;
+  };
+  if (one_depth) return run(jobs, num_jobs, results);
+  // Stacks of different branch_and_bound_depth (the level loop is per depth): one pass per
+  // depth, results scattered back into job order.
+  std::map<int, std::vector<int>> by_depth;
+  for (int j = 0; j < num_jobs; ++j) by_depth[stacks[jobs[j].stack_index]->h.depth].push_back(j);
+  for (const auto& kv : by_depth) {
+    const std::vector<int>& idx = kv.second;
+    std::vector<csm_job2d> js(idx.size());
+    std::vector<csm_result2d> rs(idx.size());
+    for (size_t i = 0; i < idx.size(); ++i) js[i] = jobs[idx[i]];
+    CSM_TRY(run(js.data(), static_cast<int>(js.size()), rs.data()));
+    for (size_t i = 0; i < idx.size(); ++i) results[idx[i]] = rs[i];
   }
   return CSM_OK;
 }

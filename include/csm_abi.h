@@ -57,7 +57,7 @@ typedef struct csm_stats {
   int32_t best_x_offset;
   int32_t best_y_offset;
   int32_t host_tie_resolves;            /* top-level std::sort replays */
-  int32_t reserved;
+  int32_t host_syncs;                   /* stream synchronisations inside the call (2D batch: 1 + ties) */
   float device_ms;                      /* CUDA-event time of the device work of this call */
   float reserved_f;
 } csm_stats;

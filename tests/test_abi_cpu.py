@@ -69,7 +69,7 @@ def test_no_cpu_fallback_without_gpu(csm):
                                 C.c_float(0.1), C.c_float(0.9), 3, 0, C.byref(out))
     assert st == 2, "expected CSM_E_CUDA"
     from cartographer_b200 import scan_matching as sm
-    from cartographer_b200 import synthetic
+    from benchmarks import synthetic
     grid = synthetic.GridSpec(cells, 0.05, 0.1, 0.1)
     with pytest.raises(csm.CsmError):
         sm.FastCorrelativeScanMatcher2D(grid, sm.FastCorrelativeScanMatcherOptions2D(1.0, 0.5, 3))

@@ -15,7 +15,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from cartographer_b200 import constraint_builder as cb
-from cartographer_b200 import synthetic
+from benchmarks import synthetic
 
 
 class OracleExecutor:

@@ -6,7 +6,7 @@ import math
 import numpy as np
 import pytest
 
-from cartographer_b200 import synthetic
+from benchmarks import synthetic
 from tests import worlds
 
 pytestmark = pytest.mark.gpu

@@ -1,7 +1,7 @@
 """Small fixture builders for the tests (CPU, numpy)."""
 import numpy as np
 
-from cartographer_b200 import synthetic
+from benchmarks import synthetic
 
 
 def insert_range_data(oracle, nx, ny, res, max_x, max_y, origin_xy, returns_xyz, grow=True,

@@ -3,7 +3,7 @@ import math
 
 import numpy as np
 
-from cartographer_b200 import synthetic
+from benchmarks import synthetic
 
 # fast_correlative_scan_matcher_3d_test.cc:42-55
 AXIS_CLOUD = np.array([[4, 0, 0], [4.5, 0, 0], [5, 0, 0], [5.5, 0, 0],
