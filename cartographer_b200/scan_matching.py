@@ -229,6 +229,98 @@ def _rt_match_tsdf(self, initial_pose_estimate, point_cloud, grid):
 RealTimeCorrelativeScanMatcher2D.MatchTSDF = _rt_match_tsdf
 
 
+class CsmRtJob2D(C.Structure):
+    _fields_ = [("xyz", C.POINTER(C.c_float)), ("num_points", C.c_int32), ("reserved", C.c_int32),
+                ("initial_pose", C.c_double * 3)]
+
+
+class CsmRtResult2D(C.Structure):
+    _fields_ = [("score", C.c_double), ("pose_estimate", C.c_double * 3),
+                ("best_scan_index", C.c_int32), ("best_x_offset", C.c_int32),
+                ("best_y_offset", C.c_int32), ("num_scans", C.c_int32),
+                ("candidates_scored", C.c_int64)]
+
+
+class RealTimeGrid2D:
+    """A ProbabilityGrid resident on the device (csm_rt_grid2d): what
+    LocalTrajectoryBuilder2D's active submap grid is to the real-time matcher
+    (local_trajectory_builder_2d.cc:77-82).  update() re-uploads the cells after a scan
+    insertion (same cell limits)."""
+
+    def __init__(self, grid, device=0):
+        cells = np.ascontiguousarray(grid.cells, dtype=np.uint16)
+        self.shape = cells.shape
+        self.device = device
+        self._h = C.c_void_p()
+        check(lib().csm_rt_grid2d_create(
+            ptr(cells, C.c_uint16), C.c_int32(cells.shape[1]), C.c_int32(cells.shape[0]),
+            C.c_double(grid.resolution), C.c_double(grid.max_x), C.c_double(grid.max_y),
+            C.c_int32(device), C.byref(self._h)))
+
+    def update(self, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.uint16)
+        if cells.shape != self.shape:
+            raise ValueError("cell limits changed: create a new RealTimeGrid2D")
+        check(lib().csm_rt_grid2d_update(self._h, ptr(cells, C.c_uint16)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().csm_rt_grid2d_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def _rt_match_batch(self, initial_pose_estimates, point_clouds, rt_grid):
+    """Many RealTimeCorrelativeScanMatcher2D::Match calls against one device-resident
+    grid in one launch (csm_rt_match2d_batch).  Returns (scores[float64], poses[n, 3],
+    stats dict); entry j equals Match(initial_pose_estimates[j], point_clouds[j], grid)."""
+    n = len(point_clouds)
+    clouds = [_f32(c) for c in point_clouds]
+    jobs = (CsmRtJob2D * n)()
+    for j in range(n):
+        jobs[j].xyz = ptr(clouds[j], C.c_float)
+        jobs[j].num_points = len(clouds[j])
+        for k in range(3):
+            jobs[j].initial_pose[k] = float(initial_pose_estimates[j][k])
+    res = (CsmRtResult2D * n)()
+    stats = CsmStats()
+    o = self.options
+    check(lib().csm_rt_match2d_batch(
+        rt_grid._h, jobs, C.c_int32(n), C.c_double(o.linear_search_window),
+        C.c_double(o.angular_search_window), C.c_double(o.translation_delta_cost_weight),
+        C.c_double(o.rotation_delta_cost_weight), res, C.byref(stats)))
+    self.last_stats = stats.as_dict()
+    scores = np.array([r.score for r in res], np.float64)
+    poses = np.array([[r.pose_estimate[0], r.pose_estimate[1], r.pose_estimate[2]] for r in res])
+    self.last_results = res
+    return scores, poses, self.last_stats
+
+
+def _rt_score_candidates(self, grid, discrete_scans, num_angular_perturbations,
+                         angular_perturbation_step_size, candidates):
+    """RealTimeCorrelativeScanMatcher2D::ScoreCandidates (public in the reference,
+    real_time_correlative_scan_matcher_2d.h:75): candidates = [[scan, x_off, y_off], ...]."""
+    cells = np.ascontiguousarray(grid.cells, dtype=np.uint16)
+    ds = np.ascontiguousarray(discrete_scans, dtype=np.int32)
+    cand = np.ascontiguousarray(candidates, dtype=np.int32).reshape(-1, 3)
+    S, n, _ = ds.shape
+    scores = np.empty(len(cand), np.float32)
+    o = self.options
+    check(lib().csm_rt_score_candidates2d(
+        ptr(cells, C.c_uint16), C.c_int32(cells.shape[1]), C.c_int32(cells.shape[0]),
+        C.c_double(grid.resolution), C.c_double(grid.max_x), C.c_double(grid.max_y),
+        ptr(ds, C.c_int32), C.c_int32(S), C.c_int32(n), C.c_int32(num_angular_perturbations),
+        C.c_double(angular_perturbation_step_size), ptr(cand, C.c_int32), C.c_int32(len(cand)),
+        C.c_double(o.translation_delta_cost_weight), C.c_double(o.rotation_delta_cost_weight),
+        C.c_int32(self.device), ptr(scores, C.c_float)))
+    return scores
+
+
+RealTimeCorrelativeScanMatcher2D.MatchBatch = _rt_match_batch
+RealTimeCorrelativeScanMatcher2D.ScoreCandidates = _rt_score_candidates
+
+
 def kernel_launch_count():
     return int(lib().csm_kernel_launch_count())
 
@@ -241,7 +333,7 @@ def device_count():
 
 __all__ = ["FastCorrelativeScanMatcherOptions2D", "RealTimeCorrelativeScanMatcherOptions",
            "FastCorrelativeScanMatcher2D", "RealTimeCorrelativeScanMatcher2D", "DeviceCloud",
-           "match_batch", "kernel_launch_count", "device_count", "JOB2D_DTYPE",
+           "match_batch", "RealTimeGrid2D", "kernel_launch_count", "device_count", "JOB2D_DTYPE",
            "RESULT2D_DTYPE", "_lib"]
 
 

@@ -187,6 +187,59 @@ csm_status csm_rt_match2d_tsdf(const uint16_t* tsd_cells, const uint16_t* weight
                                double rotation_delta_cost_weight, int32_t device, double* score,
                                double pose_estimate[3], csm_stats* stats /* may be NULL */);
 
+/* ---- grid-resident / batched real-time matcher ------------------------------ */
+/* LocalTrajectoryBuilder2D::ScanMatch (internal/2d/local_trajectory_builder_2d.cc:77-82)
+ * matches every incoming scan against the active submap's grid.  A csm_rt_grid2d keeps
+ * that ProbabilityGrid on the device (refresh it with csm_rt_grid2d_update after a scan
+ * was inserted; same cell limits), and csm_rt_match2d_batch scores many scans against it
+ * in ONE launch: job j is exactly RealTimeCorrelativeScanMatcher2D::Match
+ * (real_time_correlative_scan_matcher_2d.cc:117-149) of jobs[j] — same score, same pose. */
+typedef struct csm_rt_grid2d csm_rt_grid2d;
+csm_status csm_rt_grid2d_create(const uint16_t* cells, int32_t num_x_cells, int32_t num_y_cells,
+                                double resolution, double max_x, double max_y, int32_t device,
+                                csm_rt_grid2d** out);
+csm_status csm_rt_grid2d_update(csm_rt_grid2d* grid, const uint16_t* cells);
+csm_status csm_rt_grid2d_destroy(csm_rt_grid2d* grid);
+
+typedef struct csm_rt_job2d {
+  const float* xyz;          /* sensor::PointCloud, num_points x {x, y, z} (host memory) */
+  int32_t num_points;
+  int32_t reserved;
+  double initial_pose[3];    /* initial_pose_estimate {x, y, yaw} */
+} csm_rt_job2d;
+
+typedef struct csm_rt_result2d {
+  double score;              /* Match's return value (best_candidate.score) */
+  double pose_estimate[3];
+  int32_t best_scan_index, best_x_offset, best_y_offset;
+  int32_t num_scans;
+  int64_t candidates_scored; /* num_scans * (2 * num_linear_perturbations + 1)^2 */
+} csm_rt_result2d;
+
+csm_status csm_rt_match2d_batch(const csm_rt_grid2d* grid, const csm_rt_job2d* jobs,
+                                int32_t num_jobs, double linear_search_window,
+                                double angular_search_window,
+                                double translation_delta_cost_weight,
+                                double rotation_delta_cost_weight, csm_rt_result2d* results,
+                                csm_stats* stats /* may be NULL */);
+
+/* RealTimeCorrelativeScanMatcher2D::ScoreCandidates — public in the reference
+ * (real_time_correlative_scan_matcher_2d.h:75, .cc:151-176): scores caller-supplied
+ * candidates {scan_index, x_index_offset, y_index_offset} against caller-supplied
+ * discrete scans (num_scans x num_points x {x, y} int32).  The two SearchParameters
+ * fields give Candidate2D::orientation = (scan_index - num_angular_perturbations) *
+ * angular_perturbation_step_size (correlative_scan_matcher_2d.h:77-86). */
+csm_status csm_rt_score_candidates2d(const uint16_t* cells, int32_t num_x_cells,
+                                     int32_t num_y_cells, double resolution, double max_x,
+                                     double max_y, const int32_t* discrete_scans,
+                                     int32_t num_scans, int32_t num_points,
+                                     int32_t num_angular_perturbations,
+                                     double angular_perturbation_step_size,
+                                     const int32_t* candidates, int32_t num_candidates,
+                                     double translation_delta_cost_weight,
+                                     double rotation_delta_cost_weight, int32_t device,
+                                     float* scores);
+
 /* ==== 3D: FastCorrelativeScanMatcher3D ====================================== */
 /* A HybridGrid crosses the ABI in the flat form of proto::HybridGrid
  * (mapping/proto/hybrid_grid.proto:19-28): voxel indices (n x {x,y,z} int32, origin
