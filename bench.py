@@ -2,22 +2,29 @@
 """bench.py — headline benchmark of the correlative scan-matching hot path.
 
 Metric (BASELINE.json): candidate poses scored / s (+ loop-closure constraints / s).
-Workload at every N: BASELINE config[1] — 2D FastCorrelativeScanMatcher
-MatchFullSubmap, 1081-beam synthetic scans vs a 1000x1000 @5 cm ProbabilityGrid,
-depth-7 PrecomputationGridStack.  A step = MATCHES_PER_STEP full-submap matches of
-distinct scans against the rank's submap (one csm_match2d_batch call); at N > 1
-every rank owns its own submap + scans (weak scaling, the ConstraintBuilder queue
-sharded by submap) and the winning constraints are all-gathered over NCCL once per
-step.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C]
 
-`value`  : device-resident inputs (clouds + stack in HBM before the timed region).
-`e2e`    : the same matches through csm_match2d with HOST clouds (H2D + D2H inside).
+--config 2 (default, the headline at every N): BASELINE config[1] — 2D
+  FastCorrelativeScanMatcher MatchFullSubmap, 1081-beam synthetic scans vs a 1000x1000
+  @5 cm ProbabilityGrid, depth-7 PrecomputationGridStack.  A step = MATCHES_PER_STEP
+  full-submap matches per GPU.  At N > 1 every rank owns its own submap + scans (weak
+  scaling: the ConstraintBuilder queue sharded by submap) and ONE ncclAllGather per step,
+  issued inside libcsm_b200.so (csm_cb_batch2d_run), leaves all constraints on all ranks.
+--config 4: ConstraintBuilder2D batch at BASELINE size — 1000 submaps x 200 nodes local
+  searches (7 m / 30 deg / depth 7 / min_score 0.55), the queue sharded submap-major over
+  the N GPUs (STRONG scaling: the total queue is fixed), one allgather of the 200 k records.
+--config 5: ConstraintBuilder3D batch — 500 submaps x 100 nodes (64 rings x 1024 az).
+--config 1: RealTimeCorrelativeScanMatcher2D, 1081 beams vs 200x200, 1000 scans / step.
+  (`--scale f` shrinks configs 4/5 for quick runs; the line states the size it ran.)
+
+`value`  : device-resident inputs (stacks + clouds in HBM before the timed region).
+`e2e`    : the same work through the C ABI with HOST point clouds (H2D + D2H inside).
 `--impl reference`: the CPU oracle (restated reference path; the real reference does
 not build here) on the host cores, same metric / workload.
 """
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -33,12 +40,18 @@ sys.path.insert(0, ROOT)
 
 from benchmarks import synthetic  # noqa: E402
 
-BYTES_PER_CANDIDATE = 1081 * (8 + 1) + 16  # N*(8+1)+16 @ N=1081
+BYTES_PER_CANDIDATE = 1081 * (8 + 1) + 16   # N*(8+1)+16 @ N=1081
+BYTES_PER_CANDIDATE_RT = 1081 * (8 + 2) + 16
 MATCHES_PER_STEP = 16
 MIN_SCORE = 0.6          # pose_graph.lua:28 global_localization_min_score
 DEPTH = 7                # pose_graph.lua:27
 LIN, ANG = 7.0, math.radians(30.0)
-WORKLOAD = "fast2d_MatchFullSubmap_1081beams_1000x1000_5cm_depth7"
+WORKLOADS = {
+    1: "rt2d_Match_1081beams_200x200_5cm_0.1m_7deg",
+    2: "fast2d_MatchFullSubmap_1081beams_1000x1000_5cm_depth7",
+    4: "constraint_builder2d_queue_1000submaps_x_200nodes_7m_30deg_depth7",
+    5: "constraint_builder3d_queue_500submaps_x_100nodes_64x1024",
+}
 
 
 def make_world(seed, num_scans):
@@ -55,7 +68,7 @@ def make_world(seed, num_scans):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons (separate pass, see `clocks.note`)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -82,7 +95,7 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         self.stop_flag = True
-        time.sleep(0.15)
+        time.sleep(0.25)
         if getattr(self, "proc", None):
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -102,23 +115,109 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measured_peak_gbs():
+def sample_clocks(local_rank, workload, min_seconds=1.5, min_iters=3):
+    """Clocks under load: the poller runs while `workload()` repeats the timed steps right
+    after the timed region — never inside it (an nvidia-smi loop contends with kernel
+    launches on the driver lock and perturbed round 1's `value`)."""
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.15)
+    t_end = time.perf_counter() + min_seconds
+    it = 0
+    while time.perf_counter() < t_end or it < min_iters:
+        workload(it)
+        it += 1
+    out = sampler.summary()
+    out["note"] = ("nvidia-smi -lms 100 while the same steps ran again right after the timed "
+                   "region; no poller inside the timed legs")
+    return out
+
+
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, 1965.0, "fallback"
 
 
-def cpu_reference_step(oracle, og_matcher, scans, threads):
-    """One bounded CPU sample: `threads` full-submap matches, one per worker thread."""
-    jobs = list(range(len(scans)))
-    secs, found, scores, poses, cs = oracle.fast2d_batch(
-        [og_matcher], [0] * len(jobs), jobs, np.zeros((len(jobs), 3)), scans, True, MIN_SCORE,
-        threads)
-    return secs, int(cs.sum()), len(jobs), int(found.sum())
+def read_profile(lib):
+    buf = C.create_string_buffer(16384)
+    lib().csm_profile_read(buf, 16384)
+    kernels = {}
+    for ln in buf.value.decode().strip().splitlines():
+        nm, n_l, ms, units = ln.split()
+        kernels[nm] = {"launches": int(n_l), "ms": float(ms), "units": float(units)}
+    return kernels
 
 
+def roofline_block(kernels, bytes_per_unit, sm_mhz):
+    """Roofline of the dominant kernel.  Three readings, all labelled:
+      * `frac` / `bound`: the unit ncu shows saturated for this kernel (L1 data-pipe LSU
+        wavefronts for the branch kernel: one wavefront / clk / SM), from the COMMITTED ncu
+        capture's per-step count (profiles/r2_roofline.json) over the LIVE CUDA-event
+        duration — a fraction that can be compared with 1;
+      * `hbm`: ncu DRAM bytes over the live duration vs the measured HBM peak (the working
+        set is L2-resident, so this is small — no wasted HBM traffic);
+      * `algorithmic_GBps`: SURVEY §8d's byte model (one index + one cell per point per
+        candidate) — NOT a bound: one loaded word serves 4 children and one staged point
+        serves 32 parents, so it exceeds the HBM figure."""
+    if not kernels:
+        return None
+    tot_ms = sum(k["ms"] for k in kernels.values())
+    top = max(kernels, key=lambda k: kernels[k]["ms"])
+    k = kernels[top]
+    peak, sm_max, how = measured_peaks()
+    sec = k["ms"] * 1e-3
+    alg = k["units"] * bytes_per_unit / sec / 1e9 if sec > 0 else 0.0
+    static = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_roofline.json")) as f:
+            static = json.load(f).get(top, {})
+    except Exception:
+        pass
+    clk_hz = (sm_mhz or sm_max) * 1e6
+    out = {"kernel": top, "launches": k["launches"],
+           "avg_launch_ms": k["ms"] / max(1, k["launches"]),
+           "share_of_step": k["ms"] / tot_ms if tot_ms else None,
+           "unit": "GB/s", "peak": peak, "peak_source": how,
+           "algorithmic_GBps": alg, "algorithmic_over_hbm_peak": alg / peak,
+           "bytes_per_candidate": bytes_per_unit,
+           "kernels": {n: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                           "candidates": v["units"]} for n, v in kernels.items()}}
+    # the captured per-step totals scale with the candidates the live launches scored
+    cap_units = static.get("units_per_step")
+    scale = (k["units"] / cap_units) if cap_units else 1.0
+    if static.get("dram_bytes_per_step") is not None:
+        dram = static["dram_bytes_per_step"] * scale
+        out["traffic"] = dram / max(1, k["launches"])
+        out["hbm"] = {"achieved": dram / sec / 1e9, "peak": peak, "frac": dram / sec / 1e9 / peak}
+    else:
+        out["traffic"] = None
+    if static.get("l1_lsu_wavefronts_per_step") is not None:
+        wf = static["l1_lsu_wavefronts_per_step"] * scale
+        peak_wf = 148 * clk_hz     # one data-pipe wavefront per clock per SM
+        out["bound"] = "l1tex_lsu_wavefronts"
+        out["achieved"] = wf / sec
+        out["peak_bound"] = peak_wf
+        out["bound_unit"] = "wavefronts/s"
+        out["frac"] = wf / sec / peak_wf
+        out["ncu_pct_of_peak"] = static.get("l1_lsu_pct")
+        if static.get("lts_bytes_per_step") is not None:
+            out["l2_GBps"] = static["lts_bytes_per_step"] * scale / sec / 1e9
+        out["source"] = static.get("source")
+    else:
+        # no capture committed for this kernel: the HBM reading is all there is
+        out["bound"] = "hbm"
+        out["achieved"] = out.get("hbm", {}).get("achieved")
+        out["frac"] = out.get("hbm", {}).get("frac")
+    return out
+
+
+# =============================================================================
+# --impl reference: the CPU oracle on the host cores
+# =============================================================================
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,232 +225,248 @@ def run_reference(args):
     from oracle import pyoracle as oracle
     oracle.build()
     threads = max(1, min(os.cpu_count() or 1, 64))
-    per_step = threads  # one full-submap match per host thread per step (bounded sample)
+    if args.config == 1:
+        return run_reference_rt(args, oracle, threads)
+    full = args.config == 2
+    per_step = threads if full else threads * 4  # bounded sample per step
     grid, scans = make_world(0, per_step)
     og = oracle.Grid2D(grid.cells, grid.resolution, grid.max_x, grid.max_y)
     t0 = time.perf_counter()
     om = oracle.FastCorrelativeScanMatcher2D(og, LIN, ANG, DEPTH)
     build_s = time.perf_counter() - t0
+    inits = np.zeros((per_step, 3))
+    min_score = MIN_SCORE if full else 0.55
     tot_s, tot_c, tot_m = 0.0, 0, 0
     for it in range(args.warmup + args.steps):
-        secs, cands, matches, _ = cpu_reference_step(oracle, om, scans, threads)
+        secs, found, scores, poses, cs = oracle.fast2d_batch(
+            [om], [0] * per_step, list(range(per_step)), inits, scans, full, min_score, threads)
         if it >= args.warmup:
             tot_s += secs
-            tot_c += cands
-            tot_m += matches
+            tot_c += int(cs.sum())
+            tot_m += per_step
     value = tot_c / tot_s
     line = {
         "impl": "reference", "metric": "candidate_poses_scored_per_sec", "value": value,
         "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "matches_per_step": per_step,
-                   "min_score": MIN_SCORE, "oracle_stack_build_s": build_s},
+        "scaling": "weak" if args.config == 2 else "strong", "vs_baseline": None,
+        "dtype": "u8/int32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "matches_per_step": per_step,
+                   "min_score": min_score, "oracle_stack_build_s": build_s},
         "constraints_per_sec": tot_m / tot_s,
         "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": threads,
                          "kind": "port",
-                         "sample": "%d MatchFullSubmap per step, one per host thread, "
-                                   "oracle/ (C++ restatement, -O3 -DNDEBUG, no -march)" % per_step},
+                         "sample": "%d searches per step on %d host threads, oracle/ (C++ "
+                                   "restatement, -O3 -DNDEBUG, no -march)" % (per_step, threads)},
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
-    if args.impl == "reference":
-        run_reference(args)
-        return
+def rt_world(n):
+    big, occ = synthetic.make_grid2d(7, 1000)
+    grid, occ2 = synthetic.crop_grid(big, occ, 400, 400, 200, 200)
+    rng = np.random.RandomState(1)
+    scans, inits = [], []
+    for i in range(n):
+        pose = synthetic.random_free_pose(occ2, grid, rng, margin_cells=15)
+        scans.append(synthetic.cast_scan(occ2, grid, pose, seed=i, max_range=30.0))
+        inits.append(pose + rng.uniform(-1, 1, 3) * [0.05, 0.05, math.radians(3)])
+    return grid, scans, inits
 
-    import torch
+
+def cpu_rt_sample(oracle, grid, scans, inits, threads):
+    """All host threads, one real-time match per task (thread pool over the oracle)."""
+    from concurrent.futures import ThreadPoolExecutor
+    og = oracle.Grid2D(grid.cells, grid.resolution, grid.max_x, grid.max_y)
+
+    def one(k):
+        return oracle.rt2d_match(og, scans[k], inits[k], 0.1, math.radians(7.0), 0.1, 0.1)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:     # ctypes releases the GIL inside the oracle
+        out = list(ex.map(one, range(len(scans))))
+    return time.perf_counter() - t0, out
+
+
+def run_reference_rt(args, oracle, threads):
+    n = threads * 8
+    grid, scans, inits = rt_world(n)
+    tot_s, tot_c, tot_m = 0.0, 0, 0
+    for it in range(args.warmup + args.steps):
+        secs, out = cpu_rt_sample(oracle, grid, scans, inits, threads)
+        if it >= args.warmup:
+            tot_s += secs
+            tot_c += sum(o["candidates_scored"] for o in out)
+            tot_m += n
+    value = tot_c / tot_s
+    print(json.dumps({
+        "impl": "reference", "metric": "candidate_poses_scored_per_sec", "value": value,
+        "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 ordered sum", "data": "synthetic",
+        "config": {"workload": WORKLOADS[1], "matches_per_step": n},
+        "matches_per_sec": tot_m / tot_s,
+        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": threads, "kind": "port",
+                         "sample": "%d real-time matches per step on %d host threads" % (n, threads)},
+        "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0}}))
+
+
+# =============================================================================
+# distributed plumbing: torch.distributed only carries the barrier, the scalar
+# reductions of the timing and the bootstrap id; the data-path collective is the
+# library's own ncclAllGather (csm_cb_batch2d_run).
+# =============================================================================
+class Dist:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+
+    def make_context(self, sm):
+        uid = None
+        if self.world > 1:
+            box = [sm.MultiGpuContext.unique_id() if self.rank == 0 else None]
+            self.dist.broadcast_object_list(box, src=0)
+            uid = box[0]
+        return sm.MultiGpuContext(self.world, self.rank, self.local_rank, uid)
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(v) for v in t]
+
+    def finish(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+# =============================================================================
+# config 2 (headline): MatchFullSubmap, weak scaling
+# =============================================================================
+def bench_full_submap(args, D):
+    torch = D.torch
     from cartographer_b200 import scan_matching as sm
     from cartographer_b200._lib import lib
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    dist = None
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
+    rank, world, dev = D.rank, D.world, D.dev
+    ctx = D.make_context(sm)
     total_steps = args.warmup + args.steps
     num_scans = total_steps * MATCHES_PER_STEP
-    grid, scans = make_world(rank, num_scans + MATCHES_PER_STEP)
+    grid, scans = make_world(rank, num_scans)
     opts = sm.FastCorrelativeScanMatcherOptions2D(LIN, ANG, DEPTH)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    matcher = sm.FastCorrelativeScanMatcher2D(grid, opts, device=local_rank)
+    matcher = sm.FastCorrelativeScanMatcher2D(grid, opts, device=D.local_rank)
     stack_build_ms = 1e3 * (time.perf_counter() - t0)
-    clouds = [sm.DeviceCloud(s, device=local_rank) for s in scans]
+    clouds = [sm.DeviceCloud(s, device=D.local_rank) for s in scans]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # the global queue of one step: rank r owns submap r and its MATCHES_PER_STEP searches
+    matchers_g = [matcher if r == rank else None for r in range(world)]
+    owner = np.arange(world, dtype=np.int32)
 
-    def jobs_for(step):
+    # (the job list is the same every step: built once, outside the timed region)
+    jobs_all = np.zeros(world * MATCHES_PER_STEP, sm.JOB2D_DTYPE)
+    jobs_all["stack_index"] = np.repeat(np.arange(world), MATCHES_PER_STEP)
+    jobs_all["cloud_index"] = np.arange(world * MATCHES_PER_STEP)
+    jobs_all["full_submap"] = 1
+    jobs_all["min_score"] = MIN_SCORE
+    pad_lo = [None] * (rank * MATCHES_PER_STEP)
+    pad_hi = [None] * ((world - 1 - rank) * MATCHES_PER_STEP)
+
+    def run_step(step, step_clouds=None):
+        """Identical job list on every rank; only this rank's clouds are materialised
+        (the others are never dereferenced here)."""
+        own = (step_clouds if step_clouds is not None
+               else clouds[step * MATCHES_PER_STEP:(step + 1) * MATCHES_PER_STEP])
+        return sm.match_batch_sharded(ctx, matchers_g, pad_lo + list(own) + pad_hi, jobs_all,
+                                      LIN, ANG, owner)
+
+    # ---- device-resident leg (value) -------------------------------------------
+    launches0 = sm.kernel_launch_count()
+    step_s, cand, found, dev_ms, host_syncs = [], 0, 0, 0.0, 0
+    mine = slice(rank * MATCHES_PER_STEP, (rank + 1) * MATCHES_PER_STEP)
+    results_by_step = []
+    for it in range(total_steps):
+        flush.zero_()
+        D.barrier()
+        if it == args.warmup:
+            launches0 = sm.kernel_launch_count()
+        t0 = time.perf_counter()
+        res, st = run_step(it)   # local searches + the allgather + the final synchronise
+        dt = time.perf_counter() - t0
+        results_by_step.append(res[mine].copy())
+        if it >= args.warmup:
+            step_s.append(dt)
+            cand += st["candidates_scored"]
+            found += int(res[mine]["found"].sum())
+            dev_ms += st["device_ms"]
+            host_syncs = max(host_syncs, st["host_syncs"])
+    launches = sm.kernel_launch_count() - launches0
+    elapsed = D.reduce([float(sum(step_s))], "MAX")[0]
+    cand_all, found_all = D.reduce([float(cand), float(found)], "SUM")
+    matches_all = world * args.steps * MATCHES_PER_STEP
+    value = cand_all / elapsed
+
+    # ---- end-to-end leg: the step's scans start in HOST memory ---------------------
+    e2e_s, e2e_c = [], 0
+    for it in range(total_steps):
+        flush.zero_()
+        D.barrier()
+        t0 = time.perf_counter()
+        step_clouds = [sm.DeviceCloud(scans[it * MATCHES_PER_STEP + b], device=D.local_rank)
+                       for b in range(MATCHES_PER_STEP)]          # csm_cloud_create = H2D
+        res_e, st_e = run_step(it, step_clouds)                    # results land in host memory
+        for c in step_clouds:
+            c.close()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            e2e_s.append(dt)
+            e2e_c += st_e["candidates_scored"]
+    e2e_elapsed = D.reduce([float(sum(e2e_s))], "MAX")[0]
+    e2e_value = D.reduce([float(e2e_c)], "SUM")[0] / e2e_elapsed
+    h2d = MATCHES_PER_STEP * 1081 * 12
+    d2h = world * MATCHES_PER_STEP * sm.RESULT2D_DTYPE.itemsize
+
+    # ---- clocks (separate pass), roofline (per-kernel CUDA events), CPU baseline ----
+    def queue_local(it):
         jobs = np.zeros(MATCHES_PER_STEP, sm.JOB2D_DTYPE)
+        s = args.warmup + it % max(1, args.steps)
         for b in range(MATCHES_PER_STEP):
-            jobs[b]["stack_index"] = 0
-            jobs[b]["cloud_index"] = step * MATCHES_PER_STEP + b
+            jobs[b]["cloud_index"] = s * MATCHES_PER_STEP + b
             jobs[b]["full_submap"] = 1
             jobs[b]["min_score"] = MIN_SCORE
         return jobs
 
-    gathered = None
-    if dist is not None:
-        gathered = torch.empty(world * MATCHES_PER_STEP * sm.RESULT2D_DTYPE.itemsize,
-                               dtype=torch.uint8, device=dev)
-
-    def allgather_results(res):
-        """The path's only collective: every rank ends up with all constraints."""
-        if dist is None:
-            return res
-        mine = torch.from_numpy(res.view(np.uint8).reshape(-1).copy()).to(dev, non_blocking=False)
-        dist.all_gather_into_tensor(gathered, mine)
-        return gathered
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def finish():
-        # end of a step on this rank: the allgather (a collective, so it already waits
-        # for every rank's results) has completed and the device is idle
-        torch.cuda.synchronize()
-
-    # ---- device-resident leg (value) -------------------------------------------
-    # No poller runs during the timed legs (an nvidia-smi loop contends on the driver
-    # lock with kernel launches); the clocks are sampled in a separate pass that repeats
-    # the same steps right after the timed ones (see `clocks.note`).
-    launches0 = sm.kernel_launch_count()
-    step_s, cand, found = [], 0, 0
-    dev_ms = 0.0
-    host_syncs = 0
-    results_by_step = []
-    for it in range(total_steps):
-        flush.zero_()
-        barrier()
-        if it == args.warmup:
-            launches0 = sm.kernel_launch_count()
-        t0 = time.perf_counter()
-        res, st = sm.match_batch([matcher], clouds, jobs_for(it), LIN, ANG)
-        allgather_results(res)
-        finish()
-        dt = time.perf_counter() - t0
-        results_by_step.append(res.copy())
-        if it >= args.warmup:
-            step_s.append(dt)
-            cand += st["candidates_scored"]
-            found += int(res["found"].sum())
-            dev_ms += st["device_ms"]
-            host_syncs = max(host_syncs, st["host_syncs"])
-    launches = sm.kernel_launch_count() - launches0
-    elapsed = float(sum(step_s))
-    t = torch.tensor([elapsed, float(cand), float(found)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        elapsed, cand_all, found_all = float(tmax[0]), float(tsum[1]), float(tsum[2])
-    else:
-        cand_all, found_all = float(cand), float(found)
-    matches_all = world * args.steps * MATCHES_PER_STEP
-    value = cand_all / elapsed
-
-    # ---- end-to-end leg (host clouds through csm_match2d) ------------------------
-    e2e_s, e2e_c = [], 0
-    for it in range(total_steps):
-        flush.zero_()
-        barrier()
-        t0 = time.perf_counter()
-        # the step's scans start in HOST memory: upload them (csm_cloud_create = H2D),
-        # run the batch, read the results back, release the device copies
-        step_clouds = [sm.DeviceCloud(scans[it * MATCHES_PER_STEP + b], device=local_rank)
-                       for b in range(MATCHES_PER_STEP)]
-        jobs = jobs_for(0)
-        res, st_e = sm.match_batch([matcher], step_clouds, jobs, LIN, ANG)
-        c_step = st_e["candidates_scored"]
-        for c in step_clouds:
-            c.close()
-        allgather_results(res)
-        finish()
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            e2e_s.append(dt)
-            e2e_c += c_step
-    te = torch.tensor([float(sum(e2e_s)), float(e2e_c)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        a = te.clone()
-        dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        b = te.clone()
-        dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        e2e_value = float(b[1]) / float(a[0])
-    else:
-        e2e_value = float(te[1]) / float(te[0])
-    h2d = MATCHES_PER_STEP * 1081 * 12
-    d2h = MATCHES_PER_STEP * sm.RESULT2D_DTYPE.itemsize
-
-    # ---- clocks under load (separate pass over the same steps, rank 0's GPU) -------
+    def one(it):
+        return sm.match_batch([matcher], clouds, queue_local(it), LIN, ANG)
     clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
     if rank == 0:
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        t_end = time.perf_counter() + 1.5
-        it = 0
-        while time.perf_counter() < t_end or it < args.steps:
-            sm.match_batch([matcher], clouds, jobs_for(args.warmup + it % max(1, args.steps)), LIN, ANG)
-            it += 1
-        clocks = sampler.summary()
-        clocks["note"] = ("sampled with nvidia-smi -lms 100 while the same steps ran again right "
-                          "after the timed region (no poller inside the timed legs)")
-    barrier()
-
-    # ---- roofline of the dominant kernel (CUDA events on the engine's stream) ----
-    import ctypes as C
+        clocks = sample_clocks(D.local_rank, one)
+    D.barrier()
     roofline = None
     if rank == 0:
         lib().csm_profile_enable(1)
-        sm.match_batch([matcher], clouds, jobs_for(args.warmup), LIN, ANG)
-        buf = C.create_string_buffer(8192)
-        lib().csm_profile_read(buf, 8192)
+        one(0)
+        kernels = read_profile(lib)
         lib().csm_profile_enable(0)
-        kernels = {}
-        for ln in buf.value.decode().strip().splitlines():
-            nm, n_l, ms, units = ln.split()
-            kernels[nm] = {"launches": int(n_l), "ms": float(ms), "units": float(units)}
-        tot_ms = sum(k["ms"] for k in kernels.values())
-        top = max(kernels, key=lambda k: kernels[k]["ms"])
-        k = kernels[top]
-        peak, how = measured_peak_gbs()
-        ach = k["units"] * BYTES_PER_CANDIDATE / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
-        traffic = None
-        try:  # DRAM bytes per launch of this kernel from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                traffic = json.load(f).get(top)
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak,
-                    "peak_source": how, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_note": "ncu dram bytes of the largest launch of this kernel; the "
-                                    "working set is L2-resident, so DRAM traffic << algorithmic bytes",
-                    "launches": k["launches"],
-                    "avg_launch_ms": k["ms"] / max(1, k["launches"]),
-                    "share_of_step": k["ms"] / tot_ms if tot_ms else None,
-                    "bytes_per_candidate": BYTES_PER_CANDIDATE,
-                    "kernels": {n: {"ms": round(v["ms"], 4), "launches": v["launches"],
-                                    "candidates": v["units"]} for n, v in kernels.items()}}
-
-    # ---- CPU baseline (oracle on the host cores, bounded sample) -----------------
+        roofline = roofline_block(kernels, BYTES_PER_CANDIDATE, clocks.get("sm_mhz"))
     cpu = None
     parity_checked = parity_failed = 0
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -360,13 +475,12 @@ def main():
         threads = max(1, min(os.cpu_count() or 1, 64))
         og = oracle.Grid2D(grid.cells, grid.resolution, grid.max_x, grid.max_y)
         om = oracle.FastCorrelativeScanMatcher2D(og, LIN, ANG, DEPTH)
-        sample = scans[:threads] if len(scans) >= threads else (scans * threads)[:threads]
+        sample = (scans * (threads // len(scans) + 1))[:threads]
         secs, found_c, scores_c, poses_c, cs_c = oracle.fast2d_batch(
             [om], [0] * len(sample), list(range(len(sample))), np.zeros((len(sample), 3)), sample,
             True, MIN_SCORE, threads)
-        c_cpu, m_cpu = int(cs_c.sum()), len(sample)
         # the same scans went through the engine in the timed steps: compare bit for bit
-        for k in range(min(len(sample), len(scans), total_steps * MATCHES_PER_STEP)):
+        for k in range(min(len(sample), len(scans))):
             g = results_by_step[k // MATCHES_PER_STEP][k % MATCHES_PER_STEP]
             ok = bool(g["found"]) == bool(found_c[k])
             if ok and found_c[k]:
@@ -374,34 +488,272 @@ def main():
                       np.array_equal(g["pose_estimate"], poses_c[k]))
             parity_checked += 1
             parity_failed += 0 if ok else 1
-        cpu = {"value": c_cpu / secs, "unit": "candidates/s", "cores": threads, "kind": "port",
-               "constraints_per_sec": m_cpu / secs,
+        cpu = {"value": float(cs_c.sum()) / secs, "unit": "candidates/s", "cores": threads,
+               "kind": "port", "constraints_per_sec": len(sample) / secs,
                "sample": "%d MatchFullSubmap (one per host thread) of the same workload, "
-                         "%.1f s wall" % (m_cpu, secs)}
+                         "%.1f s wall" % (len(sample), secs)}
 
     if rank == 0:
-        line = {
+        print(json.dumps({
             "metric": "candidate_poses_scored_per_sec", "value": value, "unit": "candidates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "matches_per_step_per_gpu": MATCHES_PER_STEP,
-                       "world": "one submap of the same synthetic floor plan per rank, per-rank node scans",
-                       "min_score": MIN_SCORE, "l2": "flushed between steps (256 MB write)",
+            "config": {"workload": WORKLOADS[2], "matches_per_step_per_gpu": MATCHES_PER_STEP,
+                       "world": "one submap of the same synthetic floor plan per rank, per-rank "
+                                "node scans", "min_score": MIN_SCORE,
+                       "l2": "flushed between steps (256 MB write)",
+                       "collective": ("one ncclAllGather per step inside libcsm_b200.so "
+                                      "(csm_cb_batch2d_run)" if world > 1 else "none (1 GPU)"),
                        "stack_build_ms": stack_build_ms, "found": found_all,
                        "parallelism": "submap-sharded x%d" % world},
             "constraints_per_sec": matches_all / elapsed,
             "device_ms_per_step": dev_ms / max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+                    "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_elapsed / max(1, args.steps)},
             "gpu_launches": int(launches), "host_syncs_per_batch": host_syncs, "clocks": clocks,
             "parity_checked": parity_checked, "parity_failed": parity_failed,
-            "roofline": roofline, "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+            "roofline": roofline, "cpu_baseline": cpu}))
+    ctx.close()
+
+
+# =============================================================================
+# config 4: the ConstraintBuilder2D queue at BASELINE size, strong scaling
+# =============================================================================
+def bench_cb2d(args, D):
+    torch = D.torch
+    from cartographer_b200 import scan_matching as sm
+    rank, world = D.rank, D.world
+    ctx = D.make_context(sm)
+    n_sub = max(world, int(round(1000 * args.scale)))
+    n_node = max(2, int(round(200 * args.scale)))
+    min_score = 0.55
+    distinct = min(n_sub, 16)
+    worlds = [synthetic.make_grid2d(s, 1000) for s in range(distinct)]
+    opts = sm.FastCorrelativeScanMatcherOptions2D(LIN, ANG, DEPTH)
+    # node scans: every node lives in one of the floor plans; all ranks hold all scans
+    rng = np.random.RandomState(3)
+    scans, truths = [], []
+    for nidx in range(n_node):
+        g, occ = worlds[nidx % distinct]
+        pose = synthetic.random_free_pose(occ, g, rng)
+        scans.append(synthetic.cast_scan(occ, g, pose, seed=1000 + nidx))
+        truths.append(pose)
+    # the whole queue (identical on every rank): submap-major, initial pose = truth (+) U
+    jobs = np.zeros(n_sub * n_node, sm.JOB2D_DTYPE)
+    k = 0
+    for si in range(n_sub):
+        for ni in range(n_node):
+            jobs[k]["stack_index"] = si
+            jobs[k]["cloud_index"] = ni
+            jobs[k]["initial_pose"] = truths[ni] + rng.uniform(-1, 1, 3) * [3.0, 3.0, math.radians(15)]
+            jobs[k]["min_score"] = min_score
+            k += 1
+    owner = (np.arange(n_sub) % world).astype(np.int32)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    matchers = [sm.FastCorrelativeScanMatcher2D(worlds[s % distinct][0], opts, device=D.local_rank)
+                if owner[s] == rank else None for s in range(n_sub)]
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    clouds = [sm.DeviceCloud(s, device=D.local_rank) for s in scans]
+    step_s, cand = [], 0
+    res = None
+    for it in range(args.warmup + args.steps):
+        D.barrier()
+        t0 = time.perf_counter()
+        res, st = sm.match_batch_sharded(ctx, matchers, clouds, jobs, LIN, ANG, owner)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            step_s.append(dt)
+            cand += st["candidates_scored"]
+    elapsed = D.reduce([float(sum(step_s))], "MAX")[0]
+    cand_all = D.reduce([float(cand)], "SUM")[0]
+    found = int(res["found"].sum())
+    # e2e: node scans start in host memory (H2D of every scan on every rank), results to host
+    e2e_s = []
+    for it in range(max(1, min(args.steps, 2))):
+        D.barrier()
+        t0 = time.perf_counter()
+        step_clouds = [sm.DeviceCloud(s, device=D.local_rank) for s in scans]
+        sm.match_batch_sharded(ctx, matchers, step_clouds, jobs, LIN, ANG, owner)
+        for c in step_clouds:
+            c.close()
+        e2e_s.append(time.perf_counter() - t0)
+    e2e_elapsed = D.reduce([float(np.mean(e2e_s))], "MAX")[0]
+    cand_step = cand_all / max(1, args.steps)
+    # parity + CPU baseline on a bounded sample (rank 0, any N: results are on every rank)
+    cpu, parity_checked, parity_failed = None, 0, 0
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import pyoracle as oracle
+        oracle.build()
+        threads = max(1, min(os.cpu_count() or 1, 64))
+        sample = np.unique(np.linspace(0, len(jobs) - 1, threads * 4).astype(int))
+        oms = {}
+        for si in sorted({int(jobs[j]["stack_index"]) % distinct for j in sample}):
+            g = worlds[si][0]
+            oms[si] = oracle.FastCorrelativeScanMatcher2D(
+                oracle.Grid2D(g.cells, g.resolution, g.max_x, g.max_y), LIN, ANG, DEPTH)
+        keys = sorted(oms)
+        secs, found_c, scores_c, poses_c, cs_c = oracle.fast2d_batch(
+            [oms[kk] for kk in keys],
+            [keys.index(int(jobs[j]["stack_index"]) % distinct) for j in sample],
+            [int(jobs[j]["cloud_index"]) for j in sample],
+            np.array([jobs[j]["initial_pose"] for j in sample]), scans, False, min_score, threads)
+        for i, j in enumerate(sample):
+            ok = bool(res[j]["found"]) == bool(found_c[i])
+            if ok and found_c[i]:
+                ok = (np.float32(res[j]["score"]) == scores_c[i] and
+                      np.array_equal(res[j]["pose_estimate"], poses_c[i]))
+            parity_checked += 1
+            parity_failed += 0 if ok else 1
+        cpu = {"value": float(cs_c.sum()) / secs, "unit": "candidates/s", "cores": threads,
+               "kind": "port", "constraints_per_sec": len(sample) / secs,
+               "sample": "%d of the queue's searches on %d host threads, %.1f s wall" %
+                         (len(sample), threads, secs)}
+    clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if rank == 0:
+        sub = jobs[owner[jobs["stack_index"]] == 0][:2000]
+        dense = [m if m is not None else matchers[0] for m in matchers]
+        clocks = sample_clocks(D.local_rank,
+                               lambda it: sm.match_batch(dense, clouds, sub, LIN, ANG))
+    D.barrier()
+    if rank == 0:
+        steps = max(1, args.steps)
+        print(json.dumps({
+            "metric": "candidate_poses_scored_per_sec", "value": cand_all / elapsed,
+            "unit": "candidates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[4], "submaps": n_sub, "nodes": n_node,
+                       "jobs": len(jobs), "found": found, "min_score": min_score,
+                       "distinct_floor_plans": distinct,
+                       "note": "%d device stacks built from %d distinct synthetic floor plans; "
+                               "inputs (%.1f GB of stacks per rank) exceed L2" %
+                               (n_sub, distinct, 0.04 * n_sub / world),
+                       "collective": ("one ncclAllGather of %d x 56 B records per step inside "
+                                      "libcsm_b200.so" % len(jobs) if world > 1 else "none (1 GPU)"),
+                       "stack_build_s_per_rank": build_s,
+                       "parallelism": "submap-major shards x%d" % world},
+            "constraints_per_sec": len(jobs) * steps / elapsed,
+            "e2e": {"value": cand_step / e2e_elapsed, "unit": "candidates/s",
+                    "constraints_per_sec": len(jobs) / e2e_elapsed,
+                    "h2d_bytes_per_step": n_node * 1081 * 12,
+                    "d2h_bytes_per_step": len(jobs) * sm.RESULT2D_DTYPE.itemsize},
+            "gpu_launches": int(sm.kernel_launch_count()), "clocks": clocks,
+            "parity_checked": parity_checked, "parity_failed": parity_failed,
+            "cpu_baseline": cpu, "roofline": None}))
+    ctx.close()
+
+
+# =============================================================================
+# config 1: RealTimeCorrelativeScanMatcher2D, batched against a device-resident grid
+# =============================================================================
+def bench_rt(args, D):
+    torch = D.torch
+    from cartographer_b200 import scan_matching as sm
+    from cartographer_b200._lib import lib
+    rank, world = D.rank, D.world
+    n = 1000
+    grid, scans, inits = rt_world(n)
+    opts = sm.RealTimeCorrelativeScanMatcherOptions(0.1, math.radians(7.0), 0.1, 0.1)
+    rt = sm.RealTimeCorrelativeScanMatcher2D(opts, device=D.local_rank)
+    dg = sm.RealTimeGrid2D(grid, device=D.local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=D.dev)
+    step_s, cand, dev_ms = [], 0, 0.0
+    scores = poses = None
+    for it in range(args.warmup + args.steps):
+        flush.zero_()
+        D.barrier()
+        t0 = time.perf_counter()
+        scores, poses, st = rt.MatchBatch(inits, scans, dg)   # host scans in, host poses out
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            step_s.append(dt)
+            cand += st["candidates_scored"]
+            dev_ms += st["device_ms"]
+    elapsed = D.reduce([float(sum(step_s))], "MAX")[0]
+    cand_all = D.reduce([float(cand)], "SUM")[0]
+    # single-call form (the reference signature: grid passed per call)
+    t0 = time.perf_counter()
+    for k in range(100):
+        rt.Match(inits[k], scans[k], grid)
+    single_s = (time.perf_counter() - t0) / 100
+    roofline = None
+    if rank == 0:
+        lib().csm_profile_enable(1)
+        rt.MatchBatch(inits, scans, dg)
+        kernels = read_profile(lib)
+        lib().csm_profile_enable(0)
+        roofline = roofline_block(kernels, BYTES_PER_CANDIDATE_RT, None)
+    cpu, parity_checked, parity_failed = None, 0, 0
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import pyoracle as oracle
+        oracle.build()
+        threads = max(1, min(os.cpu_count() or 1, 64))
+        m = min(n, threads * 8)
+        secs, out = cpu_rt_sample(oracle, grid, scans[:m], inits[:m], threads)
+        for k in range(m):
+            ok = (np.float32(scores[k]) == np.float32(out[k]["score"]) and
+                  np.array_equal(poses[k], out[k]["pose"]))
+            parity_checked += 1
+            parity_failed += 0 if ok else 1
+        cpu = {"value": sum(o["candidates_scored"] for o in out) / secs, "unit": "candidates/s",
+               "cores": threads, "kind": "port", "matches_per_sec": m / secs,
+               "sample": "%d real-time matches on %d host threads, %.2f s wall" % (m, threads, secs)}
+    clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if rank == 0:
+        clocks = sample_clocks(D.local_rank, lambda it: rt.MatchBatch(inits, scans, dg))
+    D.barrier()
+    if rank == 0:
+        steps = max(1, args.steps)
+        v = cand_all / elapsed
+        print(json.dumps({
+            "metric": "candidate_poses_scored_per_sec", "value": v, "unit": "candidates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 ordered sum / f64 weight", "data": "synthetic",
+            "config": {"workload": WORKLOADS[1], "matches_per_step_per_gpu": n,
+                       "l2": "flushed between steps (256 MB write)",
+                       "note": "value == e2e: the batch entry takes HOST scans and returns host "
+                               "poses (H2D + D2H inside every step); only the grid is resident"},
+            "matches_per_sec": world * n * steps / elapsed,
+            "device_ms_per_step": dev_ms / steps,
+            "single_call_ms": 1e3 * single_s,
+            "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": n * 1081 * 12,
+                    "d2h_bytes_per_step": n * 8},
+            "gpu_launches": int(sm.kernel_launch_count()), "clocks": clocks,
+            "parity_checked": parity_checked, "parity_failed": parity_failed,
+            "roofline": roofline, "cpu_baseline": cpu}))
+    dg.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    D = Dist()
+    if args.config == 2:
+        bench_full_submap(args, D)
+    elif args.config == 4:
+        bench_cb2d(args, D)
+    elif args.config == 1:
+        bench_rt(args, D)
+    else:
+        from benchmarks import bench_cb3d
+        bench_cb3d.run(args, D, WORKLOADS[5], sample_clocks)
+    D.finish()
 
 
 if __name__ == "__main__":

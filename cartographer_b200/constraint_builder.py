@@ -171,10 +171,14 @@ class ConstraintBuilder2D:
     matching (CudaExecutor in production); `process_group` (torch.distributed) turns
     on submap-major sharding + the single all_gather of constraint records."""
 
-    def __init__(self, options, executor=None, process_group=None, device=0):
+    def __init__(self, options, executor=None, process_group=None, device=0, context=None):
+        """`context` (scan_matching.MultiGpuContext): the library's own NCCL communicator;
+        when given, the single all-gather runs inside libcsm_b200.so (csm_ctx_allgather ->
+        ncclAllGather) and no torch.distributed group is needed."""
         self.options = options
         self.executor = executor if executor is not None else CudaExecutor(options, device)
         self.pg = process_group
+        self.ctx = context
         self.device = device
         self._jobs = []
         self._submaps = {}
@@ -231,6 +235,8 @@ class ConstraintBuilder2D:
 
     # -- drain ---------------------------------------------------------------------
     def _world(self):
+        if self.ctx is not None:
+            return self.ctx.rank, self.ctx.world_size
         if self.pg is None:
             return 0, 1
         import torch.distributed as dist
@@ -283,11 +289,23 @@ class ConstraintBuilder2D:
         shard, gathered to every rank and re-ordered into queue order."""
         if world == 1:
             return local
-        import torch
-        import torch.distributed as dist
         counts = [sum(1 for j in self._jobs if self._submap_order[j.submap_id] % world == r)
                   for r in range(world)]
         cap = max(1, max(counts))
+        if self.ctx is not None:   # ncclAllGather inside the library
+            send = np.zeros(cap, RECORD_DTYPE)
+            send[:len(local)] = local
+            parts = self.ctx.allgather(send.tobytes())
+            allrec = np.stack([np.frombuffer(p, dtype=RECORD_DTYPE) for p in parts])
+            out = np.zeros(total, RECORD_DTYPE)
+            cursor = [0] * world
+            for i, j in enumerate(self._jobs):
+                r = self._submap_order[j.submap_id] % world
+                out[i] = allrec[r, cursor[r]]
+                cursor[r] += 1
+            return out
+        import torch
+        import torch.distributed as dist
         backend = dist.get_backend(self.pg)
         dev = torch.device("cuda", self.device) if backend == "nccl" else torch.device("cpu")
         send = np.zeros(cap, RECORD_DTYPE)

@@ -321,6 +321,70 @@ RealTimeCorrelativeScanMatcher2D.MatchBatch = _rt_match_batch
 RealTimeCorrelativeScanMatcher2D.ScoreCandidates = _rt_score_candidates
 
 
+class MultiGpuContext:
+    """csm_ctx: this process's place in a one-process-per-GPU job and its NCCL
+    communicator (created inside the library).  Rank 0 calls MultiGpuContext.unique_id()
+    and the 128 bytes are handed to every rank by the application (bench.py uses a
+    torch.distributed object broadcast; a file or socket works as well)."""
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * MultiGpuContext.ID_BYTES)()
+        check(lib().csm_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, world_size=1, rank=0, device=0, unique_id=None):
+        self.world_size, self.rank, self.device = world_size, rank, device
+        self._h = C.c_void_p()
+        idbuf = None
+        if world_size > 1:
+            if unique_id is None or len(unique_id) != self.ID_BYTES:
+                raise ValueError("unique_id (128 bytes from rank 0) is required for world_size > 1")
+            idbuf = (C.c_uint8 * self.ID_BYTES).from_buffer_copy(unique_id)
+        check(lib().csm_ctx_create(C.c_int32(world_size), C.c_int32(rank), C.c_int32(device),
+                                   idbuf, C.byref(self._h)))
+
+    def allgather(self, payload):
+        """bytes -> list of world_size byte strings (one ncclAllGather)."""
+        n = len(payload)
+        send = (C.c_uint8 * max(1, n)).from_buffer_copy(payload if n else b"\0")
+        recv = (C.c_uint8 * max(1, n * self.world_size))()
+        check(lib().csm_ctx_allgather(self._h, send, C.c_int64(n), recv))
+        raw = bytes(recv)
+        return [raw[r * n:(r + 1) * n] for r in range(self.world_size)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().csm_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def match_batch_sharded(ctx, matchers, clouds, jobs, linear_search_window, angular_search_window,
+                        submap_owner=None):
+    """csm_cb_batch2d_run: the whole ConstraintBuilder2D queue on all GPUs of `ctx`.
+    `matchers[s]` may be None on ranks that do not own submap s (owner = submap_owner[s],
+    default s % world_size).  Every rank gets the results of ALL jobs, in job order."""
+    jobs = np.ascontiguousarray(jobs, dtype=JOB2D_DTYPE)
+    hs = (C.c_void_p * len(matchers))(*[(m._h if m is not None else None) for m in matchers])
+    cs = (C.c_void_p * len(clouds))(*[(c._h if c is not None else None) for c in clouds])
+    results = np.zeros(len(jobs), RESULT2D_DTYPE)
+    stats = CsmStats()
+    owner = None
+    if submap_owner is not None:
+        owner_arr = np.ascontiguousarray(submap_owner, dtype=np.int32)
+        owner = ptr(owner_arr, C.c_int32)
+    check(lib().csm_cb_batch2d_run(ctx._h, hs, C.c_int32(len(matchers)), cs,
+                                   C.c_int32(len(clouds)), jobs.ctypes.data_as(C.c_void_p),
+                                   C.c_int32(len(jobs)), owner, C.c_double(linear_search_window),
+                                   C.c_double(angular_search_window),
+                                   results.ctypes.data_as(C.c_void_p), C.byref(stats)))
+    return results, stats.as_dict()
+
+
 def kernel_launch_count():
     return int(lib().csm_kernel_launch_count())
 
@@ -333,7 +397,8 @@ def device_count():
 
 __all__ = ["FastCorrelativeScanMatcherOptions2D", "RealTimeCorrelativeScanMatcherOptions",
            "FastCorrelativeScanMatcher2D", "RealTimeCorrelativeScanMatcher2D", "DeviceCloud",
-           "match_batch", "RealTimeGrid2D", "kernel_launch_count", "device_count", "JOB2D_DTYPE",
+           "match_batch", "match_batch_sharded", "MultiGpuContext", "RealTimeGrid2D",
+           "kernel_launch_count", "device_count", "JOB2D_DTYPE",
            "RESULT2D_DTYPE", "_lib"]
 
 

@@ -346,6 +346,44 @@ csm_status csm_discretize3d(const csm_matcher3d* matcher, const csm_node3d* node
                             int32_t* num_scans, int32_t* cells, float* poses,
                             float* rotational_scores);
 
+/* ==== multi-GPU: one process per GPU, the sharded ConstraintBuilder queue ==== */
+/* Every (submap, node) search only depends on its submap's matcher
+ * (constraints/constraint_builder_2d.cc:102-111), so the queue shards by submap with no
+ * data-path exchange; RunWhenDoneCallback (:279-300) hands ONE vector of all constraints
+ * to the caller, so the results are combined with exactly one ncclAllGather of fixed-size
+ * records on the context's stream.  Bootstrap: rank 0 calls csm_comm_unique_id and the
+ * application hands the 128 bytes to every rank by any means (file, socket, MPI, a
+ * torch.distributed object broadcast); then every rank calls csm_ctx_create. */
+#define CSM_COMM_ID_BYTES 128
+typedef struct csm_ctx csm_ctx;
+csm_status csm_comm_unique_id(uint8_t id[CSM_COMM_ID_BYTES]);
+csm_status csm_ctx_create(int32_t world_size, int32_t rank, int32_t device,
+                          const uint8_t id[CSM_COMM_ID_BYTES] /* NULL iff world_size == 1 */,
+                          csm_ctx** out);
+csm_status csm_ctx_destroy(csm_ctx* ctx);
+csm_status csm_ctx_info(const csm_ctx* ctx, int32_t* world_size, int32_t* rank, int32_t* device);
+/* recv = world_size x bytes, rank-major (host buffers; one ncclAllGather inside). */
+csm_status csm_ctx_allgather(csm_ctx* ctx, const void* send, int64_t bytes, void* recv);
+
+/* ConstraintBuilder2D's drained queue on all GPUs.  `jobs` is the WHOLE queue and must be
+ * identical on every rank; job j runs on rank submap_owner[jobs[j].stack_index]
+ * (submap_owner == NULL: stack_index % world_size).  stacks[s] may be NULL on ranks that
+ * do not own submap s; clouds[] must exist on every rank that uses them (node scans are
+ * replicated by H2D, 13 KB each).  On return EVERY rank holds results[0 .. num_jobs) in
+ * job order.  `stats` counts this rank's searches. */
+csm_status csm_cb_batch2d_run(csm_ctx* ctx, const csm_stack2d* const* stacks, int32_t num_stacks,
+                              const csm_cloud* const* clouds, int32_t num_clouds,
+                              const csm_job2d* jobs, int32_t num_jobs,
+                              const int32_t* submap_owner, double linear_search_window,
+                              double angular_search_window, csm_result2d* results,
+                              csm_stats* stats /* may be NULL */);
+/* Same for ConstraintBuilder3D (constraints/constraint_builder_3d.cc:107-116). */
+csm_status csm_cb_batch3d_run(csm_ctx* ctx, const csm_matcher3d* const* matchers,
+                              int32_t num_matchers, const csm_node3d* nodes, int32_t num_nodes,
+                              const csm_job3d* jobs, int32_t num_jobs,
+                              const int32_t* submap_owner, int32_t max_concurrency,
+                              csm_result3d* results, csm_stats* stats /* may be NULL */);
+
 #ifdef __cplusplus
 }
 #endif
