@@ -1707,16 +1707,24 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     d.tx = static_cast<float>(ix);
     d.ty = static_cast<float>(iy);
     d.min_score = jb.min_score;
-    // upper bound of lowest-resolution candidates per axis after ShrinkToFit:
-    // window <= min(2*lin, max(cells - 1 + scan extent, lin))
+    // upper bound of lowest-resolution candidates per axis after ShrinkToFit
+    // (corr...2d.cc:73-91): with c = cell of the sensor origin and e = scan radius in
+    // cells, every point index lies in [c - e, c + e], so the window is at most
+    //   min(lin, max(0, cells - 1 - (c - e))) + min(lin, max(0, c + e)).
+    // (k_discretize re-checks the bound on the device and reports a violation.)
     const int step = 1 << (h.depth - 1);
-    const long long extent = 2LL * static_cast<long long>(std::ceil(cl->max_norm / h.resolution)) + 4;
-    // (a scan wholly outside the grid on one axis keeps a window of min(lin, distance),
-    // which can exceed cells - 1 + extent: hence the max with lin)
-    const long long span_x =
-        std::min<long long>(2LL * sp.lin, std::max<long long>(h.nx - 1 + extent, sp.lin));
-    const long long span_y =
-        std::min<long long>(2LL * sp.lin, std::max<long long>(h.ny - 1 + extent, sp.lin));
+    const long long e = static_cast<long long>(std::ceil(cl->max_norm / h.resolution)) + 4;
+    auto clampll = [](double v) {
+      return static_cast<long long>(std::max(-4e9, std::min(4e9, std::floor(v))));
+    };
+    const long long c_x = clampll((h.max_y - iy) / h.resolution - 0.5);  // index x <- world y
+    const long long c_y = clampll((h.max_x - ix) / h.resolution - 0.5);
+    auto span = [&](long long cells, long long c) {
+      const long long lin = sp.lin;
+      return std::min(lin, std::max<long long>(0, cells - 1 - (c - e))) +
+             std::min(lin, std::max<long long>(0, c + e));
+    };
+    const long long span_x = span(h.nx, c_x), span_y = span(h.ny, c_y);
     const long long cx = (span_x + step) / step, cy = (span_y + step) / step;
     d.cap_y = static_cast<int>(cy);
     d.cap = static_cast<int>(cx * cy);

@@ -611,3 +611,52 @@ def rotational_match(submap_histogram, histogram, initial_angle, angles, device=
                                        C.c_int32(len(ang)), C.c_int32(device),
                                        ptr(out, C.c_float)))
     return out
+
+
+# ===========================================================================
+# RealTimeCorrelativeScanMatcher3D (real_time_correlative_scan_matcher_3d.h:41-67)
+# ===========================================================================
+class DeviceHybridGrid:
+    """A HybridGrid resident on the device (csm_grid3d); `hybrid_grid` is any record with
+    resolution, indices (n x 3 int32) and values (n uint16) — proto::HybridGrid's flat form."""
+
+    def __init__(self, hybrid_grid, device=0):
+        idx = np.ascontiguousarray(hybrid_grid.indices, dtype=np.int32).reshape(-1, 3)
+        val = np.ascontiguousarray(hybrid_grid.values, dtype=np.uint16).reshape(-1)
+        self.resolution = float(hybrid_grid.resolution)
+        self._h = C.c_void_p()
+        check(lib().csm_grid3d_create(ptr(idx, C.c_int32), ptr(val, C.c_uint16),
+                                      C.c_int64(len(val)), C.c_float(self.resolution),
+                                      C.c_int32(device), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().csm_grid3d_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class RealTimeCorrelativeScanMatcher3D:
+    """Match(initial_pose_estimate, point_cloud, hybrid_grid) -> (score, pose_estimate);
+    poses are {tx, ty, tz, qw, qx, qy, qz}.  `hybrid_grid` is a DeviceHybridGrid."""
+
+    def __init__(self, options):
+        self.options = options
+        self.last_stats = None
+
+    def Match(self, initial_pose_estimate, point_cloud, hybrid_grid):
+        xyz = _f32(point_cloud)
+        ip = np.ascontiguousarray(initial_pose_estimate, dtype=np.float64)
+        pose = np.zeros(7, np.float64)
+        score = C.c_float(0.0)
+        stats = CsmStats()
+        o = self.options
+        check(lib().csm_rt_match3d(
+            hybrid_grid._h, ptr(xyz, C.c_float), C.c_int32(len(xyz)), ptr(ip, C.c_double),
+            C.c_double(o.linear_search_window), C.c_double(o.angular_search_window),
+            C.c_double(o.translation_delta_cost_weight),
+            C.c_double(o.rotation_delta_cost_weight), C.byref(score), ptr(pose, C.c_double),
+            C.byref(stats)))
+        self.last_stats = stats.as_dict()
+        return np.float32(score.value), pose

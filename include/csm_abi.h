@@ -346,6 +346,24 @@ csm_status csm_discretize3d(const csm_matcher3d* matcher, const csm_node3d* node
                             int32_t* num_scans, int32_t* cells, float* poses,
                             float* rotational_scores);
 
+/* ==== RealTimeCorrelativeScanMatcher3D ======================================== */
+/* A HybridGrid resident on the device (dense uint16 box over its non-zero voxels; reads
+ * outside the box return 0 = unknown, as HybridGrid::value does for unallocated cells,
+ * mapping/3d/hybrid_grid.h:263-279).  Same flat form as csm_matcher3d_create. */
+typedef struct csm_grid3d csm_grid3d;
+csm_status csm_grid3d_create(const int32_t* indices, const uint16_t* values, int64_t num_voxels,
+                             float resolution, int32_t device, csm_grid3d** out);
+csm_status csm_grid3d_destroy(csm_grid3d* grid);
+/* RealTimeCorrelativeScanMatcher3D::Match
+ * (internal/3d/scan_matching/real_time_correlative_scan_matcher_3d.cc:34-53): exhaustive
+ * (2L+1)^3 x (2A+1)^3 window; *score is the return value, pose_estimate the best
+ * candidate.cast<double>() ({tx,ty,tz, qw,qx,qy,qz}).  stats->num_scans = rotations. */
+csm_status csm_rt_match3d(const csm_grid3d* grid, const float* xyz, int32_t num_points,
+                          const double initial_pose[7], double linear_search_window,
+                          double angular_search_window, double translation_delta_cost_weight,
+                          double rotation_delta_cost_weight, float* score,
+                          double pose_estimate[7], csm_stats* stats /* may be NULL */);
+
 /* ==== multi-GPU: one process per GPU, the sharded ConstraintBuilder queue ==== */
 /* Every (submap, node) search only depends on its submap's matcher
  * (constraints/constraint_builder_2d.cc:102-111), so the queue shards by submap with no

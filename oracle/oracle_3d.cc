@@ -584,4 +584,102 @@ FastCorrelativeScanMatcher3D::GenerateDiscreteScansForTest(bool full,
                                node, submap, nullptr);
 }
 
+// ---- real_time_correlative_scan_matcher_3d.cc ---------------------------------------
+// transform/transform.h:34-37: 2 * atan2(rotation.vec().norm(), |rotation.w()|)
+float GetAngle(const Rigid3f& transform) {
+  const float vec_norm = std::sqrt(transform.q.x * transform.q.x + transform.q.y * transform.q.y +
+                                   transform.q.z * transform.q.z);
+  return 2.f * std::atan2(vec_norm, std::abs(transform.q.w));
+}
+
+// .cc:55-98
+std::vector<Rigid3f> RealTimeCorrelativeScanMatcher3D::GenerateExhaustiveSearchTransforms(
+    const float resolution, const PointCloud& point_cloud) const {
+  std::vector<Rigid3f> result;
+  const int linear_window_size = RoundToInt(options_.linear_search_window / resolution);
+  // "something on the order of resolution to make sure that the std::acos() below is defined"
+  float max_scan_range = 3.f * resolution;
+  for (const Vec3f& point : point_cloud) {
+    const float range = std::sqrt(point.x * point.x + point.y * point.y + point.z * point.z);
+    max_scan_range = std::max(range, max_scan_range);
+  }
+  const float kSafetyMargin = 1.f - 1e-3f;
+  const float angular_step_size =
+      kSafetyMargin * std::acos(1.f - (resolution * resolution) /
+                                          (2.f * (max_scan_range * max_scan_range)));
+  const int angular_window_size = RoundToInt(options_.angular_search_window / angular_step_size);
+  for (int z = -linear_window_size; z <= linear_window_size; ++z) {
+    for (int y = -linear_window_size; y <= linear_window_size; ++y) {
+      for (int x = -linear_window_size; x <= linear_window_size; ++x) {
+        for (int rz = -angular_window_size; rz <= angular_window_size; ++rz) {
+          for (int ry = -angular_window_size; ry <= angular_window_size; ++ry) {
+            for (int rx = -angular_window_size; rx <= angular_window_size; ++rx) {
+              const Vec3f angle_axis{rx * angular_step_size, ry * angular_step_size,
+                                     rz * angular_step_size};
+              result.push_back(Rigid3f{Vec3f{x * resolution, y * resolution, z * resolution},
+                                       AngleAxisVectorToRotationQuaternion(angle_axis)});
+            }
+          }
+        }
+      }
+    }
+  }
+  return result;
+}
+
+// .cc:100-117
+float RealTimeCorrelativeScanMatcher3D::ScoreCandidate(const HybridGrid& hybrid_grid,
+                                                       const PointCloud& transformed_point_cloud,
+                                                       const Rigid3f& transform) const {
+  float score = 0.f;
+  for (const Vec3f& point : transformed_point_cloud) {
+    score += hybrid_grid.GetProbability(hybrid_grid.GetCellIndex(point));
+  }
+  score /= static_cast<float>(transformed_point_cloud.size());
+  const float angle = GetAngle(transform);
+  const float t_norm = std::sqrt(transform.t.x * transform.t.x + transform.t.y * transform.t.y +
+                                 transform.t.z * transform.t.z);
+  const double e = t_norm * options_.translation_delta_cost_weight +
+                   angle * options_.rotation_delta_cost_weight;
+  score *= std::exp(-(e * e));   // float *= double
+  return score;                  // (CHECK_GT(score, 0.f) in the reference)
+}
+
+// .cc:34-53
+float RealTimeCorrelativeScanMatcher3D::Match(const Rigid3d& initial_pose_estimate,
+                                              const PointCloud& point_cloud,
+                                              const HybridGrid& hybrid_grid,
+                                              Rigid3d* pose_estimate, int64_t* num_candidates,
+                                              int64_t* best_index) const {
+  float best_score = -1.f;
+  // initial_pose_estimate.cast<float>()
+  const Rigid3f initial{
+      Vec3f{static_cast<float>(initial_pose_estimate.t.x),
+            static_cast<float>(initial_pose_estimate.t.y),
+            static_cast<float>(initial_pose_estimate.t.z)},
+      Quatf{static_cast<float>(initial_pose_estimate.q.w),
+            static_cast<float>(initial_pose_estimate.q.x),
+            static_cast<float>(initial_pose_estimate.q.y),
+            static_cast<float>(initial_pose_estimate.q.z)}};
+  const std::vector<Rigid3f> transforms =
+      GenerateExhaustiveSearchTransforms(hybrid_grid.resolution(), point_cloud);
+  int64_t index = 0;
+  PointCloud transformed(point_cloud.size());
+  for (const Rigid3f& transform : transforms) {
+    const Rigid3f candidate = Rigid3Mul(initial, transform);
+    for (size_t i = 0; i < point_cloud.size(); ++i)   // sensor::TransformPointCloud
+      transformed[i] = Rigid3Apply(candidate, point_cloud[i]);
+    const float score = ScoreCandidate(hybrid_grid, transformed, transform);
+    if (score > best_score) {
+      best_score = score;
+      *pose_estimate = Rigid3d{Vec3d{candidate.t.x, candidate.t.y, candidate.t.z},
+                               Quatd{candidate.q.w, candidate.q.x, candidate.q.y, candidate.q.z}};
+      if (best_index) *best_index = index;
+    }
+    ++index;
+  }
+  if (num_candidates) *num_candidates = static_cast<int64_t>(transforms.size());
+  return best_score;
+}
+
 }  // namespace oracle

@@ -219,6 +219,32 @@ struct FastCorrelativeScanMatcher3D::DiscreteScan3D {  // .cc:79-84
 std::function<float(const Rigid3f&)> CreateLowResolutionMatcher(const HybridGrid* grid,
                                                                 const PointCloud* points);
 
+// ---- real_time_correlative_scan_matcher_3d.{h,cc} -----------------------------------
+struct RealTimeOptions3D {  // proto/scan_matching/real_time_correlative_scan_matcher_options.proto
+  double linear_search_window;
+  double angular_search_window;
+  double translation_delta_cost_weight;
+  double rotation_delta_cost_weight;
+};
+float GetAngle(const Rigid3f& transform);  // transform/transform.h:34-37
+
+class RealTimeCorrelativeScanMatcher3D {  // real_time_correlative_scan_matcher_3d.h:41-67
+ public:
+  explicit RealTimeCorrelativeScanMatcher3D(const RealTimeOptions3D& options)
+      : options_(options) {}
+  // .cc:34-53; num_candidates / best_index (generation order) are reported for the tests
+  float Match(const Rigid3d& initial_pose_estimate, const PointCloud& point_cloud,
+              const HybridGrid& hybrid_grid, Rigid3d* pose_estimate,
+              int64_t* num_candidates = nullptr, int64_t* best_index = nullptr) const;
+  std::vector<Rigid3f> GenerateExhaustiveSearchTransforms(float resolution,
+                                                          const PointCloud& point_cloud) const;
+  float ScoreCandidate(const HybridGrid& hybrid_grid, const PointCloud& transformed_point_cloud,
+                       const Rigid3f& transform) const;
+
+ private:
+  const RealTimeOptions3D options_;
+};
+
 }  // namespace oracle
 
 #endif  // ORACLE_3D_H_

@@ -390,6 +390,23 @@ float orc_hybrid_get_probability(void* h, int x, int y, int z) {
   return static_cast<HybridGrid*>(h)->GetProbability(Array3i{x, y, z});
 }
 
+// RealTimeCorrelativeScanMatcher3D::Match (real_time_correlative_scan_matcher_3d.cc:34-53).
+// pose in / out = {tx,ty,tz, qw,qx,qy,qz}; stats_out = {num_candidates, best_index}.
+float orc_rt3d_match(void* hybrid, const float* xyz, int n, const double* initial_pose,
+                     double lin, double ang, double w_t, double w_r, double* pose_out,
+                     int64_t* stats_out) {
+  const HybridGrid* g = static_cast<HybridGrid*>(hybrid);
+  const RealTimeCorrelativeScanMatcher3D matcher(RealTimeOptions3D{lin, ang, w_t, w_r});
+  Rigid3d pose{Vec3d{0., 0., 0.}, Quatd{1., 0., 0., 0.}};
+  int64_t num = 0, best = -1;
+  const float score =
+      matcher.Match(MakeRigid3d(initial_pose), MakeCloud(xyz, n), *g, &pose, &num, &best);
+  pose_out[0] = pose.t.x; pose_out[1] = pose.t.y; pose_out[2] = pose.t.z;
+  pose_out[3] = pose.q.w; pose_out[4] = pose.q.x; pose_out[5] = pose.q.y; pose_out[6] = pose.q.z;
+  if (stats_out) { stats_out[0] = num; stats_out[1] = best; }
+  return score;
+}
+
 void* orc_fast3d_create(void* hi, void* lo, const float* hist, int hist_n, int bb_depth,
                         int full_res_depth, double min_rot, double min_low, double lin_xy,
                         double lin_z, double ang) {

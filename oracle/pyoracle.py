@@ -46,6 +46,7 @@ def lib():
         _lib.orc_fast3d_create.restype = C.c_void_p
         _lib.orc_hybrid_create.restype = C.c_void_p
         _lib.orc_hybrid_get_probability.restype = C.c_float
+        _lib.orc_rt3d_match.restype = C.c_float
     return _lib
 
 
@@ -438,3 +439,17 @@ def rotational_match(submap_hist, hist, initial_angle, angles):
                                C.c_float(initial_angle), _p(ang, C.c_float), C.c_int(len(ang)),
                                _p(out, C.c_float))
     return out
+
+
+def rt3d_match(hybrid_grid, xyz, initial_pose, lin, ang, w_t, w_r):
+    """RealTimeCorrelativeScanMatcher3D::Match; initial_pose / pose = {t xyz, q wxyz}."""
+    xyz = _f32(xyz)
+    ip = np.ascontiguousarray(initial_pose, dtype=np.float64)
+    pose = np.zeros(7, np.float64)
+    stats = np.zeros(2, np.int64)
+    score = lib().orc_rt3d_match(hybrid_grid._h, _p(xyz, C.c_float), C.c_int(len(xyz)),
+                                 _p(ip, C.c_double), C.c_double(lin), C.c_double(ang),
+                                 C.c_double(w_t), C.c_double(w_r), _p(pose, C.c_double),
+                                 _p(stats, C.c_int64))
+    return dict(score=np.float32(score), pose=pose, candidates_scored=int(stats[0]),
+                best_index=int(stats[1]))

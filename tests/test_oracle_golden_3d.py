@@ -124,3 +124,54 @@ def test_fast_matcher_3d_full_submap(oracle):
     assert worlds3d.is_nearly(expected, r["pose"], 0.05), (expected, r["pose"])
     far = worlds3d.node_data(worlds3d.AXIS_CLOUD, low=np.array([[42.0, 42.0, 42.0]], np.float32))
     assert not m.match_full_submap([1, 0, 0, 0], [1, 0, 0, 0], far, 0.1)["found"]
+
+
+# ---- real_time_correlative_scan_matcher_3d_test.cc:35-136 -------------------------------
+def _rt3d_fixture(oracle):
+    """The reference fixture: 7 points, grid cells of expected_pose * point set to
+    probability 1 (clamped to kMaxProbability), resolution 0.1; options 0.3 m / 1 deg /
+    1e-1 / 1."""
+    pts = np.array([[-3, 2, 0], [-4, 2, 0], [-5, 2, 0], [-6, 2, 0], [-6, 3, 1], [-6, 4, 2],
+                    [-7, 3, 1]], np.float32)
+    idx = [oracle.hybrid_get_cell_index(0.1, p + np.array([-1, 0, 0], np.float32)) for p in pts]
+    v = oracle.probability_to_value(1.0)
+    grid = oracle.HybridGrid(0.1, np.array(idx, np.int32), np.full(len(idx), v, np.uint16))
+    return pts, grid, np.array(idx, np.int32), np.full(len(idx), v, np.uint16)
+
+
+def _mat4(pose):
+    t, (w, x, y, z) = pose[:3], pose[3:]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    M = np.eye(4)
+    M[:3, :3] = R
+    M[:3, 3] = t
+    return M
+
+
+def rt3d_reference_initial_poses():
+    """PerfectEstimate, AlongX, AlongZ, AlongXYZ, RotationAroundX / Y / YZ.  Eigen::AngleAxisd
+    with the un-normalised axis (0, 1, 1) yields the quaternion (cos a/2, sin a/2 * axis)."""
+    a = 0.8 / 180.0 * math.pi
+    c, s = math.cos(a / 2), math.sin(a / 2)
+    return [[-1, 0, 0, 1, 0, 0, 0], [-0.8, 0, 0, 1, 0, 0, 0], [-1, 0, -0.2, 1, 0, 0, 0],
+            [-0.9, -0.2, 0.2, 1, 0, 0, 0], [-1, 0, 0, c, s, 0, 0], [-1, 0, 0, c, 0, s, 0],
+            [-1, 0, 0, c, 0, s, s]]
+
+
+def is_nearly(pose, expected, eps):
+    """transform::IsNearly = Eigen isApprox on the 4x4 matrices
+    (transform/rigid_transform_test_helpers.h:42-46)."""
+    A, B = _mat4(np.asarray(pose, float)), _mat4(np.asarray(expected, float))
+    return np.linalg.norm(A - B) <= eps * min(np.linalg.norm(A), np.linalg.norm(B))
+
+
+def test_rt3d_reference_test_cases(oracle):
+    pts, grid, _, _ = _rt3d_fixture(oracle)
+    for init in rt3d_reference_initial_poses():
+        r = oracle.rt3d_match(grid, pts, init, 0.3, math.radians(1.0), 1e-1, 1.0)
+        assert r["score"] > 0.0
+        assert is_nearly(r["pose"], [-1, 0, 0, 1, 0, 0, 0], 1e-3), (init, r)
+        # (2 * 3 + 1)^3 translations x (2 * 1 + 1)^3 rotations
+        assert r["candidates_scored"] == 343 * 27
