@@ -1,0 +1,163 @@
+"""bench.py --config 5: the ConstraintBuilder3D queue at BASELINE size — 500 submaps x
+100 nodes of a 64-ring x 1024-azimuth synthetic lidar (~64 k points per node), local
+searches with the pose_graph.lua 3D options (depth 8 / full-resolution depth 3, 5 m / 1 m /
+15 deg, min_score 0.55; min_rotational_score 0.45, see benchmarks/run_configs.py), sharded
+submap-major over the GPUs with one ncclAllGather of the results inside libcsm_b200.so
+(csm_cb_batch3d_run).  Strong scaling: the queue is fixed, the GPUs split it.
+
+Synthetic worlds are expensive to build on the host (16 s per submap, 2 s per node), so a
+handful of distinct buildings / node scans is generated and reused: every (submap, node)
+pair still gets its own initial pose, and all 500 device matchers are really built.
+"""
+import json
+import math
+import os
+import time
+
+import numpy as np
+
+from benchmarks import synthetic
+
+
+def run(args, D, workload, sample_clocks):
+    torch = D.torch
+    from cartographer_b200 import scan_matching as sm
+    rank, world = D.rank, D.world
+    ctx = D.make_context(sm)
+    n_sub = max(world, int(round(500 * args.scale)))
+    n_node = max(2, int(round(100 * args.scale)))
+    rings, az = 64, 1024
+    min_score = 0.55
+    o3 = sm.FastCorrelativeScanMatcherOptions3D(min_rotational_score=0.45)
+    distinct_sub = min(n_sub, 2)
+    distinct_node = min(n_node, 6)
+    t0 = time.perf_counter()
+    subs = []
+    for s in range(distinct_sub):
+        hi, lo, sub_hist, wd = synthetic.make_submap3d(40 + s, 40.0, rings, az, 20.0)
+        rng = np.random.RandomState(500 + s)
+        nodes = [synthetic.make_node3d(wd, rng, rings, az, 20.0, seed=7000 + 100 * s + k)
+                 for k in range(max(1, distinct_node // distinct_sub))]
+        subs.append(dict(hi=hi, lo=lo, hist=sub_hist, nodes=nodes))
+    gen_s = time.perf_counter() - t0
+    owner = (np.arange(n_sub) % world).astype(np.int32)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    matchers = [sm.FastCorrelativeScanMatcher3D(subs[s % distinct_sub]["hi"],
+                                                subs[s % distinct_sub]["lo"],
+                                                subs[s % distinct_sub]["hist"], o3,
+                                                device=D.local_rank)
+                if owner[s] == rank else None for s in range(n_sub)]
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    # node table: node k is scan (k % per-world count) of world (k % distinct_sub)
+    node_recs = []
+    for k in range(n_node):
+        sub = subs[k % distinct_sub]
+        node_recs.append((k % distinct_sub, sub["nodes"][(k // distinct_sub) % len(sub["nodes"])]))
+    nodes = [sm.TrajectoryNodeData3D(n["cloud"], n["low"], n["hist"]) for _, n in node_recs]
+    ident = [0, 0, 0, 1, 0, 0, 0]
+    rng = np.random.RandomState(9)
+    jobs = []
+    for si in range(n_sub):
+        for ni in range(n_node):
+            n = node_recs[ni][1]
+            init = n["pose"].copy()
+            init[:3] += rng.uniform(-1, 1, 3) * [2.0, 2.0, 0.3]
+            yaw = 2 * math.atan2(n["pose"][6], n["pose"][3]) + rng.uniform(-1, 1) * math.radians(8)
+            init[3:] = [math.cos(yaw / 2), 0, 0, math.sin(yaw / 2)]
+            jobs.append((si, ni, False, init, ident, min_score))
+    conc = 16
+    step_s, cand = [], 0
+    results = None
+    for it in range(args.warmup + args.steps):
+        D.barrier()
+        t0 = time.perf_counter()
+        results, st = sm.match_batch3d(matchers, nodes, jobs, max_concurrency=conc, ctx=ctx,
+                                       submap_owner=owner)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            step_s.append(dt)
+            cand += st["candidates_scored"]
+    elapsed = D.reduce([float(sum(step_s))], "MAX")[0]
+    cand_all = D.reduce([float(cand)], "SUM")[0]
+    found = sum(r is not None for r in results)
+    npts = int(np.mean([len(n["cloud"]) for _, n in node_recs]))
+    b3 = npts * 13 + 20
+    # parity + CPU baseline: a bounded sample of the queue through the oracle (rank 0)
+    cpu, parity_checked, parity_failed = None, 0, 0
+    if rank == 0 and not args.no_cpu_baseline:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import pyoracle as oracle
+        oracle.build()
+        threads = max(1, min(os.cpu_count() or 1, 64))
+        od = dict(branch_and_bound_depth=8, full_resolution_depth=3, min_rotational_score=0.45,
+                  min_low_resolution_score=0.55, linear_xy_search_window=5.0,
+                  linear_z_search_window=1.0, angular_search_window=math.radians(15.0))
+        oms = []
+        for s in subs:
+            ohi = oracle.HybridGrid(s["hi"].resolution, s["hi"].indices, s["hi"].values)
+            olo = oracle.HybridGrid(s["lo"].resolution, s["lo"].indices, s["lo"].values)
+            oms.append((oracle.FastCorrelativeScanMatcher3D(ohi, olo, s["hist"], od), ohi, olo))
+        sample = np.unique(np.linspace(0, len(jobs) - 1, min(len(jobs), threads)).astype(int))
+
+        def one(j):
+            si, ni, _, init, _, ms = jobs[j]
+            n = node_recs[ni][1]
+            node = dict(gravity_alignment=(1.0, 0.0, 0.0, 0.0),
+                        high_resolution_point_cloud=n["cloud"],
+                        low_resolution_point_cloud=n["low"],
+                        rotational_scan_matcher_histogram=n["hist"])
+            return oms[si % distinct_sub][0].match(init, ident, node, ms)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            outs = list(ex.map(one, sample))
+        secs = time.perf_counter() - t0
+        for j, w in zip(sample, outs):
+            g = results[j]
+            ok = (g is not None) == w["found"]
+            if ok and w["found"]:
+                ok = g["score"] == w["score"] and np.array_equal(g["pose_estimate"], w["pose"])
+            parity_checked += 1
+            parity_failed += 0 if ok else 1
+        cpu = {"value": sum(w["candidates_scored"] for w in outs) / secs, "unit": "candidates/s",
+               "cores": threads, "kind": "port", "constraints_per_sec": len(sample) / secs,
+               "sample": "%d of the queue's searches, one per host thread, %.1f s wall" %
+                         (len(sample), secs)}
+    clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if rank == 0:
+        mine = [j for j in jobs[:400] if owner[j[0]] == 0][:64]
+        dense = [m if m is not None else matchers[0] for m in matchers]
+        clocks = sample_clocks(D.local_rank,
+                               lambda it: sm.match_batch3d(dense, nodes, mine, max_concurrency=conc))
+    D.barrier()
+    if rank == 0:
+        steps = max(1, args.steps)
+        print(json.dumps({
+            "metric": "candidate_poses_scored_per_sec", "value": cand_all / elapsed,
+            "unit": "candidates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8/int32 + f32 gate", "data": "synthetic",
+            "config": {"workload": workload, "submaps": n_sub, "nodes": n_node, "jobs": len(jobs),
+                       "points_per_node": npts, "found": found, "min_score": min_score,
+                       "matches_in_flight_per_gpu": conc,
+                       "distinct_buildings": distinct_sub, "distinct_node_scans": len(set(
+                           (w, id(n)) for w, n in node_recs)),
+                       "note": "all %d device matchers are built (from %d distinct synthetic "
+                               "buildings); node clouds are uploaded once per call and shared by "
+                               "the submaps they are matched against" % (n_sub, distinct_sub),
+                       "collective": ("one ncclAllGather of the results inside libcsm_b200.so "
+                                      "(csm_cb_batch3d_run)" if world > 1 else "none (1 GPU)"),
+                       "host_generation_s": gen_s, "matcher_build_s_per_rank": build_s,
+                       "parallelism": "submap-major shards x%d" % world},
+            "constraints_per_sec": len(jobs) * steps / elapsed,
+            "algorithmic_GBps": cand_all * b3 / elapsed / 1e9,
+            "e2e": {"value": cand_all / elapsed, "unit": "candidates/s",
+                    "note": "node clouds are host buffers: their H2D is inside every step",
+                    "h2d_bytes_per_step": int(sum(12 * (len(n["cloud"]) + len(n["low"]))
+                                                  for _, n in node_recs)),
+                    "d2h_bytes_per_step": len(jobs) * 112},
+            "gpu_launches": int(sm.kernel_launch_count()), "clocks": clocks,
+            "parity_checked": parity_checked, "parity_failed": parity_failed,
+            "cpu_baseline": cpu, "roofline": None}))
+    ctx.close()

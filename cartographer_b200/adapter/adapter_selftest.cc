@@ -4,11 +4,20 @@
 // (no CPU fallback) — either way the binary proves the adapter builds and links.
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 
 #include "constraint_builder_b200.h"
 #include "scan_matchers_b200.h"
 
 using namespace cartographer;
+
+// RESULT lines are parsed by tests/test_gpu_adapter.py and compared with the oracle:
+// float scores as their bit patterns, doubles with 17 significant digits.
+static unsigned Bits(float f) {
+  unsigned u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
 
 // Host-only part (runs everywhere): the builder's gating and WhenDone cycle when no
 // pair survives the gates — nothing reaches the device — and the sampler's sequence
@@ -81,8 +90,47 @@ int main() {
   const bool found = matcher.Match(transform::Rigid2d({0.2, -0.15}, 0.05), cloud, 0.5f, &score, &pose);
   std::printf("adapter_selftest: found=%d score=%.4f pose=(%.3f, %.3f, %.4f)\n", found, score,
               pose.translation().x(), pose.translation().y(), pose.rotation().angle());
+  std::printf("RESULT fast2d %d %08x %.17g %.17g %.17g\n", found ? 1 : 0, Bits(score),
+              pose.translation().x(), pose.translation().y(), pose.rotation().angle());
   if (!found || std::fabs(pose.translation().x()) > 0.051 || std::fabs(pose.translation().y()) > 0.051)
     return 1;
+  {
+    float score_f = 0.f;
+    transform::Rigid2d pose_f;
+    const bool found_f = matcher.MatchFullSubmap(cloud, 0.5f, &score_f, &pose_f);
+    std::printf("RESULT fast2d_full %d %08x %.17g %.17g %.17g\n", found_f ? 1 : 0, Bits(score_f),
+                pose_f.translation().x(), pose_f.translation().y(), pose_f.rotation().angle());
+  }
+  // ---- RealTimeCorrelativeScanMatcher2D: Match and the public ScoreCandidates ----
+  {
+    mapping::scan_matching::proto::RealTimeCorrelativeScanMatcherOptions ro;
+    ro.set_linear_search_window(0.1);
+    ro.set_angular_search_window(0.1);
+    ro.set_translation_delta_cost_weight(0.1);
+    ro.set_rotation_delta_cost_weight(0.1);
+    mapping::scan_matching::RealTimeCorrelativeScanMatcher2D rt(ro);
+    transform::Rigid2d rt_pose;
+    const double rt_score = rt.Match(transform::Rigid2d({0.06, -0.04}, 0.02), cloud, grid, &rt_pose);
+    std::printf("RESULT rt2d %08x %.17g %.17g %.17g\n", Bits(static_cast<float>(rt_score)),
+                rt_pose.translation().x(), rt_pose.translation().y(), rt_pose.rotation().angle());
+    if (std::fabs(rt_pose.translation().x()) > 0.051 || std::fabs(rt_pose.translation().y()) > 0.051)
+      return 1;
+    // three candidates on one un-rotated discrete scan (cells of the wall points themselves)
+    const mapping::scan_matching::SearchParameters sp(2, 0, 0.01, 0.05);
+    mapping::scan_matching::DiscreteScan2D scan;
+    for (int i = 20; i < 100; i += 2) {
+      scan.push_back(mapping::scan_matching::Array2i{{i, 40}});
+      scan.push_back(mapping::scan_matching::Array2i{{30, i}});
+    }
+    std::vector<mapping::scan_matching::Candidate2D> cands;
+    cands.emplace_back(0, 0, 0, sp);
+    cands.emplace_back(0, 1, 0, sp);
+    cands.emplace_back(0, -2, 2, sp);
+    rt.ScoreCandidates(grid, {scan}, sp, &cands);
+    std::printf("RESULT rt2d_candidates %08x %08x %08x\n", Bits(cands[0].score),
+                Bits(cands[1].score), Bits(cands[2].score));
+    if (!(cands[0].score > cands[1].score && cands[1].score > cands[2].score)) return 1;
+  }
 
   // ---- 3D: the reference's 12-point axis cloud inserted at a known pose ----
   mapping::HybridGrid hybrid(0.05f);
@@ -116,10 +164,36 @@ int main() {
   std::printf("adapter_selftest: 3D score=%.4f t=(%.3f, %.3f, %.3f) low=%.3f\n", result->score,
               result->pose_estimate.translation().x(), result->pose_estimate.translation().y(),
               result->pose_estimate.translation().z(), result->low_resolution_score);
+  std::printf("RESULT fast3d %08x %.17g %.17g %.17g %.17g %.17g %.17g %.17g %08x %08x\n",
+              Bits(result->score), result->pose_estimate.translation().x(),
+              result->pose_estimate.translation().y(), result->pose_estimate.translation().z(),
+              result->pose_estimate.rotation().w(), result->pose_estimate.rotation().x(),
+              result->pose_estimate.rotation().y(), result->pose_estimate.rotation().z(),
+              Bits(result->rotational_score), Bits(result->low_resolution_score));
   if (std::fabs(result->pose_estimate.translation().x() - tx) > 0.051 ||
       std::fabs(result->pose_estimate.translation().y() - ty) > 0.051 ||
       std::fabs(result->pose_estimate.translation().z() - tz) > 0.051)
     return 1;
+  // ---- RealTimeCorrelativeScanMatcher3D on the same grid ----
+  {
+    mapping::scan_matching::proto::RealTimeCorrelativeScanMatcherOptions ro;
+    ro.set_linear_search_window(0.1);
+    ro.set_angular_search_window(0.01);
+    ro.set_translation_delta_cost_weight(0.1);
+    ro.set_rotation_delta_cost_weight(1.0);
+    mapping::scan_matching::RealTimeCorrelativeScanMatcher3D rt3(ro);
+    transform::Rigid3d pose3;
+    const float s3 = rt3.Match(transform::Rigid3d({{0.25, -0.1, 0.05}}, transform::Quaterniond{1., 0., 0., 0.}),
+                               cloud3, hybrid, &pose3);
+    std::printf("RESULT rt3d %08x %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", Bits(s3),
+                pose3.translation().x(), pose3.translation().y(), pose3.translation().z(),
+                pose3.rotation().w(), pose3.rotation().x(), pose3.rotation().y(),
+                pose3.rotation().z());
+    if (std::fabs(pose3.translation().x() - tx) > 0.051 ||
+        std::fabs(pose3.translation().y() - ty) > 0.051 ||
+        std::fabs(pose3.translation().z() - tz) > 0.051)
+      return 1;
+  }
 
   // ---- ConstraintBuilder2D / 3D: the reference's call cycle (constraint_builder_2d_test.cc:58-112) ----
   {
@@ -151,6 +225,10 @@ int main() {
                 calls, got.size(), builder.GetNumFinishedNodes(),
                 static_cast<long long>(builder.last_stats().candidates_scored));
     if (calls != 1 || got.size() != 2 || builder.GetNumFinishedNodes() != 1) return 1;
+    for (const auto& c : got)
+      std::printf("RESULT cb2d %d %.17g %.17g %.17g\n", c.node_id.node_index,
+                  c.pose.zbar_ij.translation().x(), c.pose.zbar_ij.translation().y(),
+                  2. * std::atan2(c.pose.zbar_ij.rotation().z(), c.pose.zbar_ij.rotation().w()));
     for (const auto& c : got) {
       // zbar_ij = submap_pose^-1 * pose_estimate, pose_estimate ~ identity
       const transform::Rigid2d want = submap_pose.inverse();

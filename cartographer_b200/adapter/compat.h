@@ -170,6 +170,42 @@ class TSDF2D : public Grid2D {
 };
 
 namespace scan_matching {
+// internal/2d/scan_matching/correlative_scan_matcher_2d.h:32-103 — the types in the
+// signature of the public RealTimeCorrelativeScanMatcher2D::ScoreCandidates.
+struct Array2i { int v[2]; int x() const { return v[0]; } int y() const { return v[1]; } };
+typedef std::vector<Array2i> DiscreteScan2D;
+struct SearchParameters {
+  struct LinearBounds { int min_x, max_x, min_y, max_y; };
+  SearchParameters(int num_linear_perturbations, int num_angular_perturbations,
+                   double angular_perturbation_step_size, double resolution)
+      : num_angular_perturbations(num_angular_perturbations),
+        angular_perturbation_step_size(angular_perturbation_step_size), resolution(resolution),
+        num_scans(2 * num_angular_perturbations + 1),
+        linear_bounds(num_scans, LinearBounds{-num_linear_perturbations, num_linear_perturbations,
+                                              -num_linear_perturbations, num_linear_perturbations}) {}
+  int num_angular_perturbations;
+  double angular_perturbation_step_size;
+  double resolution;
+  int num_scans;
+  std::vector<LinearBounds> linear_bounds;
+};
+struct Candidate2D {   // :74-103
+  Candidate2D(int init_scan_index, int init_x_index_offset, int init_y_index_offset,
+              const SearchParameters& sp)
+      : scan_index(init_scan_index), x_index_offset(init_x_index_offset),
+        y_index_offset(init_y_index_offset), x(-y_index_offset * sp.resolution),
+        y(-x_index_offset * sp.resolution),
+        orientation((scan_index - sp.num_angular_perturbations) *
+                    sp.angular_perturbation_step_size) {}
+  int scan_index = 0, x_index_offset = 0, y_index_offset = 0;
+  double x = 0., y = 0., orientation = 0.;
+  float score = 0.f;
+  bool operator<(const Candidate2D& other) const { return score < other.score; }
+  bool operator>(const Candidate2D& other) const { return score > other.score; }
+};
+}  // namespace scan_matching
+
+namespace scan_matching {
 namespace proto {
 // proto/scan_matching/fast_correlative_scan_matcher_options_2d.proto
 class FastCorrelativeScanMatcherOptions2D {

@@ -51,9 +51,17 @@ class ConstraintBuilder2D {
   using Refiner = std::function<transform::Rigid2d(
       const transform::Rigid2d&, const sensor::PointCloud&, const Grid2D&)>;
 
+  // `multi_gpu` (optional, csm_ctx_create): one process per GPU; every process must feed
+  // the SAME sequence of MaybeAdd*Constraint / WhenDone calls.  The queue is then sharded
+  // submap-major (a submap's stack only ever exists on its owner) and every process gets
+  // the complete Result after one ncclAllGather inside csm_cb_batch2d_run.
   ConstraintBuilder2D(const proto::ConstraintBuilderOptions& options,
-                      common::ThreadPoolInterface* thread_pool, int device = 0)
-      : options_(options), thread_pool_(thread_pool), device_(device) {}
+                      common::ThreadPoolInterface* thread_pool, int device = 0,
+                      csm_ctx* multi_gpu = nullptr)
+      : options_(options), thread_pool_(thread_pool), device_(device), ctx_(multi_gpu) {
+    if (ctx_ != nullptr)
+      scan_matching::b200_internal::Check(csm_ctx_info(ctx_, &world_, &rank_, nullptr));
+  }
 
   ~ConstraintBuilder2D() {  // constraint_builder_2d.cc:68-75
     std::lock_guard<std::mutex> lock(mutex_);
@@ -175,6 +183,7 @@ class ConstraintBuilder2D {
       const auto& fo = options_.fast_correlative_scan_matcher_options();
       // distinct stacks / clouds of this queue
       std::vector<const csm_stack2d*> stacks;
+      std::vector<int32_t> owners;
       std::map<SubmapId, int> stack_index;
       std::vector<csm_cloud*> clouds;
       std::map<const TrajectoryNodeData*, int> cloud_index;
@@ -184,7 +193,9 @@ class ConstraintBuilder2D {
         auto si = stack_index.find(p.submap_id);
         if (si == stack_index.end()) {
           si = stack_index.emplace(p.submap_id, static_cast<int>(stacks.size())).first;
-          stacks.push_back(StackFor(p.submap_id, p.submap->grid()));
+          const int owner = OwnerOf(p.submap_id);
+          owners.push_back(owner);
+          stacks.push_back(owner == rank_ ? StackFor(p.submap_id, p.submap->grid()) : nullptr);
         }
         auto ci = cloud_index.find(p.constant_data);
         if (ci == cloud_index.end()) {
@@ -208,11 +219,29 @@ class ConstraintBuilder2D {
       }
       std::vector<csm_result2d> results(jobs.size());
       if (!jobs.empty()) {
-        scan_matching::b200_internal::Check(csm_match2d_batch(
-            stacks.data(), static_cast<int32_t>(stacks.size()),
-            const_cast<const csm_cloud* const*>(clouds.data()), static_cast<int32_t>(clouds.size()),
-            jobs.data(), static_cast<int32_t>(jobs.size()), fo.linear_search_window(),
-            fo.angular_search_window(), results.data(), &last_stats_));
+        const auto run = [&](const csm_job2d* js, int32_t n, csm_result2d* rs) {
+          const csm_cloud* const* cl = const_cast<const csm_cloud* const*>(clouds.data());
+          if (ctx_ != nullptr)
+            return csm_cb_batch2d_run(ctx_, stacks.data(), static_cast<int32_t>(stacks.size()), cl,
+                                      static_cast<int32_t>(clouds.size()), js, n, owners.data(),
+                                      fo.linear_search_window(), fo.angular_search_window(), rs,
+                                      &last_stats_);
+          return csm_match2d_batch(stacks.data(), static_cast<int32_t>(stacks.size()), cl,
+                                   static_cast<int32_t>(clouds.size()), js, n,
+                                   fo.linear_search_window(), fo.angular_search_window(), rs,
+                                   &last_stats_);
+        };
+        if (!scan_matching::b200_internal::Check(
+                run(jobs.data(), static_cast<int32_t>(jobs.size()), results.data()))) {
+          // An engine capacity limit was hit somewhere in the batch: run the pairs one by
+          // one; a pair that still exceeds it yields no constraint (the reference would
+          // have produced a match or none — it never aborts here).
+          for (size_t i = 0; i < jobs.size(); ++i) {
+            results[i] = csm_result2d{};
+            if (!scan_matching::b200_internal::Check(run(&jobs[i], 1, &results[i])))
+              results[i].found = 0;
+          }
+        }
       }
       for (csm_cloud* c : clouds) csm_cloud_destroy(c);
       for (size_t i = 0; i < pending_.size(); ++i) {
@@ -242,9 +271,18 @@ class ConstraintBuilder2D {
     (*callback)(result);
   }
 
+  // submap-major ownership, stable across drains
+  int OwnerOf(const SubmapId& id) const {
+    return world_ <= 1 ? 0 : static_cast<int>((static_cast<unsigned>(id.trajectory_id) * 7919u +
+                                               static_cast<unsigned>(id.submap_index)) %
+                                              static_cast<unsigned>(world_));
+  }
+
   const proto::ConstraintBuilderOptions options_;
   common::ThreadPoolInterface* thread_pool_;
   const int device_;
+  csm_ctx* const ctx_;
+  int32_t world_ = 1, rank_ = 0;
   std::mutex mutex_;
   std::unique_ptr<std::function<void(const Result&)>> when_done_;
   int num_started_nodes_ = 0;

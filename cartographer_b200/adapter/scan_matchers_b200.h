@@ -24,6 +24,8 @@
 
 #if defined(__has_include) && __has_include("cartographer/mapping/2d/grid_2d.h")
 #include "cartographer/mapping/2d/grid_2d.h"
+#include "cartographer/mapping/internal/2d/scan_matching/correlative_scan_matcher_2d.h"
+#include "cartographer/mapping/internal/2d/tsdf_2d.h"
 #include "cartographer/mapping/proto/scan_matching/fast_correlative_scan_matcher_options_2d.pb.h"
 #include "cartographer/mapping/proto/scan_matching/real_time_correlative_scan_matcher_options.pb.h"
 #include "cartographer/sensor/point_cloud.h"
@@ -38,11 +40,16 @@ namespace mapping {
 namespace scan_matching {
 
 namespace b200_internal {
-inline void Check(csm_status s) {
-  if (s != CSM_OK) {
-    std::fprintf(stderr, "libcsm_b200: %s\n", csm_last_error_string());
-    std::abort();  // glog CHECK semantics of the reference
-  }
+// Programmer errors and CUDA failures keep the reference's CHECK semantics (abort with the
+// ABI's message).  CSM_E_CAPACITY — an engine limit the reference does not have (more than
+// 2^21 exactly tied optima, a scan point more than 30 000 cells from the grid origin) — is
+// logged and reported to the caller, which treats the search as "no match": one
+// pathological (submap, node) pair must not take the SLAM process down.
+inline bool Check(csm_status s) {
+  if (s == CSM_OK) return true;
+  std::fprintf(stderr, "libcsm_b200: %s\n", csm_last_error_string());
+  if (s == CSM_E_CAPACITY) return false;
+  std::abort();  // glog CHECK semantics of the reference
 }
 inline std::vector<float> Flatten(const sensor::PointCloud& point_cloud) {
   std::vector<float> xyz;
@@ -99,10 +106,12 @@ class FastCorrelativeScanMatcher2D {
     int32_t found = 0;
     float s = 0.f;
     double pose[3] = {0., 0., 0.};
-    b200_internal::Check(csm_match2d(stack_, xyz.data(), static_cast<int32_t>(point_cloud.size()),
-                                     init, full, options_.linear_search_window(),
-                                     options_.angular_search_window(), min_score, &found, &s,
-                                     pose, nullptr));
+    if (!b200_internal::Check(csm_match2d(stack_, xyz.data(),
+                                          static_cast<int32_t>(point_cloud.size()), init, full,
+                                          options_.linear_search_window(),
+                                          options_.angular_search_window(), min_score, &found,
+                                          &s, pose, nullptr)))
+      return false;
     if (!found) return false;
     *score = s;
     *pose_estimate = transform::Rigid2d({pose[0], pose[1]}, pose[2]);
@@ -129,28 +138,86 @@ class RealTimeCorrelativeScanMatcher2D {
                             initial_pose_estimate.translation().y(),
                             initial_pose_estimate.rotation().angle()};
     double score = 0., pose[3] = {0., 0., 0.};
-#ifndef CSM_ADAPTER_REAL_CARTOGRAPHER
+    bool ok;
     if (grid.GetGridType() == GridType::TSDF) {  // real_time…2d.cc:160-166
       const TSDF2D& tsdf = static_cast<const TSDF2D&>(grid);
-      b200_internal::Check(csm_rt_match2d_tsdf(
-          tsdf.correspondence_cost_cells().data(), tsdf.weight_cells().data(),
-          l.cell_limits().num_x_cells, l.cell_limits().num_y_cells, l.resolution(), l.max().x(),
-          l.max().y(), tsdf.truncation_distance(), tsdf.max_weight(), xyz.data(),
+#ifdef CSM_ADAPTER_REAL_CARTOGRAPHER
+      // TSDF2D keeps its weight cells and converter private (internal/2d/tsdf_2d.h:57-60);
+      // the proto form carries exactly what the kernel needs (grid_2d.proto:23-42).
+      const proto::Grid2D p = tsdf.ToProto();
+      std::vector<uint16_t> tsd(p.cells().begin(), p.cells().end());
+      std::vector<uint16_t> weights(p.tsdf_2d().weight_cells().begin(),
+                                    p.tsdf_2d().weight_cells().end());
+      const float truncation = p.tsdf_2d().truncation_distance();
+      const float max_weight = p.tsdf_2d().max_weight();
+      const uint16_t* tsd_cells = tsd.data();
+      const uint16_t* weight_cells = weights.data();
+#else
+      const float truncation = tsdf.truncation_distance(), max_weight = tsdf.max_weight();
+      const uint16_t* tsd_cells = tsdf.correspondence_cost_cells().data();
+      const uint16_t* weight_cells = tsdf.weight_cells().data();
+#endif
+      ok = b200_internal::Check(csm_rt_match2d_tsdf(
+          tsd_cells, weight_cells, l.cell_limits().num_x_cells, l.cell_limits().num_y_cells,
+          l.resolution(), l.max().x(), l.max().y(), truncation, max_weight, xyz.data(),
           static_cast<int32_t>(point_cloud.size()), init, options_.linear_search_window(),
           options_.angular_search_window(), options_.translation_delta_cost_weight(),
           options_.rotation_delta_cost_weight(), device_, &score, pose, nullptr));
-      *pose_estimate = transform::Rigid2d({pose[0], pose[1]}, pose[2]);
-      return score;
+    } else {
+      ok = b200_internal::Check(csm_rt_match2d(
+          grid.correspondence_cost_cells().data(), l.cell_limits().num_x_cells,
+          l.cell_limits().num_y_cells, l.resolution(), l.max().x(), l.max().y(), xyz.data(),
+          static_cast<int32_t>(point_cloud.size()), init, options_.linear_search_window(),
+          options_.angular_search_window(), options_.translation_delta_cost_weight(),
+          options_.rotation_delta_cost_weight(), device_, &score, pose, nullptr));
     }
-#endif
-    b200_internal::Check(csm_rt_match2d(
-        grid.correspondence_cost_cells().data(), l.cell_limits().num_x_cells,
-        l.cell_limits().num_y_cells, l.resolution(), l.max().x(), l.max().y(), xyz.data(),
-        static_cast<int32_t>(point_cloud.size()), init, options_.linear_search_window(),
-        options_.angular_search_window(), options_.translation_delta_cost_weight(),
-        options_.rotation_delta_cost_weight(), device_, &score, pose, nullptr));
+    if (!ok) {  // engine capacity: keep the initial estimate (a zero-offset candidate)
+      *pose_estimate = initial_pose_estimate;
+      return 0.;
+    }
     *pose_estimate = transform::Rigid2d({pose[0], pose[1]}, pose[2]);
     return score;
+  }
+
+  // Public in the reference (real_time_correlative_scan_matcher_2d.h:75, .cc:151-176):
+  // computes the score of every candidate of `candidates` in place.
+  void ScoreCandidates(const Grid2D& grid, const std::vector<DiscreteScan2D>& discrete_scans,
+                       const SearchParameters& search_parameters,
+                       std::vector<Candidate2D>* const candidates) const {
+    if (candidates == nullptr || candidates->empty()) return;
+    if (grid.GetGridType() != GridType::PROBABILITY_GRID) {
+      std::fprintf(stderr, "ScoreCandidates (b200): only ProbabilityGrid is supported\n");
+      std::abort();
+    }
+    const MapLimits& l = grid.limits();
+    const int32_t num_scans = static_cast<int32_t>(discrete_scans.size());
+    const int32_t n = num_scans ? static_cast<int32_t>(discrete_scans[0].size()) : 0;
+    std::vector<int32_t> ds;
+    ds.reserve(2 * static_cast<size_t>(num_scans) * n);
+    for (const DiscreteScan2D& scan : discrete_scans) {
+      if (static_cast<int32_t>(scan.size()) != n) std::abort();  // one cloud, S rotations
+      for (const auto& xy : scan) {
+        ds.push_back(xy.x());
+        ds.push_back(xy.y());
+      }
+    }
+    std::vector<int32_t> cand;
+    cand.reserve(3 * candidates->size());
+    for (const Candidate2D& c : *candidates) {
+      cand.push_back(c.scan_index);
+      cand.push_back(c.x_index_offset);
+      cand.push_back(c.y_index_offset);
+    }
+    std::vector<float> scores(candidates->size());
+    if (!b200_internal::Check(csm_rt_score_candidates2d(
+            grid.correspondence_cost_cells().data(), l.cell_limits().num_x_cells,
+            l.cell_limits().num_y_cells, l.resolution(), l.max().x(), l.max().y(), ds.data(),
+            num_scans, n, search_parameters.num_angular_perturbations,
+            search_parameters.angular_perturbation_step_size, cand.data(),
+            static_cast<int32_t>(candidates->size()), options_.translation_delta_cost_weight(),
+            options_.rotation_delta_cost_weight(), device_, scores.data())))
+      return;
+    for (size_t i = 0; i < scores.size(); ++i) (*candidates)[i].score = scores[i];
   }
 
  private:
@@ -248,7 +315,8 @@ class FastCorrelativeScanMatcher3D {
     Pose7(node_pose, np);
     Pose7(submap_pose, sp);
     csm_result3d r;
-    b200_internal::Check(csm_match3d(matcher_, &node, np, sp, full, min_score, &r, nullptr));
+    if (!b200_internal::Check(csm_match3d(matcher_, &node, np, sp, full, min_score, &r, nullptr)))
+      return nullptr;
     if (!r.found) return nullptr;  // fast_correlative_scan_matcher_3d.cc:197
     return std::unique_ptr<Result>(new Result{
         r.score,
@@ -258,6 +326,79 @@ class FastCorrelativeScanMatcher3D {
         r.rotational_score, r.low_resolution_score});
   }
   csm_matcher3d* matcher_ = nullptr;
+};
+
+// real_time_correlative_scan_matcher_3d.h:41-67.  The reference takes the HybridGrid per
+// call; flattening + uploading a whole submap grid for every scan would dominate, so the
+// grid lives in a DeviceHybridGrid that the caller refreshes when the submap changed
+// (LocalTrajectoryBuilder3D matches against the active submap's high-resolution grid,
+// internal/3d/local_trajectory_builder_3d.cc:139-148).
+class DeviceHybridGrid {
+ public:
+  explicit DeviceHybridGrid(const HybridGrid& grid, int device = 0) {
+    std::vector<int32_t> idx;
+    std::vector<uint16_t> val;
+    for (const auto& v : grid.voxels()) {
+      idx.push_back(v.x);
+      idx.push_back(v.y);
+      idx.push_back(v.z);
+      val.push_back(v.value);
+    }
+    b200_internal::Check(csm_grid3d_create(idx.data(), val.data(),
+                                           static_cast<int64_t>(val.size()), grid.resolution(),
+                                           device, &grid_));
+  }
+  ~DeviceHybridGrid() { csm_grid3d_destroy(grid_); }
+  DeviceHybridGrid(const DeviceHybridGrid&) = delete;
+  DeviceHybridGrid& operator=(const DeviceHybridGrid&) = delete;
+  const csm_grid3d* handle() const { return grid_; }
+
+ private:
+  csm_grid3d* grid_ = nullptr;
+};
+
+class RealTimeCorrelativeScanMatcher3D {
+ public:
+  explicit RealTimeCorrelativeScanMatcher3D(
+      const proto::RealTimeCorrelativeScanMatcherOptions& options)
+      : options_(options) {}
+  RealTimeCorrelativeScanMatcher3D(const RealTimeCorrelativeScanMatcher3D&) = delete;
+  RealTimeCorrelativeScanMatcher3D& operator=(const RealTimeCorrelativeScanMatcher3D&) = delete;
+
+  // The reference signature (grid per call: one upload per call).
+  float Match(const transform::Rigid3d& initial_pose_estimate,
+              const sensor::PointCloud& point_cloud, const HybridGrid& hybrid_grid,
+              transform::Rigid3d* pose_estimate) const {
+    const DeviceHybridGrid device_grid(hybrid_grid);
+    return Match(initial_pose_estimate, point_cloud, device_grid, pose_estimate);
+  }
+  float Match(const transform::Rigid3d& initial_pose_estimate,
+              const sensor::PointCloud& point_cloud, const DeviceHybridGrid& hybrid_grid,
+              transform::Rigid3d* pose_estimate) const {
+    if (pose_estimate == nullptr) std::abort();  // CHECK(:38)
+    const std::vector<float> xyz = b200_internal::Flatten(point_cloud);
+    const double init[7] = {initial_pose_estimate.translation().x(),
+                            initial_pose_estimate.translation().y(),
+                            initial_pose_estimate.translation().z(),
+                            initial_pose_estimate.rotation().w(),
+                            initial_pose_estimate.rotation().x(),
+                            initial_pose_estimate.rotation().y(),
+                            initial_pose_estimate.rotation().z()};
+    float score = -1.f;
+    double pose[7] = {0., 0., 0., 1., 0., 0., 0.};
+    if (!b200_internal::Check(csm_rt_match3d(
+            hybrid_grid.handle(), xyz.data(), static_cast<int32_t>(point_cloud.size()), init,
+            options_.linear_search_window(), options_.angular_search_window(),
+            options_.translation_delta_cost_weight(), options_.rotation_delta_cost_weight(),
+            &score, pose, nullptr)))
+      return -1.f;
+    *pose_estimate = transform::Rigid3d(
+        {{pose[0], pose[1], pose[2]}}, transform::Quaterniond{pose[3], pose[4], pose[5], pose[6]});
+    return score;
+  }
+
+ private:
+  const proto::RealTimeCorrelativeScanMatcherOptions options_;
 };
 #endif  // !CSM_ADAPTER_REAL_CARTOGRAPHER
 

@@ -55,7 +55,7 @@ static csm_status NewCtx(int device, std::unique_ptr<Ctx>* out) {
 static std::mutex g_lane_mu;
 static std::map<int, std::vector<std::unique_ptr<Ctx>>> g_lanes;
 static std::atomic<unsigned> g_lane_rr{0};
-constexpr size_t kMaxLanes = 8;
+constexpr size_t kMaxLanes = 16;
 
 csm_status AcquireLane(int device, LaneGuard* out) {
   {

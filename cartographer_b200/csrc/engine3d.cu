@@ -51,9 +51,10 @@ struct Job3 {
   const Low3Dev* low;
   const float* hi_xyz;
   const float* lo_xyz;
-  const Scan3* scans;
+  const Scan3* scans;  // the scans that passed the rotational filter (written on the device)
+  const int* ctl;      // control block (kC3*): [kC3Scans] = number of such scans
   short4* cells;       // [scan][point]
-  int n_hi, n_lo, num_scans;
+  int n_hi, n_lo, max_scans;   // max_scans = number of angles (upper bound of the scan count)
   int wxy, wz;         // linear window sizes in voxels
   int nxc, nzc;        // lowest-resolution candidates per axis (x == y)
   float min_score;
@@ -200,11 +201,81 @@ __global__ void k3_rotational(const float* __restrict__ submap_hist,
   scores[a] = normalization < 1e-3f ? 1.f : __fdiv_rn(dot, normalization);
 }
 
+__global__ void k3_fill(float* __restrict__ p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- device-resident control of a match ---------------------------------------------
+// Frontier sizes, the scan count after the rotational filter and the bound never visit the
+// host between kernels: a match is one stream of launches and one synchronisation.
+enum : int {
+  kC3Leaf = 16,      // leaves recorded
+  kC3Best = 17,      // optimal leaves after compaction
+  kC3Scans = 18,     // scans that passed the rotational filter
+  kC3Overflow = 20,
+  kC3Start = 25,     // chunk of the current level: first node / count
+  kC3Count = 26,
+  kC3Bound = 28,     // the bound (order-preserving uint)
+  kC3Ints = 32
+};
+
+// GenerateDiscreteScans' filter (:273-281): keeps the angles whose rotational score is not
+// below min_rotational_score (float < double), in angle order.  One CTA, ordered compaction.
+__global__ void __launch_bounds__(1024)
+k3_select_scans(const Scan3* __restrict__ all, const float* __restrict__ rot_scores,
+                int num_angles, double min_rotational_score, Scan3* __restrict__ out,
+                int* __restrict__ sel, int* __restrict__ ctl, unsigned lb0) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int a0 = 0; a0 < num_angles; a0 += 1024) {
+    const int a = a0 + threadIdx.x;
+    const float rs = a < num_angles ? rot_scores[a] : 0.f;
+    const bool keep = a < num_angles && !(static_cast<double>(rs) < min_rotational_score);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_warp[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (keep) {
+      const int k = s_base + before + __popc(m & ((1u << lane) - 1));
+      Scan3 sc = all[a];
+      sc.rot_score = rs;
+      out[k] = sc;
+      sel[k] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    ctl[kC3Scans] = s_base;
+    reinterpret_cast<unsigned*>(ctl)[kC3Bound] = lb0;
+  }
+}
+
+__global__ void k3_level_begin(int* __restrict__ ctl, int h, int chunk_cap) {
+  if (threadIdx.x != 0) return;
+  const int have = ctl[h];
+  const int n = min(have, chunk_cap);
+  ctl[h] = have - n;          // the chunk is taken from the END of the queue
+  ctl[kC3Start] = have - n;
+  ctl[kC3Count] = n;
+}
+
 // ---------------------------------------------------------------------------
 // K2-3D: DiscretizeScan (full-resolution cell indices; :200-218)
 // ---------------------------------------------------------------------------
 __global__ void k3_discretize(Job3 jb) {
   const int s = blockIdx.y;
+  if (s >= jb.ctl[kC3Scans]) return;
   const Scan3 sc = jb.scans[s];
   const F3 qv{sc.qx, sc.qy, sc.qz}, t{sc.tx, sc.ty, sc.tz};
   const float res = jb.stack->resolution;
@@ -341,6 +412,7 @@ __global__ void __launch_bounds__(kT3) k3_score_top(Job3 jb, int* __restrict__ t
   const int per_scan = jb.nxc * jb.nxc * jb.nzc;
   const int c = blockIdx.x;
   const int scan = c / per_scan;
+  if (scan >= jb.ctl[kC3Scans]) return;
   int r = c - scan * per_scan;
   const int kz = r / (jb.nxc * jb.nxc);
   r -= kz * jb.nxc * jb.nxc;
@@ -361,6 +433,7 @@ k3_dive(Job3 jb, const int* __restrict__ top_sum, unsigned* __restrict__ lb,
   __shared__ float s_buf[kT3];
   __shared__ int s_pick[4];
   const int scan = blockIdx.x;
+  if (scan >= jb.ctl[kC3Scans]) return;
   const int per_scan = jb.nxc * jb.nxc * jb.nzc;
   if (threadIdx.x == 0) {
     int best = -1, bi = 0;
@@ -415,14 +488,14 @@ k3_dive(Job3 jb, const int* __restrict__ top_sum, unsigned* __restrict__ lb,
   if (threadIdx.x == 0) atomicAdd(&counters[0], scored);
 }
 
-__global__ void k3_filter_top(Job3 jb, const int* __restrict__ top_sum, int total,
+__global__ void k3_filter_top(Job3 jb, const int* __restrict__ top_sum,
                               const unsigned* __restrict__ lb, Node3* __restrict__ queue,
                               int* __restrict__ qcount) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= total) return;
+  const int per_scan = jb.nxc * jb.nxc * jb.nzc;
+  if (c >= jb.ctl[kC3Scans] * per_scan) return;
   const float score = ToScore3(top_sum[c], jb.n_hi);
   if (!(score > jb.min_score && score >= OrderedToFloat3(*lb))) return;
-  const int per_scan = jb.nxc * jb.nxc * jb.nzc;
   const int scan = c / per_scan;
   int r = c - scan * per_scan;
   const int kz = r / (jb.nxc * jb.nxc);
@@ -434,72 +507,102 @@ __global__ void k3_filter_top(Job3 jb, const int* __restrict__ top_sum, int tota
                      -jb.wz + (kz << hmax), score};
 }
 
-// Branch step: one CTA per parent node of level h (:403-437).
+// Branch step (:403-437): CTAs walk the parents of the current chunk (device-side start /
+// count, grid-stride), one parent at a time.
 __global__ void __launch_bounds__(kT3)
-k3_expand(Job3 jb, const Node3* __restrict__ parents, int count, int h,
-          unsigned* __restrict__ lb, Node3* __restrict__ next, int* __restrict__ next_count,
-          int next_cap, Leaf3* __restrict__ leaves, int* __restrict__ leaf_count, int leaf_cap,
-          int* __restrict__ overflow, unsigned long long* __restrict__ counters) {
+k3_expand(Job3 jb, const Node3* __restrict__ queue, int* __restrict__ ctl, int h,
+          Node3* __restrict__ next, int* __restrict__ next_count,
+          int next_cap, Leaf3* __restrict__ leaves, int leaf_cap,
+          unsigned long long* __restrict__ counters) {
   __shared__ int s_red[kT3 / 32 * 8];
   __shared__ float s_buf[kT3];
   __shared__ int s_sums[8];
   __shared__ float s_bound;
   __shared__ int s_go;
-  const Node3 nd = parents[blockIdx.x];
-  // the bound moves while the kernel runs: one thread samples it, all threads agree
-  if (threadIdx.x == 0) s_bound = OrderedToFloat3(*lb);
-  __syncthreads();
-  if (!(nd.score >= s_bound)) return;
-  const int half = 1 << (h - 1);
-  const unsigned mask = ChildMask3(jb, nd.ox, nd.oy, nd.oz, half);
-  int sums[8];
-  ScoreOct(jb, nd.scan, h - 1, nd.ox, nd.oy, nd.oz, half, mask, sums, s_red);
-  if (threadIdx.x == 0) {
-    for (int t = 0; t < 8; ++t) s_sums[t] = sums[t];
-    atomicAdd(&counters[0], (unsigned long long)__popc(mask));
-    atomicAdd(&counters[1], 1ull);
-  }
-  __syncthreads();
-  if (h - 1 == 0) {
-    for (int t = 0; t < 8; ++t) {
-      if (!((mask >> t) & 1u)) continue;
-      const float sc = ToScore3(s_sums[t], jb.n_hi);
-      // leaf candidates that cannot beat (or tie) the bound need no gate evaluation
-      __syncthreads();
-      if (threadIdx.x == 0) s_go = (sc > jb.min_score && sc >= OrderedToFloat3(*lb)) ? 1 : 0;
-      __syncthreads();
-      if (!s_go) continue;
-      const int ox = nd.ox + (t & 1) * half, oy = nd.oy + ((t >> 1) & 1) * half,
-                oz = nd.oz + ((t >> 2) & 1) * half;
-      const float low = LowResScore(jb, nd.scan, ox, oy, oz, s_buf);
-      if (threadIdx.x == 0) {
-        atomicAdd(&counters[2], 1ull);
-        if (static_cast<double>(low) >= jb.min_low_d) {
-          const unsigned o = FloatToOrdered3(sc);
-          const unsigned old = atomicMax(lb, o);
-          if (o >= old) {
-            const int idx = atomicAdd(leaf_count, 1);
-            if (idx < leaf_cap) leaves[idx] = Leaf3{nd.scan, ox, oy, oz, sc, low};
-            else *overflow = 1;
+  unsigned* lb = reinterpret_cast<unsigned*>(ctl) + kC3Bound;
+  int* leaf_count = ctl + kC3Leaf;
+  int* overflow = ctl + kC3Overflow;
+  const int count = ctl[kC3Count];
+  const Node3* __restrict__ parents = queue + ctl[kC3Start];
+  for (int pi = blockIdx.x; pi < count; pi += gridDim.x) {
+    const Node3 nd = parents[pi];
+    // the bound moves while the kernel runs: one thread samples it, all threads agree
+    __syncthreads();
+    if (threadIdx.x == 0) s_bound = OrderedToFloat3(*lb);
+    __syncthreads();
+    if (!(nd.score >= s_bound)) continue;
+    const int half = 1 << (h - 1);
+    const unsigned mask = ChildMask3(jb, nd.ox, nd.oy, nd.oz, half);
+    int sums[8];
+    ScoreOct(jb, nd.scan, h - 1, nd.ox, nd.oy, nd.oz, half, mask, sums, s_red);
+    if (threadIdx.x == 0) {
+      for (int t = 0; t < 8; ++t) s_sums[t] = sums[t];
+      atomicAdd(&counters[0], (unsigned long long)__popc(mask));
+      atomicAdd(&counters[1], 1ull);
+    }
+    __syncthreads();
+    if (h - 1 == 0) {
+      for (int t = 0; t < 8; ++t) {
+        if (!((mask >> t) & 1u)) continue;
+        const float sc = ToScore3(s_sums[t], jb.n_hi);
+        // leaf candidates that cannot beat (or tie) the bound need no gate evaluation
+        __syncthreads();
+        if (threadIdx.x == 0) s_go = (sc > jb.min_score && sc >= OrderedToFloat3(*lb)) ? 1 : 0;
+        __syncthreads();
+        if (!s_go) continue;
+        const int ox = nd.ox + (t & 1) * half, oy = nd.oy + ((t >> 1) & 1) * half,
+                  oz = nd.oz + ((t >> 2) & 1) * half;
+        const float low = LowResScore(jb, nd.scan, ox, oy, oz, s_buf);
+        if (threadIdx.x == 0) {
+          atomicAdd(&counters[2], 1ull);
+          if (static_cast<double>(low) >= jb.min_low_d) {
+            const unsigned o = FloatToOrdered3(sc);
+            const unsigned old = atomicMax(lb, o);
+            if (o >= old) {
+              const int idx = atomicAdd(leaf_count, 1);
+              if (idx < leaf_cap) leaves[idx] = Leaf3{nd.scan, ox, oy, oz, sc, low};
+              else *overflow = 1;
+            }
           }
         }
+        __syncthreads();
       }
-      __syncthreads();
-    }
-  } else if (threadIdx.x == 0) {
-    const float bound = OrderedToFloat3(*lb);
-    for (int t = 0; t < 8; ++t) {
-      if (!((mask >> t) & 1u)) continue;
-      const float sc = ToScore3(s_sums[t], jb.n_hi);
-      if (sc > jb.min_score && sc >= bound) {
-        const int idx = atomicAdd(next_count, 1);
-        if (idx < next_cap)
-          next[idx] = Node3{nd.scan, nd.ox + (t & 1) * half, nd.oy + ((t >> 1) & 1) * half,
-                            nd.oz + ((t >> 2) & 1) * half, sc};
-        else
-          *overflow = 1;
+    } else if (threadIdx.x == 0) {
+      const float bound = OrderedToFloat3(*lb);
+      for (int t = 0; t < 8; ++t) {
+        if (!((mask >> t) & 1u)) continue;
+        const float sc = ToScore3(s_sums[t], jb.n_hi);
+        if (sc > jb.min_score && sc >= bound) {
+          const int idx = atomicAdd(next_count, 1);
+          if (idx < next_cap)
+            next[idx] = Node3{nd.scan, nd.ox + (t & 1) * half, nd.oy + ((t >> 1) & 1) * half,
+                              nd.oz + ((t >> 2) & 1) * half, sc};
+          else
+            *overflow = 1;
+        }
       }
     }
+  }
+}
+
+// Leaves whose score equals the final bound, with the angle index and rotational score of
+// their scan (what the host needs to assemble the Result).
+struct BestLeaf3 { int scan, angle, ox, oy, oz; float score, low, rot; };
+__global__ void __launch_bounds__(256)
+k3_collect(const Leaf3* __restrict__ leaves, const Scan3* __restrict__ scans,
+           const int* __restrict__ sel, int* __restrict__ ctl, int leaf_cap,
+           BestLeaf3* __restrict__ out, int out_cap) {
+  const unsigned bound = reinterpret_cast<const unsigned*>(ctl)[kC3Bound];
+  const int count = min(ctl[kC3Leaf], leaf_cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const Leaf3 l = leaves[i];
+    if (FloatToOrdered3(l.score) != bound) continue;
+    const int idx = atomicAdd(&ctl[kC3Best], 1);
+    if (idx < out_cap)
+      out[idx] = BestLeaf3{l.scan, sel[l.scan], l.ox, l.oy, l.oz, l.score, l.low,
+                           scans[l.scan].rot_score};
+    else
+      ctl[kC3Overflow] = 1;
   }
 }
 
@@ -849,18 +952,32 @@ csm_status csm_rotational_match3d(const float* submap_hist, const float* hist, i
 
 }  // extern "C"
 
-// GenerateDiscreteScans up to (not including) DiscretizeScan (:246-295): angles,
-// rotational scores (device), surviving scan poses.
-static csm_status PlanScans(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node,
-                            const HostSearch3& sp, ScanPlan* plan) {
-  cudaStream_t s = ctx->stream;
-  const float resolution = m->hs.resolution;
-  float max_scan_range = 3.f * resolution;
+// A node's clouds and histogram on the device (a queue matches one node against many
+// submaps: uploaded once per csm_match3d_batch call), plus the max point range both
+// SearchParameters need (:151-158, :255-260).
+struct NodeDev3 {
+  const float* hi = nullptr;
+  const float* lo = nullptr;
+  const float* hist = nullptr;
+  float max_range = 0.f;   // max_i |p_i| over the high-resolution cloud (0 if it is empty)
+};
+
+static float MaxRange3(const csm_node3d* node) {
+  float m = 0.f;
   for (int i = 0; i < node->num_high; ++i) {
     const float* p = node->high_resolution_point_cloud + 3 * i;
-    const float range = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-    max_scan_range = std::max(range, max_scan_range);
+    m = std::max(m, std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
   }
+  return m;
+}
+
+// GenerateDiscreteScans up to (not including) DiscretizeScan (:246-295), host part: the
+// angles and the scan pose of EVERY angle.  The rotational scores and the filter (:273-281)
+// run on the device (k3_rotational, k3_select_scans), so nothing is read back here.
+static csm_status PlanScans(const csm_matcher3d* m, const csm_node3d* node, float max_range,
+                            const HostSearch3& sp, ScanPlan* plan, float* initial_angle) {
+  const float resolution = m->hs.resolution;
+  const float max_scan_range = std::max(max_range, 3.f * resolution);
   const float kSafetyMargin = 1.f - 1e-2f;
   const float angular_step_size =
       kSafetyMargin * std::acos(1.f - (resolution * resolution) /
@@ -880,36 +997,12 @@ static csm_status PlanScans(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* 
   if (n2 > 0.)
     ginv = Qf{static_cast<float>(g[0] / n2), static_cast<float>(-g[1] / n2),
               static_cast<float>(-g[2] / n2), static_cast<float>(-g[3] / n2)};
-  const float initial_angle = HYaw(HMul(node_to_submap.q, ginv));
-  // rotational scores on the device (K7)
-  const int hn = node->histogram_size;
-  CSM_REQUIRE(hn == static_cast<int>(m->hist.size()), "histogram sizes differ");
-  plan->all_scores.assign(plan->num_angles, 1.f);
-  if (hn > 0) {
-    DevBuf& b = ctx->D("rot_b");
-    DevBuf& c = ctx->D("rot_c");
-    DevBuf& d = ctx->D("rot_d");
-    CSM_TRY(b.Reserve(4 * hn));
-    CSM_TRY(c.Reserve(4 * plan->num_angles));
-    CSM_TRY(d.Reserve(4 * plan->num_angles));
-    CSM_CUDA(cudaMemcpyAsync(b.p, node->rotational_scan_matcher_histogram, 4 * hn,
-                             cudaMemcpyHostToDevice, s));
-    CSM_CUDA(cudaMemcpyAsync(c.p, plan->angles.data(), 4 * plan->num_angles,
-                             cudaMemcpyHostToDevice, s));
-    ProfBegin(ctx);
-    k3_rotational<<<DivUp3(plan->num_angles, 128), 128, 0, s>>>(
-        m->d_hist, b.as<float>(), hn, initial_angle, c.as<float>(), plan->num_angles,
-        d.as<float>());
-    CSM_LAUNCH_CHECK();
-    ProfEnd(ctx, "k3_rotational", plan->num_angles);
-    CSM_CUDA(cudaMemcpyAsync(plan->all_scores.data(), d.p, 4 * plan->num_angles,
-                             cudaMemcpyDeviceToHost, s));
-    CSM_CUDA(cudaStreamSynchronize(s));
-  }
+  *initial_angle = HYaw(HMul(node_to_submap.q, ginv));
+  CSM_REQUIRE(node->histogram_size == static_cast<int>(m->hist.size()), "histogram sizes differ");
   plan->scans.clear();
+  plan->scans.reserve(plan->num_angles);
   const Qf sub_inv = HInverse(sp.submap.q);
   for (int i = 0; i < plan->num_angles; ++i) {
-    if (plan->all_scores[i] < m->opt.min_rotational_score) continue;  // float < double (:279)
     const Qf q = HMul(HMul(sub_inv, HAngleAxisZ(plan->angles[i])), sp.node.q);
     // GetPoseFromCandidate's rotation: (identity * q).normalized()
     const Qf nq = HNormalized(HMul(Qf{1.f, 0.f, 0.f, 0.f}, q));
@@ -917,15 +1010,14 @@ static csm_status PlanScans(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* 
     sc.tx = node_to_submap.t.x; sc.ty = node_to_submap.t.y; sc.tz = node_to_submap.t.z;
     sc.qw = q.w; sc.qx = q.x; sc.qy = q.y; sc.qz = q.z;
     sc.nw = nq.w; sc.nx = nq.x; sc.ny = nq.y; sc.nz = nq.z;
-    sc.rot_score = plan->all_scores[i];
+    sc.rot_score = 1.f;   // overwritten on the device for the scans that are kept
     plan->scans.push_back(sc);
   }
   return CSM_OK;
 }
 
-static csm_status MakeSearch3(const csm_matcher3d* m, const csm_node3d* node,
-                              const double node_pose[7], const double submap_pose[7], int full,
-                              HostSearch3* sp) {
+static csm_status MakeSearch3(const csm_matcher3d* m, float max_range, const double node_pose[7],
+                              const double submap_pose[7], int full, HostSearch3* sp) {
   auto cast = [](const double p[7], bool rotation_only) {
     Rf r;
     r.t = rotation_only ? Vf{0.f, 0.f, 0.f}
@@ -937,12 +1029,7 @@ static csm_status MakeSearch3(const csm_matcher3d* m, const csm_node3d* node,
   };
   const float resolution = m->hs.resolution;
   if (full) {  // :146-170
-    float max_point_distance = 0.f;
-    for (int i = 0; i < node->num_high; ++i) {
-      const float* p = node->high_resolution_point_cloud + 3 * i;
-      max_point_distance =
-          std::max(max_point_distance, std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
-    }
+    const float max_point_distance = max_range;
     const int w = (m->grid_size + 1) / 2 +
                   static_cast<int>(std::lround(max_point_distance / resolution + 0.5f));
     sp->wxy = w;
@@ -959,191 +1046,237 @@ static csm_status MakeSearch3(const csm_matcher3d* m, const csm_node3d* node,
   return CSM_OK;
 }
 
+// One match = one stream of launches + one synchronisation.  `dev` (optional) carries the
+// node's clouds already on the device.
 static csm_status Run3D(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node,
-                        const double node_pose[7],
+                        const NodeDev3* dev, const double node_pose[7],
                         const double submap_pose[7], int full, float min_score,
                         csm_result3d* result, csm_stats* stats, bool discretize_only,
                         int32_t* out_num_scans, int32_t* out_cells, float* out_poses,
                         float* out_rot) {
   CSM_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
+  const float max_range = dev ? dev->max_range : MaxRange3(node);
   HostSearch3 sp;
-  CSM_TRY(MakeSearch3(m, node, node_pose, submap_pose, full, &sp));
-  CSM_CUDA(cudaEventRecord(ctx->ev0, s));
+  CSM_TRY(MakeSearch3(m, max_range, node_pose, submap_pose, full, &sp));
   ScanPlan plan;
-  CSM_TRY(PlanScans(ctx, m, node, sp, &plan));
-  const int S = static_cast<int>(plan.scans.size());
-  if (out_num_scans) *out_num_scans = S;
-  if (result) {
-    std::memset(result, 0, sizeof(*result));
+  float initial_angle = 0.f;
+  CSM_TRY(PlanScans(m, node, max_range, sp, &plan, &initial_angle));
+  const int A = plan.num_angles;
+  if (result) std::memset(result, 0, sizeof(*result));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  const int n_hi = node->num_high, n_lo = node->num_low, hn = node->histogram_size;
+  if (!discretize_only) CSM_REQUIRE(n_lo >= 1, "empty low-resolution point cloud");
+  const int hmax = m->hs.depth - 1;
+  if (!discretize_only && hmax == 0) {
+    SetError("branch_and_bound_depth == 1 is not supported by the 3D engine");
+    return CSM_E_INVALID;
   }
-  if (stats) {
-    std::memset(stats, 0, sizeof(*stats));
-    stats->num_scans = S;
-  }
-  if (S == 0) return CSM_OK;
-  if (discretize_only && !out_cells) return CSM_OK;
 
-  const int n_hi = node->num_high, n_lo = node->num_low;
+  // ---- uploads through pinned staging: scans | angles | ones | histogram | clouds ----
+  const size_t o_ang = (sizeof(Scan3) * A + 255) / 256 * 256;
+  const size_t o_hist = (o_ang + 4 * static_cast<size_t>(A) + 255) / 256 * 256;
+  const size_t o_hi = (o_hist + 4 * static_cast<size_t>(std::max(1, hn)) + 255) / 256 * 256;
+  const size_t o_lo = dev ? o_hi : (o_hi + 12 * static_cast<size_t>(n_hi) + 255) / 256 * 256;
+  const size_t up_bytes = dev ? o_hi : o_lo + 12 * static_cast<size_t>(std::max(1, n_lo));
+  PinnedBuf& up = ctx->P("m3_upload");
+  DevBuf& d_up = ctx->D("m3_upload");
+  CSM_TRY(up.Reserve(up_bytes));
+  CSM_TRY(d_up.Reserve(up_bytes));
+  char* hup = up.as<char>();
+  std::memcpy(hup, plan.scans.data(), sizeof(Scan3) * A);
+  std::memcpy(hup + o_ang, plan.angles.data(), 4 * static_cast<size_t>(A));
+  if (hn) std::memcpy(hup + o_hist, node->rotational_scan_matcher_histogram, 4 * static_cast<size_t>(hn));
+  if (!dev) {
+    std::memcpy(hup + o_hi, node->high_resolution_point_cloud, 12 * static_cast<size_t>(n_hi));
+    if (n_lo) std::memcpy(hup + o_lo, node->low_resolution_point_cloud, 12 * static_cast<size_t>(n_lo));
+  }
   DevBuf& d_scans = ctx->D("m3_scans");
-  DevBuf& d_hi = ctx->D("m3_hi");
-  DevBuf& d_lo = ctx->D("m3_lo");
+  DevBuf& d_sel = ctx->D("m3_sel");
+  DevBuf& d_rot = ctx->D("m3_rot");
   DevBuf& d_cells = ctx->D("m3_cells");
-  CSM_TRY(d_scans.Reserve(sizeof(Scan3) * S));
-  CSM_TRY(d_hi.Reserve(sizeof(float) * 3 * n_hi));
-  CSM_TRY(d_lo.Reserve(sizeof(float) * 3 * std::max(1, n_lo)));
-  CSM_TRY(d_cells.Reserve(sizeof(short4) * static_cast<size_t>(S) * n_hi));
-  CSM_CUDA(cudaMemcpyAsync(d_scans.p, plan.scans.data(), sizeof(Scan3) * S,
-                           cudaMemcpyHostToDevice, s));
-  CSM_CUDA(cudaMemcpyAsync(d_hi.p, node->high_resolution_point_cloud, sizeof(float) * 3 * n_hi,
-                           cudaMemcpyHostToDevice, s));
-  if (n_lo)
-    CSM_CUDA(cudaMemcpyAsync(d_lo.p, node->low_resolution_point_cloud, sizeof(float) * 3 * n_lo,
-                             cudaMemcpyHostToDevice, s));
+  DevBuf& d_top = ctx->D("m3_top");
+  DevBuf& d_ctr = ctx->D("m3_ctr");
+  CSM_TRY(d_scans.Reserve(sizeof(Scan3) * A));
+  CSM_TRY(d_sel.Reserve(4 * static_cast<size_t>(A)));
+  CSM_TRY(d_rot.Reserve(4 * static_cast<size_t>(A)));
+  CSM_TRY(d_cells.Reserve(sizeof(short4) * static_cast<size_t>(A) * n_hi));
+  CSM_TRY(d_ctr.Reserve(8 * 8 + 4 * kC3Ints));
+  const char* dup = d_up.as<char>();
+  unsigned long long* ctr = d_ctr.as<unsigned long long>();
+  int* ictr = reinterpret_cast<int*>(ctr + 8);   // the control block (kC3*)
+  unsigned* lb = reinterpret_cast<unsigned*>(ictr) + kC3Bound;
+
   Job3 jb;
   std::memset(&jb, 0, sizeof(jb));
   jb.stack = m->d_stack;
   jb.low = m->d_low;
-  jb.hi_xyz = d_hi.as<float>();
-  jb.lo_xyz = d_lo.as<float>();
+  jb.hi_xyz = dev ? dev->hi : reinterpret_cast<const float*>(dup + o_hi);
+  jb.lo_xyz = dev ? dev->lo : reinterpret_cast<const float*>(dup + o_lo);
   jb.scans = d_scans.as<Scan3>();
+  jb.ctl = ictr;
   jb.cells = d_cells.as<short4>();
   jb.n_hi = n_hi;
   jb.n_lo = n_lo;
-  jb.num_scans = S;
+  jb.max_scans = A;
   jb.wxy = sp.wxy;
   jb.wz = sp.wz;
-  const int hmax = m->hs.depth - 1;
   const int step = 1 << hmax;
   jb.nxc = (2 * sp.wxy + step) / step;   // :301-306
   jb.nzc = (2 * sp.wz + step) / step;
   jb.min_score = min_score;
   jb.min_low_d = m->opt.min_low_resolution_score;
+  const long long per_scan = static_cast<long long>(jb.nxc) * jb.nxc * jb.nzc;
+  const long long max_top = per_scan * A;
+  CSM_REQUIRE(max_top < (1LL << 30), "too many lowest-resolution candidates");
 
-  ProfBegin(ctx);
-  k3_discretize<<<dim3(std::min(DivUp3(n_hi, 256), 64), S), 256, 0, s>>>(jb);
+  CSM_CUDA(cudaEventRecord(ctx->ev0, s));
+  CSM_CUDA(cudaMemcpyAsync(d_up.p, hup, up_bytes, cudaMemcpyHostToDevice, s));
+  CSM_CUDA(cudaMemsetAsync(d_ctr.p, 0, 8 * 8 + 4 * kC3Ints, s));
+  // ---- rotational scores (K7) and the filter, on the device ----
+  const float* d_node_hist = dev && dev->hist ? dev->hist : reinterpret_cast<const float*>(dup + o_hist);
+  if (hn > 0) {
+    ProfBegin(ctx);
+    k3_rotational<<<DivUp3(A, 128), 128, 0, s>>>(m->d_hist, d_node_hist, hn, initial_angle,
+                                                 reinterpret_cast<const float*>(dup + o_ang), A,
+                                                 d_rot.as<float>());
+    CSM_LAUNCH_CHECK();
+    ProfEnd(ctx, "k3_rotational", A);
+  } else {
+    k3_fill<<<DivUp3(A, 256), 256, 0, s>>>(d_rot.as<float>(), A, 1.f);
+    CSM_LAUNCH_CHECK();
+  }
+  k3_select_scans<<<1, 1024, 0, s>>>(reinterpret_cast<const Scan3*>(dup), d_rot.as<float>(), A,
+                                     m->opt.min_rotational_score, d_scans.as<Scan3>(),
+                                     d_sel.as<int>(), ictr, HostOrd(min_score));
   CSM_LAUNCH_CHECK();
-  ProfEnd(ctx, "k3_discretize", static_cast<double>(S) * n_hi);
+  ProfBegin(ctx);
+  k3_discretize<<<dim3(std::min(DivUp3(n_hi, 256), 64), A), 256, 0, s>>>(jb);
+  CSM_LAUNCH_CHECK();
+  ProfEnd(ctx, "k3_discretize", static_cast<double>(A) * n_hi);
+
+  PinnedBuf& pin = ctx->P("m3_readback");
+  const int kInlineBest = 256;
+  const size_t rb_ctr = 4 * kC3Ints;
+  const size_t rb_best = rb_ctr + 8 * 8;
+  CSM_TRY(pin.Reserve(rb_best + sizeof(BestLeaf3) * kInlineBest));
+  int* hp = pin.as<int>();
+  const unsigned long long* hctr = reinterpret_cast<const unsigned long long*>(pin.as<char>() + rb_ctr);
+  const BestLeaf3* best_inline = reinterpret_cast<const BestLeaf3*>(pin.as<char>() + rb_best);
+
   if (discretize_only) {
-    std::vector<short4> h(static_cast<size_t>(S) * n_hi);
-    CSM_CUDA(cudaMemcpyAsync(h.data(), d_cells.p, sizeof(short4) * h.size(),
-                             cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaMemcpyAsync(hp, ictr, rb_ctr, cudaMemcpyDeviceToHost, s));
     CSM_CUDA(cudaStreamSynchronize(s));
+    const int S = hp[kC3Scans];
+    if (out_num_scans) *out_num_scans = S;
+    if (stats) stats->num_scans = S;
+    if (S == 0 || !out_cells) return CSM_OK;
+    std::vector<short4> h(static_cast<size_t>(S) * n_hi);
+    std::vector<Scan3> hs(S);
+    CSM_CUDA(cudaMemcpy(h.data(), d_cells.p, sizeof(short4) * h.size(), cudaMemcpyDeviceToHost));
+    CSM_CUDA(cudaMemcpy(hs.data(), d_scans.p, sizeof(Scan3) * S, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < h.size(); ++i) {
       out_cells[3 * i] = h[i].x;
       out_cells[3 * i + 1] = h[i].y;
       out_cells[3 * i + 2] = h[i].z;
     }
     for (int k = 0; k < S; ++k) {
-      const Scan3& sc = plan.scans[k];
+      const Scan3& sc = hs[k];
       const float v[7] = {sc.tx, sc.ty, sc.tz, sc.qw, sc.qx, sc.qy, sc.qz};
       if (out_poses) std::memcpy(out_poses + 7 * k, v, sizeof(v));
       if (out_rot) out_rot[k] = sc.rot_score;
     }
     return CSM_OK;
   }
-  CSM_REQUIRE(n_lo >= 1, "empty low-resolution point cloud");
 
-  // ---- lowest-resolution pass ----
-  const long long per_scan = static_cast<long long>(jb.nxc) * jb.nxc * jb.nzc;
-  const long long total_top = per_scan * S;
-  CSM_REQUIRE(total_top < (1LL << 30), "too many lowest-resolution candidates");
-  DevBuf& d_top = ctx->D("m3_top");
-  DevBuf& d_ctr = ctx->D("m3_ctr");
-  CSM_TRY(d_top.Reserve(sizeof(int) * total_top));
-  CSM_TRY(d_ctr.Reserve(8 * 8 + 4 * 32));
-  CSM_CUDA(cudaMemsetAsync(d_ctr.p, 0, 8 * 8 + 4 * 32, s));
-  unsigned long long* ctr = d_ctr.as<unsigned long long>();
-  int* ictr = reinterpret_cast<int*>(ctr + 8);   // [h] queue counts, [16] leaves, [20] overflow
-  unsigned* lb = reinterpret_cast<unsigned*>(ictr + 24);
-  {
-    const unsigned lb0 = HostOrd(min_score);
-    CSM_CUDA(cudaMemcpyAsync(lb, &lb0, 4, cudaMemcpyHostToDevice, s));
-    CSM_CUDA(cudaStreamSynchronize(s));
-  }
+  // ---- lowest-resolution pass + dives (grids sized for all angles; filtered-out scans exit) ----
+  CSM_TRY(d_top.Reserve(sizeof(int) * max_top));
   ProfBegin(ctx);
-  k3_score_top<<<static_cast<int>(total_top), kT3, 0, s>>>(jb, d_top.as<int>());
+  k3_score_top<<<static_cast<int>(max_top), kT3, 0, s>>>(jb, d_top.as<int>());
   CSM_LAUNCH_CHECK();
-  ProfEnd(ctx, "k3_score_top", static_cast<double>(total_top));
+  ProfEnd(ctx, "k3_score_top", static_cast<double>(max_top));
   ProfBegin(ctx);
-  k3_dive<<<S, kT3, 0, s>>>(jb, d_top.as<int>(), lb, ctr);
+  k3_dive<<<A, kT3, 0, s>>>(jb, d_top.as<int>(), lb, ctr);
   CSM_LAUNCH_CHECK();
-  ProfEnd(ctx, "k3_dive", static_cast<double>(S) * 8 * hmax);
+  ProfEnd(ctx, "k3_dive", static_cast<double>(A) * 8 * hmax);
 
-  // ---- branch and bound ----
+  // ---- branch and bound: device-driven level loop (see engine2d.cu) ----
   const int kChunk = 1 << 16;
   const int kQueueCap = 8 * kChunk;
   const int kLeafCap = 1 << 20;
   DevBuf& d_qtop = ctx->D("m3_qtop");
   DevBuf& d_q = ctx->D("m3_queues");
   DevBuf& d_leaves = ctx->D("m3_leaves");
-  CSM_TRY(d_qtop.Reserve(sizeof(Node3) * static_cast<size_t>(total_top)));
+  DevBuf& d_best = ctx->D("m3_best");
+  CSM_TRY(d_qtop.Reserve(sizeof(Node3) * static_cast<size_t>(max_top)));
   CSM_TRY(d_q.Reserve(sizeof(Node3) * static_cast<size_t>(kQueueCap) * std::max(1, hmax)));
   CSM_TRY(d_leaves.Reserve(sizeof(Leaf3) * static_cast<size_t>(kLeafCap)));
+  CSM_TRY(d_best.Reserve(sizeof(BestLeaf3) * static_cast<size_t>(kLeafCap)));
   auto queue_ptr = [&](int h) -> Node3* {
     return h == hmax ? d_qtop.as<Node3>() : d_q.as<Node3>() + static_cast<size_t>(kQueueCap) * h;
   };
-  PinnedBuf& pin = ctx->P("m3_readback");
-  CSM_TRY(pin.Reserve(4 * 32));
-  int* hp = pin.as<int>();
-  std::vector<int> qn(hmax + 1, 0);
-  k3_filter_top<<<DivUp3(total_top, 256), 256, 0, s>>>(jb, d_top.as<int>(),
-                                                       static_cast<int>(total_top), lb,
-                                                       queue_ptr(hmax), ictr + hmax);
+  k3_filter_top<<<DivUp3(max_top, 256), 256, 0, s>>>(jb, d_top.as<int>(), lb, queue_ptr(hmax),
+                                                     ictr + hmax);
   CSM_LAUNCH_CHECK();
-  CSM_CUDA(cudaMemcpyAsync(hp, ictr, 4 * 32, cudaMemcpyDeviceToHost, s));
-  CSM_CUDA(cudaStreamSynchronize(s));
-  qn[hmax] = hp[hmax];
-  int h_leaf = 0;
-  if (hmax == 0) {
-    // depth 1: every lowest-resolution candidate is a leaf; expand with h = "1" is not
-    // defined, so gate them through the list path below.
-    SetError("branch_and_bound_depth == 1 is not supported by the 3D engine");
-    return CSM_E_INVALID;
-  }
-  for (;;) {
+  const int expand_grid = ctx->sm_count * 4;
+  auto level_step = [&](int h) -> csm_status {
+    k3_level_begin<<<1, 32, 0, s>>>(ictr, h, kChunk);
+    CSM_LAUNCH_CHECK();
+    ProfBegin(ctx);
+    k3_expand<<<expand_grid, kT3, 0, s>>>(jb, queue_ptr(h), ictr, h,
+                                          h - 1 >= 1 ? queue_ptr(h - 1) : nullptr,
+                                          ictr + (h - 1 >= 1 ? h - 1 : 23), kQueueCap,
+                                          d_leaves.as<Leaf3>(), kLeafCap, ctr);
+    CSM_LAUNCH_CHECK();
+    ProfEnd(ctx, "k3_expand", 0.);
+    return CSM_OK;
+  };
+  int host_syncs = 0;
+  auto collect = [&]() -> csm_status {
+    CSM_CUDA(cudaMemsetAsync(ictr + kC3Best, 0, 4, s));
+    k3_collect<<<ctx->sm_count, 256, 0, s>>>(d_leaves.as<Leaf3>(), d_scans.as<Scan3>(),
+                                             d_sel.as<int>(), ictr, kLeafCap,
+                                             d_best.as<BestLeaf3>(), kLeafCap);
+    CSM_LAUNCH_CHECK();
+    CSM_CUDA(cudaEventRecord(ctx->ev1, s));
+    CSM_CUDA(cudaMemcpyAsync(pin.as<char>(), ictr, rb_ctr, cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaMemcpyAsync(pin.as<char>() + rb_ctr, ctr, 8 * 8, cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaMemcpyAsync(pin.as<char>() + rb_best, d_best.p, sizeof(BestLeaf3) * kInlineBest,
+                             cudaMemcpyDeviceToHost, s));
+    CSM_CUDA(cudaStreamSynchronize(s));
+    ++host_syncs;
+    return CSM_OK;
+  };
+  for (int h = hmax; h >= 1; --h) CSM_TRY(level_step(h));
+  CSM_TRY(collect());
+  for (;;) {   // frontiers larger than one chunk: deepest non-empty level first
+    if (hp[kC3Overflow]) { SetError("3D branch-and-bound capacity exceeded"); return CSM_E_CAPACITY; }
     int h = -1;
     for (int l = 1; l <= hmax; ++l)
-      if (qn[l] > 0) { h = l; break; }
+      if (hp[l] > 0) { h = l; break; }
     if (h < 0) break;
-    const int chunk = std::min(qn[h], kChunk);
-    const int start = qn[h] - chunk;
-    if (h - 1 >= 1) CSM_CUDA(cudaMemsetAsync(ictr + (h - 1), 0, 4, s));
-    ProfBegin(ctx);
-    k3_expand<<<chunk, kT3, 0, s>>>(jb, queue_ptr(h) + start, chunk, h, lb,
-                                    h - 1 >= 1 ? queue_ptr(h - 1) : nullptr,
-                                    ictr + (h - 1 >= 1 ? h - 1 : 23), kQueueCap,
-                                    d_leaves.as<Leaf3>(), ictr + 16, kLeafCap, ictr + 20, ctr);
-    CSM_LAUNCH_CHECK();
-    ProfEnd(ctx, "k3_expand", static_cast<double>(chunk) * 8);
-    qn[h] -= chunk;
-    CSM_CUDA(cudaMemcpyAsync(hp, ictr, 4 * 32, cudaMemcpyDeviceToHost, s));
-    CSM_CUDA(cudaStreamSynchronize(s));
-    if (h - 1 >= 1) qn[h - 1] = hp[h - 1];
-    h_leaf = hp[16];
-    if (hp[20]) { SetError("3D branch-and-bound capacity exceeded"); return CSM_E_CAPACITY; }
+    for (int l = h; l >= 1; --l) CSM_TRY(level_step(l));
+    CSM_TRY(collect());
   }
-  CSM_CUDA(cudaEventRecord(ctx->ev1, s));
-  unsigned lbh = 0;
-  unsigned long long hctr[8];
-  std::vector<Leaf3> leaves(h_leaf);
-  CSM_CUDA(cudaMemcpyAsync(&lbh, lb, 4, cudaMemcpyDeviceToHost, s));
-  CSM_CUDA(cudaMemcpyAsync(hctr, ctr, sizeof(hctr), cudaMemcpyDeviceToHost, s));
-  if (h_leaf)
-    CSM_CUDA(cudaMemcpyAsync(leaves.data(), d_leaves.p, sizeof(Leaf3) * h_leaf,
-                             cudaMemcpyDeviceToHost, s));
-  CSM_CUDA(cudaStreamSynchronize(s));
+  const int S = hp[kC3Scans];
+  if (out_num_scans) *out_num_scans = S;
+  const long long total_top = per_scan * S;
+  const unsigned lbh = static_cast<unsigned>(hp[kC3Bound]);
   const float best_score = HostUnord(lbh);
-  std::vector<Leaf3> ties;
-  for (const Leaf3& l : leaves)
-    if (HostOrd(l.score) == lbh) ties.push_back(l);
+  const int n_best = hp[kC3Best];
+  std::vector<BestLeaf3> ties(best_inline, best_inline + std::min(n_best, kInlineBest));
+  if (n_best > kInlineBest) {
+    ties.resize(n_best);
+    CSM_CUDA(cudaMemcpy(ties.data(), d_best.p, sizeof(BestLeaf3) * n_best, cudaMemcpyDeviceToHost));
+    ++host_syncs;
+  }
 
   // ---- tie resolution: first optimal, gate-passing leaf in the reference's DFS order ----
   int host_resolves = 0;
   if (ties.size() > 1) {
     const int T = static_cast<int>(ties.size());
     std::vector<List3> lc;
-    for (const Leaf3& t : ties)
+    for (const BestLeaf3& t : ties)
       for (int l = 1; l <= hmax; ++l)
         lc.push_back(List3{t.scan, -sp.wxy + (((t.ox + sp.wxy) >> l) << l),
                            -sp.wxy + (((t.oy + sp.wxy) >> l) << l),
@@ -1161,6 +1294,7 @@ static csm_status Run3D(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node
     CSM_CUDA(cudaMemcpyAsync(anc.data(), d_ls.p, sizeof(float) * lc.size(),
                              cudaMemcpyDeviceToHost, s));
     CSM_CUDA(cudaStreamSynchronize(s));
+    ++host_syncs;
     std::vector<int> top_rank;
     auto ensure_top_rank = [&]() -> csm_status {
       if (!top_rank.empty()) return CSM_OK;
@@ -1182,19 +1316,19 @@ static csm_status Run3D(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node
     };
     csm_status err = CSM_OK;
     auto before = [&](int a, int b) -> bool {
-      const Leaf3& A = ties[a];
-      const Leaf3& B = ties[b];
+      const BestLeaf3& A_ = ties[a];
+      const BestLeaf3& B_ = ties[b];
       for (int l = hmax; l >= 0; --l) {
-        const int ax = (A.ox + sp.wxy) >> l, ay = (A.oy + sp.wxy) >> l, az = (A.oz + sp.wz) >> l;
-        const int bx = (B.ox + sp.wxy) >> l, by = (B.oy + sp.wxy) >> l, bz = (B.oz + sp.wz) >> l;
-        if (A.scan == B.scan && ax == bx && ay == by && az == bz) continue;
+        const int ax = (A_.ox + sp.wxy) >> l, ay = (A_.oy + sp.wxy) >> l, az = (A_.oz + sp.wz) >> l;
+        const int bx = (B_.ox + sp.wxy) >> l, by = (B_.oy + sp.wxy) >> l, bz = (B_.oz + sp.wz) >> l;
+        if (A_.scan == B_.scan && ax == bx && ay == by && az == bz) continue;
         const float fa = l == 0 ? 0.f : anc[static_cast<size_t>(a) * hmax + (l - 1)];
         const float fb = l == 0 ? 0.f : anc[static_cast<size_t>(b) * hmax + (l - 1)];
         if (l > 0 && fa != fb) return fa > fb;
         if (l == hmax) {
           if (ensure_top_rank() != CSM_OK) { err = CSM_E_CUDA; return false; }
-          const long long ga = ((static_cast<long long>(A.scan) * jb.nzc + az) * jb.nxc + ay) * jb.nxc + ax;
-          const long long gb = ((static_cast<long long>(B.scan) * jb.nzc + bz) * jb.nxc + by) * jb.nxc + bx;
+          const long long ga = ((static_cast<long long>(A_.scan) * jb.nzc + az) * jb.nxc + ay) * jb.nxc + ax;
+          const long long gb = ((static_cast<long long>(B_.scan) * jb.nzc + bz) * jb.nxc + by) * jb.nxc + bx;
           return top_rank[ga] < top_rank[gb];
         }
         // siblings: generation order z outer, y, x inner
@@ -1214,8 +1348,8 @@ static csm_status Run3D(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node
   if (result) {
     result->leaves_tied = static_cast<int32_t>(ties.size());
     if (!ties.empty() && best_score > min_score) {
-      const Leaf3& t = ties[0];
-      const Scan3& sc = plan.scans[t.scan];
+      const BestLeaf3& t = ties[0];
+      const Scan3& sc = plan.scans[t.angle];
       const float res = m->hs.resolution;
       result->found = 1;
       result->score = best_score;
@@ -1227,7 +1361,7 @@ static csm_status Run3D(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node
       result->pose_estimate[4] = sc.nx;
       result->pose_estimate[5] = sc.ny;
       result->pose_estimate[6] = sc.nz;
-      result->rotational_score = sc.rot_score;
+      result->rotational_score = t.rot;
       result->low_resolution_score = t.low;
       result->best_scan_index = t.scan;
       result->best_offset[0] = t.ox;
@@ -1244,6 +1378,7 @@ static csm_status Run3D(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node
     stats->leaves_tied = static_cast<int64_t>(ties.size());
     stats->num_scans = S;
     stats->host_tie_resolves = host_resolves;
+    stats->host_syncs = host_syncs;
     stats->device_ms = ms;
     if (result && result->found) {
       stats->best_scan_index = result->best_scan_index;
@@ -1265,8 +1400,8 @@ csm_status csm_match3d(const csm_matcher3d* m, const csm_node3d* node, const dou
               "low-resolution cloud");
   LaneGuard guard;
   CSM_TRY(AcquireLane(m->ctx->device, &guard));
-  return Run3D(guard.lane, m, node, node_pose, submap_pose, full, min_score, result, stats, false,
-               nullptr, nullptr, nullptr, nullptr);
+  return Run3D(guard.lane, m, node, nullptr, node_pose, submap_pose, full, min_score, result,
+               stats, false, nullptr, nullptr, nullptr, nullptr);
 }
 
 csm_status csm_match3d_batch(const csm_matcher3d* const* matchers, int32_t num_matchers,
@@ -1277,15 +1412,59 @@ csm_status csm_match3d_batch(const csm_matcher3d* const* matchers, int32_t num_m
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (num_jobs == 0) return CSM_OK;
   CSM_REQUIRE(matchers && nodes && jobs && results, "null pointer");
+  int device = -1;
+  std::vector<char> used(num_nodes, 0);
   for (int j = 0; j < num_jobs; ++j) {
     CSM_REQUIRE(jobs[j].matcher_index >= 0 && jobs[j].matcher_index < num_matchers &&
                     matchers[jobs[j].matcher_index] != nullptr,
                 "matcher_index out of range");
     CSM_REQUIRE(jobs[j].node_index >= 0 && jobs[j].node_index < num_nodes,
                 "node_index out of range");
+    const csm_node3d& nd = nodes[jobs[j].node_index];
+    CSM_REQUIRE(nd.num_high >= 1 && nd.high_resolution_point_cloud, "high-resolution cloud");
+    CSM_REQUIRE(nd.num_low >= 0 && (nd.num_low == 0 || nd.low_resolution_point_cloud),
+                "low-resolution cloud");
+    used[jobs[j].node_index] = 1;
+    const int dv = matchers[jobs[j].matcher_index]->ctx->device;
+    CSM_REQUIRE(device < 0 || device == dv, "all matchers of a batch must share one device");
+    device = dv;
   }
-  // Worker threads stand in for the reference's pool threads: every csm_match3d call
-  // borrows its own lane (stream + workspace), so the matches overlap on the device.
+  // The queue matches every node against many submaps: its clouds and histogram go to the
+  // device ONCE per call (one allocation, one staged copy), not once per job.
+  CSM_CUDA(cudaSetDevice(device));
+  std::vector<NodeDev3> ndev(num_nodes);
+  std::vector<size_t> off_hi(num_nodes, 0), off_lo(num_nodes, 0), off_h(num_nodes, 0);
+  size_t bytes = 0;
+  for (int i = 0; i < num_nodes; ++i) {
+    if (!used[i]) continue;
+    off_hi[i] = bytes; bytes += (12 * static_cast<size_t>(nodes[i].num_high) + 255) / 256 * 256;
+    off_lo[i] = bytes; bytes += (12 * static_cast<size_t>(std::max(1, nodes[i].num_low)) + 255) / 256 * 256;
+    off_h[i] = bytes; bytes += (4 * static_cast<size_t>(std::max(1, nodes[i].histogram_size)) + 255) / 256 * 256;
+  }
+  char* d_nodes = nullptr;
+  char* h_nodes = nullptr;
+  CSM_CUDA(cudaMalloc(&d_nodes, std::max<size_t>(bytes, 256)));
+  struct Free {
+    char* d; char* h;
+    ~Free() { cudaFree(d); cudaFreeHost(h); }
+  } guard_free{d_nodes, nullptr};
+  CSM_CUDA(cudaMallocHost(&h_nodes, std::max<size_t>(bytes, 256)));
+  guard_free.h = h_nodes;
+  for (int i = 0; i < num_nodes; ++i) {
+    if (!used[i]) continue;
+    std::memcpy(h_nodes + off_hi[i], nodes[i].high_resolution_point_cloud, 12 * static_cast<size_t>(nodes[i].num_high));
+    if (nodes[i].num_low)
+      std::memcpy(h_nodes + off_lo[i], nodes[i].low_resolution_point_cloud, 12 * static_cast<size_t>(nodes[i].num_low));
+    if (nodes[i].histogram_size)
+      std::memcpy(h_nodes + off_h[i], nodes[i].rotational_scan_matcher_histogram, 4 * static_cast<size_t>(nodes[i].histogram_size));
+    ndev[i].hi = reinterpret_cast<const float*>(d_nodes + off_hi[i]);
+    ndev[i].lo = reinterpret_cast<const float*>(d_nodes + off_lo[i]);
+    ndev[i].hist = reinterpret_cast<const float*>(d_nodes + off_h[i]);
+    ndev[i].max_range = MaxRange3(&nodes[i]);
+  }
+  CSM_CUDA(cudaMemcpy(d_nodes, h_nodes, std::max<size_t>(bytes, 256), cudaMemcpyHostToDevice));
+  // Worker threads stand in for the reference's pool threads: every match borrows its own
+  // lane (stream + workspace), so the matches overlap on the device.
   const int workers = std::max(1, std::min(num_jobs, max_concurrency > 0 ? max_concurrency : 8));
   std::atomic<int> next{0};
   std::atomic<int> failed{0};
@@ -1301,9 +1480,16 @@ csm_status csm_match3d_batch(const csm_matcher3d* const* matchers, int32_t num_m
       const csm_job3d& jb = jobs[j];
       csm_stats st;
       std::memset(&st, 0, sizeof(st));
-      const csm_status rc =
-          csm_match3d(matchers[jb.matcher_index], &nodes[jb.node_index], jb.global_node_pose,
-                      jb.global_submap_pose, jb.full_submap, jb.min_score, &results[j], &st);
+      csm_status rc;
+      {
+        LaneGuard guard;
+        rc = AcquireLane(device, &guard);
+        if (rc == CSM_OK)
+          rc = Run3D(guard.lane, matchers[jb.matcher_index], &nodes[jb.node_index],
+                     &ndev[jb.node_index], jb.global_node_pose, jb.global_submap_pose,
+                     jb.full_submap, jb.min_score, &results[j], &st, false, nullptr, nullptr,
+                     nullptr, nullptr);
+      }
       std::lock_guard<std::mutex> lock(mu);
       if (rc != CSM_OK) {
         if (!failed.exchange(1)) {
@@ -1317,6 +1503,7 @@ csm_status csm_match3d_batch(const csm_matcher3d* const* matchers, int32_t num_m
       total.nodes_expanded += st.nodes_expanded;
       total.num_scans += st.num_scans;
       total.host_tie_resolves += st.host_tie_resolves;
+      total.host_syncs += st.host_syncs;
       total.device_ms += st.device_ms;
     }
   };
@@ -1339,8 +1526,8 @@ csm_status csm_discretize3d(const csm_matcher3d* m, const csm_node3d* node,
   CSM_REQUIRE(node->num_high >= 1 && node->high_resolution_point_cloud, "high-resolution cloud");
   LaneGuard guard;
   CSM_TRY(AcquireLane(m->ctx->device, &guard));
-  return Run3D(guard.lane, m, node, node_pose, submap_pose, full, 0.f, nullptr, nullptr, true,
-               num_scans, cells, poses, rot);
+  return Run3D(guard.lane, m, node, nullptr, node_pose, submap_pose, full, 0.f, nullptr, nullptr,
+               true, num_scans, cells, poses, rot);
 }
 
 }  // extern "C"

@@ -576,14 +576,18 @@ def _result3d_dict(res):
                 leaves_tied=res.leaves_tied)
 
 
-def match_batch3d(matchers, nodes, jobs, max_concurrency=0):
+def match_batch3d(matchers, nodes, jobs, max_concurrency=0, ctx=None, submap_owner=None):
     """csm_match3d_batch: a queue of ConstraintBuilder3D searches in one call.
     jobs: iterable of (matcher_index, node_index, full_submap, global_node_pose[7],
-    global_submap_pose[7], min_score).  -> ([Result dict or None per job], stats dict)."""
+    global_submap_pose[7], min_score).  -> ([Result dict or None per job], stats dict).
+    With `ctx` (MultiGpuContext) the queue is sharded over the GPUs (csm_cb_batch3d_run:
+    matcher m runs on rank submap_owner[m], default m % world_size; matchers[m] may be None
+    elsewhere) and every rank gets all results after one ncclAllGather."""
     jobs = list(jobs)
     holders = [_NodeHolder(n) for n in nodes]
     c_nodes = (CsmNode3D * max(1, len(holders)))(*[h.c for h in holders])
-    c_matchers = (C.c_void_p * max(1, len(matchers)))(*[m._h for m in matchers])
+    c_matchers = (C.c_void_p * max(1, len(matchers)))(
+        *[(m._h if m is not None else None) for m in matchers])
     c_jobs = (CsmJob3D * max(1, len(jobs)))()
     for k, (mi, ni, full, npose, spose, min_score) in enumerate(jobs):
         c_jobs[k].matcher_index = int(mi)
@@ -594,9 +598,19 @@ def match_batch3d(matchers, nodes, jobs, max_concurrency=0):
         c_jobs[k].global_submap_pose = (C.c_double * 7)(*[float(v) for v in spose])
     c_res = (CsmResult3D * max(1, len(jobs)))()
     stats = CsmStats()
-    check(lib().csm_match3d_batch(c_matchers, C.c_int32(len(matchers)), c_nodes,
-                                  C.c_int32(len(holders)), c_jobs, C.c_int32(len(jobs)),
-                                  C.c_int32(int(max_concurrency)), c_res, C.byref(stats)))
+    if ctx is None:
+        check(lib().csm_match3d_batch(c_matchers, C.c_int32(len(matchers)), c_nodes,
+                                      C.c_int32(len(holders)), c_jobs, C.c_int32(len(jobs)),
+                                      C.c_int32(int(max_concurrency)), c_res, C.byref(stats)))
+    else:
+        owner = None
+        if submap_owner is not None:
+            owner_arr = np.ascontiguousarray(submap_owner, dtype=np.int32)
+            owner = ptr(owner_arr, C.c_int32)
+        check(lib().csm_cb_batch3d_run(ctx._h, c_matchers, C.c_int32(len(matchers)), c_nodes,
+                                       C.c_int32(len(holders)), c_jobs, C.c_int32(len(jobs)),
+                                       owner, C.c_int32(int(max_concurrency)), c_res,
+                                       C.byref(stats)))
     return [_result3d_dict(c_res[k]) for k in range(len(jobs))], stats.as_dict()
 
 
