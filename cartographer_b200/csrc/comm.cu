@@ -8,18 +8,59 @@
 //   * RunWhenDoneCallback (:279-300) hands the caller ONE vector with all constraints
 //     => every rank ends up with the results of ALL jobs, in job order, after exactly one
 //     ncclAllGather of fixed-size records on the engine's stream.
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include "engine2d.cuh"
 
 namespace csm {
 
+// libnccl is bound at run time, on the first multi-GPU call, not at link time: a process
+// that also hosts PyTorch must end up with ONE libnccl.so.2 (torch's bundled copy, which
+// may be newer than the system one), whichever of the two libraries was loaded first.
+// RTLD_NOLOAD picks up a copy that is already mapped; otherwise the system library loads.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+static const NcclApi& Nccl() {
+  static const NcclApi api = []() {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.AllGather && a.CommDestroy && a.GetErrorString;
+    return a;
+  }();
+  return api;
+}
+
+#define CSM_NCCL_READY()                                                                \
+  do {                                                                                  \
+    if (!::csm::Nccl().ok) {                                                            \
+      ::csm::SetError("libnccl.so.2 could not be loaded: %s", dlerror());               \
+      return CSM_E_CUDA;                                                                \
+    }                                                                                   \
+  } while (0)
+
 #define CSM_NCCL(expr)                                                                  \
   do {                                                                                  \
     ncclResult_t _r = (expr);                                                           \
     if (_r != ncclSuccess) {                                                            \
       ::csm::SetError("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                \
-                      ncclGetErrorString(_r));                                          \
+                      ::csm::Nccl().GetErrorString(_r));                                \
       return CSM_E_CUDA;                                                                \
     }                                                                                   \
   } while (0)
@@ -43,8 +84,9 @@ extern "C" {
 
 csm_status csm_comm_unique_id(uint8_t id[CSM_COMM_ID_BYTES]) {
   CSM_REQUIRE(id != nullptr, "null pointer");
+  CSM_NCCL_READY();
   ncclUniqueId u;
-  CSM_NCCL(ncclGetUniqueId(&u));
+  CSM_NCCL(Nccl().GetUniqueId(&u));
   std::memcpy(id, &u, sizeof(u));
   return CSM_OK;
 }
@@ -64,9 +106,10 @@ csm_status csm_ctx_create(int32_t world_size, int32_t rank, int32_t device,
   c->device = device;
   CSM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   if (world_size > 1) {
+    CSM_NCCL_READY();
     ncclUniqueId u;
     std::memcpy(&u, id, sizeof(u));
-    CSM_NCCL(ncclCommInitRank(&c->comm, world_size, u, rank));
+    CSM_NCCL(Nccl().CommInitRank(&c->comm, world_size, u, rank));
   }
   *out = c.release();
   return CSM_OK;
@@ -76,7 +119,7 @@ csm_status csm_ctx_destroy(csm_ctx* ctx) {
   if (!ctx) return CSM_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  if (ctx->comm) ncclCommDestroy(ctx->comm);
+  if (ctx->comm) Nccl().CommDestroy(ctx->comm);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaFree(ctx->send.p);
   cudaFree(ctx->recv.p);
@@ -112,7 +155,7 @@ csm_status csm_ctx_allgather(csm_ctx* ctx, const void* send, int64_t bytes, void
   CSM_TRY(ctx->h_recv.Reserve(b * ctx->world));
   std::memcpy(ctx->h_send.p, send, b);
   CSM_CUDA(cudaMemcpyAsync(ctx->send.p, ctx->h_send.p, b, cudaMemcpyHostToDevice, ctx->stream));
-  CSM_NCCL(ncclAllGather(ctx->send.p, ctx->recv.p, b, ncclUint8, ctx->comm, ctx->stream));
+  CSM_NCCL(Nccl().AllGather(ctx->send.p, ctx->recv.p, b, ncclUint8, ctx->comm, ctx->stream));
   CSM_CUDA(cudaMemcpyAsync(ctx->h_recv.p, ctx->recv.p, b * ctx->world, cudaMemcpyDeviceToHost,
                            ctx->stream));
   CSM_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -62,6 +62,25 @@ __device__ __forceinline__ int WarpSum(int v) {
   return v;
 }
 
+// Word index of lattice cell (X, Y) (both already shifted by +1) of phase `ph` in the
+// child-window array of a level (StackDev::win).
+//   default      : row-major per phase — x-neighbours share 128-byte lines;
+//   CSM_WIN_TILED: 8 x 4 word tiles (one line each) — x- AND y-neighbours share lines, so
+//                  a compact blob of surviving parents touches about half as many lines.
+#ifdef CSM_WIN_TILED
+__host__ __device__ __forceinline__ long long WinPhaseWords(int jd, int ids) {
+  return static_cast<long long>((jd + 3) >> 2) * ((ids + 7) >> 3) * 32;
+}
+__device__ __forceinline__ int WinCell(int X, int Y, int ids) {
+  return ((((Y >> 2) * ((ids + 7) >> 3) + (X >> 3)) << 5) | ((Y & 3) << 3) | (X & 7));
+}
+#else
+__host__ __device__ __forceinline__ long long WinPhaseWords(int jd, int ids) {
+  return static_cast<long long>(jd) * ids;
+}
+__device__ __forceinline__ int WinCell(int X, int Y, int ids) { return Y * ids + X; }
+#endif
+
 // ---------------------------------------------------------------------------
 // K1: precomputation grid stack
 // ---------------------------------------------------------------------------
@@ -123,21 +142,30 @@ __global__ void k_stack_decimate4(const uint8_t* __restrict__ lvl, int wx, int w
 __global__ void k_stack_window(const uint8_t* __restrict__ lvl, int wx, int wy, int h,
                                unsigned* __restrict__ win, int jd, int ids) {
   const int S = 1 << h, s = S >> 1;
-  const long long total = static_cast<long long>(S) * S * jd * ids;
+  const long long per_phase = WinPhaseWords(jd, ids);
+  const long long total = static_cast<long long>(S) * S * per_phase;
   for (long long u = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; u < total;
        u += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int I = static_cast<int>(u % ids) - 1;
-    long long r = u / ids;
-    const int J = static_cast<int>(r % jd) - 1;
-    r /= jd;
-    const int ax = static_cast<int>(r % S);
-    const int ay = static_cast<int>(r / S);
+    const int ph = static_cast<int>(u / per_phase);
+    const int c = static_cast<int>(u - ph * per_phase);
+#ifdef CSM_WIN_TILED
+    const int it = (ids + 7) >> 3;
+    const int tile = c >> 5, in = c & 31;
+    const int X = ((tile % it) << 3) | (in & 7), Y = ((tile / it) << 2) | (in >> 3);
+#else
+    const int X = c % ids, Y = c / ids;
+#endif
+    const int I = X - 1, J = Y - 1;
+    const int ax = ph % S, ay = ph / S;
     const int x = S * I + ax, y = S * J + ay;
     auto at = [&](int px, int py) -> unsigned {
       return (px >= 0 && py >= 0 && px < wx && py < wy) ? lvl[static_cast<size_t>(py) * wx + px]
                                                         : 0u;
     };
-    win[u] = at(x, y) | (at(x + s, y) << 8) | (at(x, y + s) << 16) | (at(x + s, y + s) << 24);
+    unsigned v = 0u;
+    if (X < ids && Y < jd)
+      v = at(x, y) | (at(x + s, y) << 8) | (at(x, y + s) << 16) | (at(x + s, y + s) << 24);
+    win[u] = v;
   }
 }
 
@@ -725,6 +753,7 @@ __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const Scan
   const int S1 = (1 << h) - 1;
   const unsigned* __restrict__ win = st.win[h];
   const int jd = st.win_jd[h], ids = st.win_ids[h];
+  const long long per_phase = WinPhaseWords(jd, ids);
   const int bx = xo + half - 1, by = yo + half - 1;
   int s00 = 0, s01 = 0, s10 = 0, s11 = 0;
   constexpr int kU = 4;
@@ -748,7 +777,8 @@ __device__ __forceinline__ unsigned ScoreChildren(const StackDev& st, const Scan
         w[u] = 0u;
         if (p + 32 * u < pend && static_cast<unsigned>(Qx) < static_cast<unsigned>(ids) &&
             static_cast<unsigned>(Qy) < static_cast<unsigned>(jd))
-          w[u] = __ldg(win + ((static_cast<long long>((ly & S1) << h | (lx & S1)) * jd + Qy) * ids + Qx));
+          w[u] = __ldg(win + (static_cast<long long>((ly & S1) << h | (lx & S1)) * per_phase +
+                              WinCell(Qx, Qy, ids)));
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
@@ -1191,6 +1221,9 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
   const int S1 = (1 << h) - 1;
   const int jd = st.win_jd[h], ids = st.win_ids[h];
   const unsigned* __restrict__ win = st.win[h];
+#ifdef CSM_WIN_TILED
+  const int per_phase = static_cast<int>(WinPhaseWords(jd, ids));
+#endif
   const short2* __restrict__ pts = dscan + jb.dscan_off +
                                    static_cast<long long>(it.scan - jb.scan_base) * jb.n;
   const bool active = pidx < it.count;
@@ -1213,7 +1246,11 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
         const int qx = (bx >> h) + 1, qy = (by >> h) + 1;
         const int ax = bx & S1, ay = by & S1;
         if (qx > -32000 && qx < 32000 && qy > -32000 && qy < 32000)
+#ifdef CSM_WIN_TILED
+          d = make_int2(((ay << h) | ax) * per_phase, (qy << 16) | (qx & 0xffff));
+#else
           d = make_int2((((ay << h) | ax) * jd + qy) * ids + qx, (qy << 16) | (qx & 0xffff));
+#endif
       }
       s_pt[t] = d;
     }
@@ -1229,13 +1266,21 @@ k_expand_lattice(const JobDev* __restrict__ jobs, const ScanInfo* __restrict__ i
         const int Jb = (d.w >> 16) + j0, Ib = static_cast<short>(d.w & 0xffff) + i0;
         if (static_cast<unsigned>(Ia) < static_cast<unsigned>(ids) &&
             static_cast<unsigned>(Ja) < static_cast<unsigned>(jd)) {
+#ifdef CSM_WIN_TILED
+          const unsigned w = __ldg(win + (d.x + WinCell(Ia, Ja, ids)));
+#else
           const unsigned w = __ldg(win + (d.x + toff));
+#endif
           r0 += __byte_perm(w, 0u, 0x4140);
           r1 += __byte_perm(w, 0u, 0x4342);
         }
         if (static_cast<unsigned>(Ib) < static_cast<unsigned>(ids) &&
             static_cast<unsigned>(Jb) < static_cast<unsigned>(jd)) {
+#ifdef CSM_WIN_TILED
+          const unsigned w = __ldg(win + (d.z + WinCell(Ib, Jb, ids)));
+#else
           const unsigned w = __ldg(win + (d.z + toff));
+#endif
           r0 += __byte_perm(w, 0u, 0x4140);
           r1 += __byte_perm(w, 0u, 0x4342);
         }
@@ -1380,6 +1425,50 @@ int DivUp(long long a, long long b) { return static_cast<int>((a + b - 1) / b); 
 
 }  // namespace
 
+// Fills every layout of the stack (levels, decimated copies, child windows) from the
+// grid's cells; caller holds ctx->mu.  Shared by csm_stack2d_create and csm_stack2d_update.
+static csm_status BuildStack2D(csm_stack2d* st, const uint16_t* cells) {
+  Ctx* ctx = st->ctx;
+  const StackDev& h = st->h;
+  const int nx = h.nx, ny = h.ny, depth = h.depth, top = depth - 1;
+  std::vector<uint8_t> lut(65536);
+  float lo, hi;
+  BuildLut(st->min_cost, st->max_cost, lut.data(), &lo, &hi);
+  const size_t* win_off = st->win_off;
+  // upload cells + LUT into scratch
+  DevBuf& d_cells = ctx->D("stack_cells");
+  DevBuf& d_lut = ctx->D("stack_lut");
+  const size_t ncell = static_cast<size_t>(nx) * ny;
+  CSM_TRY(d_cells.Reserve(ncell * sizeof(uint16_t)));
+  CSM_TRY(d_lut.Reserve(65536));
+  CSM_CUDA(cudaMemcpyAsync(d_cells.p, cells, ncell * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  CSM_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 65536, cudaMemcpyHostToDevice, ctx->stream));
+  k_stack_level0<<<DivUp(ncell, 256), 256, 0, ctx->stream>>>(
+      d_cells.as<uint16_t>(), d_lut.as<uint8_t>(), st->d_levels + st->level_off[0],
+      static_cast<int>(ncell));
+  CSM_LAUNCH_CHECK();
+  for (int l = 1; l < depth; ++l) {
+    dim3 block(32, 8), grid(DivUp(h.wx[l], 32), DivUp(h.wy[l], 8));
+    k_stack_double<<<grid, block, 0, ctx->stream>>>(st->d_levels + st->level_off[l - 1],
+                                                    h.wx[l - 1], h.wy[l - 1],
+                                                    st->d_levels + st->level_off[l], h.wx[l],
+                                                    h.wy[l], 1 << (l - 1));
+    CSM_LAUNCH_CHECK();
+  }
+  k_stack_decimate4<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+      h.level[top], h.wx[top], h.wy[top], top, st->d_dec, h.dec_lpad[top], h.dec_id[top],
+      h.dec_jd[top], h.dec_ids[top]);
+  CSM_LAUNCH_CHECK();
+  for (int l = 1; l < depth; ++l) {
+    k_stack_window<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+        h.level[l - 1], h.wx[l - 1], h.wy[l - 1], l, st->d_win + win_off[l], h.win_jd[l],
+        h.win_ids[l]);
+    CSM_LAUNCH_CHECK();
+  }
+  return CSM_OK;
+}
+
 extern "C" {
 
 csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, double resolution,
@@ -1441,44 +1530,15 @@ csm_status csm_stack2d_create(const uint16_t* cells, int32_t nx, int32_t ny, dou
     const int S = 1 << l;
     h.win_ids[l] = (h.wx[l - 1] + S - 1) / S + 1;
     h.win_jd[l] = (h.wy[l - 1] + S - 1) / S + 1;
-    const long long words = static_cast<long long>(S) * S * h.win_jd[l] * h.win_ids[l];
+    const long long words = static_cast<long long>(S) * S * WinPhaseWords(h.win_jd[l], h.win_ids[l]);
     CSM_REQUIRE(words < (1LL << 31), "window level too large");
     win_off[l] = win_total;
     win_total += (static_cast<size_t>(words) + 63) / 64 * 64;
   }
   if (win_total) CSM_CUDA(cudaMalloc(&st->d_win, win_total * sizeof(unsigned)));
   for (int l = 1; l < depth; ++l) h.win[l] = st->d_win + win_off[l];
-  // upload cells + LUT into scratch
-  DevBuf& d_cells = ctx->D("stack_cells");
-  DevBuf& d_lut = ctx->D("stack_lut");
-  const size_t ncell = static_cast<size_t>(nx) * ny;
-  CSM_TRY(d_cells.Reserve(ncell * sizeof(uint16_t)));
-  CSM_TRY(d_lut.Reserve(65536));
-  CSM_CUDA(cudaMemcpyAsync(d_cells.p, cells, ncell * sizeof(uint16_t), cudaMemcpyHostToDevice,
-                           ctx->stream));
-  CSM_CUDA(cudaMemcpyAsync(d_lut.p, lut.data(), 65536, cudaMemcpyHostToDevice, ctx->stream));
-  k_stack_level0<<<DivUp(ncell, 256), 256, 0, ctx->stream>>>(
-      d_cells.as<uint16_t>(), d_lut.as<uint8_t>(), st->d_levels + st->level_off[0],
-      static_cast<int>(ncell));
-  CSM_LAUNCH_CHECK();
-  for (int l = 1; l < depth; ++l) {
-    dim3 block(32, 8), grid(DivUp(h.wx[l], 32), DivUp(h.wy[l], 8));
-    k_stack_double<<<grid, block, 0, ctx->stream>>>(st->d_levels + st->level_off[l - 1],
-                                                    h.wx[l - 1], h.wy[l - 1],
-                                                    st->d_levels + st->level_off[l], h.wx[l],
-                                                    h.wy[l], 1 << (l - 1));
-    CSM_LAUNCH_CHECK();
-  }
-  k_stack_decimate4<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-      h.level[top], h.wx[top], h.wy[top], top, st->d_dec, h.dec_lpad[top], h.dec_id[top],
-      h.dec_jd[top], h.dec_ids[top]);
-  CSM_LAUNCH_CHECK();
-  for (int l = 1; l < depth; ++l) {
-    k_stack_window<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
-        h.level[l - 1], h.wx[l - 1], h.wy[l - 1], l, st->d_win + win_off[l], h.win_jd[l],
-        h.win_ids[l]);
-    CSM_LAUNCH_CHECK();
-  }
+  for (int l = 1; l < depth; ++l) st->win_off[l] = win_off[l];
+  CSM_TRY(BuildStack2D(st.get(), cells));
   CSM_CUDA(cudaMalloc(&st->d, sizeof(StackDev)));
   CSM_CUDA(cudaMemcpyAsync(st->d, &h, sizeof(StackDev), cudaMemcpyHostToDevice, ctx->stream));
   CSM_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1492,6 +1552,19 @@ csm_status csm_stack2d_destroy(csm_stack2d* stack) {
   cudaSetDevice(stack->ctx->device);
   cudaStreamSynchronize(stack->ctx->stream);
   delete stack;  // the destructor frees the device buffers
+  return CSM_OK;
+}
+
+// Incremental refresh: the submap's grid received new range data (same limits, same cost
+// bounds); rebuilds every layout in place.  No match may be in flight on this stack
+// (ConstraintBuilder only matches against finished submaps; a trimmed or updated submap
+// goes through DeleteScanMatcher, constraints/constraint_builder_2d.cc:307-316).
+csm_status csm_stack2d_update(csm_stack2d* stack, const uint16_t* cells) {
+  CSM_REQUIRE(stack != nullptr && cells != nullptr, "null pointer");
+  std::lock_guard<std::mutex> lock(stack->ctx->mu);
+  CSM_CUDA(cudaSetDevice(stack->ctx->device));
+  CSM_TRY(BuildStack2D(stack, cells));
+  CSM_CUDA(cudaStreamSynchronize(stack->ctx->stream));
   return CSM_OK;
 }
 

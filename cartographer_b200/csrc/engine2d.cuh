@@ -90,6 +90,7 @@ struct csm_stack2d {
   uint8_t* d_dec = nullptr;
   unsigned* d_win = nullptr;
   size_t level_off[csm::kMaxDepth];
+  size_t win_off[csm::kMaxDepth] = {};   // first word of every child-window level in d_win
   float min_cost = 0.f, max_cost = 0.f;
   // also runs when csm_stack2d_create fails half-way (cudaFree(nullptr) is a no-op)
   ~csm_stack2d() {

@@ -74,6 +74,31 @@ class FastCorrelativeScanMatcher2D:
             C.c_int32(options.branch_and_bound_depth), C.c_int32(device), C.byref(self._h)))
         self.last_stats = None
 
+    @classmethod
+    def from_proto(cls, serialized_grid2d, options, device=0):
+        """Builds the matcher straight from a serialized cartographer.mapping.proto.Grid2D
+        (csm_stack2d_create_from_proto; Grid2D::Grid2D(const proto::Grid2D&) semantics)."""
+        self = cls.__new__(cls)
+        self.options, self.device, self.last_stats = options, device, None
+        buf = (C.c_uint8 * len(serialized_grid2d)).from_buffer_copy(serialized_grid2d)
+        self._h = C.c_void_p()
+        check(lib().csm_stack2d_create_from_proto(buf, C.c_int64(len(serialized_grid2d)),
+                                                  C.c_int32(options.branch_and_bound_depth),
+                                                  C.c_int32(device), C.byref(self._h)))
+        return self
+
+    @classmethod
+    def _adopt(cls, handle, options, device):
+        self = cls.__new__(cls)
+        self.options, self.device, self.last_stats = options, device, None
+        self._h = C.c_void_p(handle)
+        return self
+
+    def update(self, cells):
+        """csm_stack2d_update: the submap's grid changed (same limits); rebuild in place."""
+        cells = np.ascontiguousarray(cells, dtype=np.uint16)
+        check(lib().csm_stack2d_update(self._h, ptr(cells, C.c_uint16)))
+
     def close(self):
         if getattr(self, "_h", None):
             lib().csm_stack2d_destroy(self._h)
@@ -142,6 +167,24 @@ class FastCorrelativeScanMatcher2D:
         bounds = np.empty((S.value, 4), np.int32)
         check(lib().csm_discretize2d(*args, ptr(ds, C.c_int32), ptr(bounds, C.c_int32)))
         return ds, bounds
+
+
+def load_pbstream_matchers2d(path, options, device=0):
+    """csm_pbstream_load_stacks2d: one FastCorrelativeScanMatcher2D per 2D submap of a
+    .pbstream file, in file order.  -> (matchers, [(trajectory_id, submap_index), ...])"""
+    n = C.c_int32(0)
+    check(lib().csm_pbstream_load_stacks2d(path.encode(), C.c_int32(options.branch_and_bound_depth),
+                                           C.c_int32(device), C.c_int32(0), None, None,
+                                           C.byref(n)))
+    count = n.value
+    handles = (C.c_void_p * max(1, count))()
+    ids = np.zeros((max(1, count), 2), np.int32)
+    check(lib().csm_pbstream_load_stacks2d(path.encode(), C.c_int32(options.branch_and_bound_depth),
+                                           C.c_int32(device), C.c_int32(count), handles,
+                                           ptr(ids, C.c_int32), C.byref(n)))
+    matchers = [FastCorrelativeScanMatcher2D._adopt(handles[k], options, device)
+                for k in range(count)]
+    return matchers, [(int(a), int(b)) for a, b in ids[:count]]
 
 
 def match_batch(matchers, clouds, jobs, linear_search_window, angular_search_window):
@@ -397,7 +440,7 @@ def device_count():
 
 __all__ = ["FastCorrelativeScanMatcherOptions2D", "RealTimeCorrelativeScanMatcherOptions",
            "FastCorrelativeScanMatcher2D", "RealTimeCorrelativeScanMatcher2D", "DeviceCloud",
-           "match_batch", "match_batch_sharded", "MultiGpuContext", "RealTimeGrid2D",
+           "match_batch", "load_pbstream_matchers2d", "match_batch_sharded", "MultiGpuContext", "RealTimeGrid2D",
            "kernel_launch_count", "device_count", "JOB2D_DTYPE",
            "RESULT2D_DTYPE", "_lib"]
 
@@ -490,6 +533,28 @@ class FastCorrelativeScanMatcher3D:
             C.c_float(low_resolution_hybrid_grid.resolution), ptr(hist, C.c_float),
             C.c_int32(len(hist)), C.byref(o), C.c_int32(device), C.byref(self._h)))
         self.last_stats = None
+
+    @classmethod
+    def from_proto(cls, serialized_hybrid_grid, serialized_low_resolution_hybrid_grid,
+                   rotational_scan_matcher_histogram, options, device=0):
+        """From two serialized cartographer.mapping.proto.HybridGrid messages
+        (csm_matcher3d_create_from_proto)."""
+        self = cls.__new__(cls)
+        self.options, self.last_stats = options, None
+        hist = np.ascontiguousarray(rotational_scan_matcher_histogram, np.float32).reshape(-1)
+        o = CsmOptions3D(options.branch_and_bound_depth, options.full_resolution_depth,
+                         options.min_rotational_score, options.min_low_resolution_score,
+                         options.linear_xy_search_window, options.linear_z_search_window,
+                         options.angular_search_window)
+        hi, lo = serialized_hybrid_grid, serialized_low_resolution_hybrid_grid
+        bh = (C.c_uint8 * len(hi)).from_buffer_copy(hi)
+        bl = (C.c_uint8 * len(lo)).from_buffer_copy(lo)
+        self._h = C.c_void_p()
+        check(lib().csm_matcher3d_create_from_proto(bh, C.c_int64(len(hi)), bl, C.c_int64(len(lo)),
+                                                    ptr(hist, C.c_float), C.c_int32(len(hist)),
+                                                    C.byref(o), C.c_int32(device),
+                                                    C.byref(self._h)))
+        return self
 
     def close(self):
         if getattr(self, "_h", None):

@@ -95,6 +95,39 @@ csm_status csm_stack2d_destroy(csm_stack2d* stack);
 csm_status csm_stack2d_read_level(const csm_stack2d* stack, int32_t level, uint8_t* out,
                                   int32_t* wide_num_x, int32_t* wide_num_y);
 
+/* Incremental refresh of a stack whose submap grid received new range data (same cell
+ * limits and cost bounds): rebuilds every device layout in place.  No match may be in
+ * flight on the stack. */
+csm_status csm_stack2d_update(csm_stack2d* stack, const uint16_t* cells);
+
+/* ---- ingest from Cartographer's serialized forms ---------------------------- */
+/* Builds the stack straight from a serialized cartographer.mapping.proto.Grid2D
+ * (mapping/proto/grid_2d.proto:23-42; what Submap2D::ToProto / a .pbstream holds), with
+ * the semantics of Grid2D::Grid2D(const proto::Grid2D&) (mapping/2d/grid_2d.cc:75-96,
+ * legacy default bounds :24-44).  No protobuf runtime is involved. */
+csm_status csm_stack2d_create_from_proto(const uint8_t* serialized_grid2d, int64_t size,
+                                         int32_t branch_and_bound_depth, int32_t device,
+                                         csm_stack2d** out);
+/* Host-only decode of the same message (usable without a GPU; cells may be NULL). */
+typedef struct csm_grid2d_info {
+  int32_t num_x_cells, num_y_cells;
+  double resolution, max_x, max_y;
+  float min_correspondence_cost, max_correspondence_cost;
+  int32_t is_tsdf;
+  int32_t reserved;
+} csm_grid2d_info;
+csm_status csm_grid2d_proto_decode(const uint8_t* serialized_grid2d, int64_t size,
+                                   csm_grid2d_info* info, uint16_t* cells,
+                                   int64_t cells_capacity);
+/* Walks a .pbstream (io/proto_stream.cc:27-110: magic, then [u64 size, gzip blob]*; the
+ * blobs after the header are proto::SerializedData, mapping/proto/serialization.proto) and
+ * builds one stack per 2D submap in file order.  submap_ids (may be NULL) receives
+ * {trajectory_id, submap_index} pairs.  *num_loaded is the number of 2D submaps in the
+ * file; if it exceeds max_stacks only the first max_stacks were built. */
+csm_status csm_pbstream_load_stacks2d(const char* path, int32_t branch_and_bound_depth,
+                                      int32_t device, int32_t max_stacks, csm_stack2d** stacks,
+                                      int32_t* submap_ids, int32_t* num_loaded);
+
 /* ---- device-resident scan (sensor::PointCloud) --------------------------- */
 /* A PointCloud (sensor/point_cloud.h:33-92: N x {x,y,z} float32) copied to the
  * device once so that many matches can borrow it (ConstraintBuilder matches one
@@ -273,6 +306,14 @@ csm_status csm_matcher3d_create(const int32_t* hi_indices, const uint16_t* hi_va
                                 int32_t histogram_size, const csm_options3d* options,
                                 int32_t device, csm_matcher3d** out);
 csm_status csm_matcher3d_destroy(csm_matcher3d* matcher);
+/* Same from two serialized cartographer.mapping.proto.HybridGrid messages
+ * (mapping/proto/hybrid_grid.proto:19-28; Submap3D::ToProto), with the semantics of
+ * HybridGrid(const proto::HybridGrid&) (mapping/3d/hybrid_grid.h:473-484). */
+csm_status csm_matcher3d_create_from_proto(const uint8_t* hi_grid, int64_t hi_size,
+                                           const uint8_t* lo_grid, int64_t lo_size,
+                                           const float* submap_histogram, int32_t histogram_size,
+                                           const csm_options3d* options, int32_t device,
+                                           csm_matcher3d** out);
 /* Test hook: one precomputation level as a dense box.  With out == NULL it
  * returns the level's bounding box (lo, dims); otherwise it fills `out`
  * (((z-lo.z)*dims.y + (y-lo.y))*dims.x + (x-lo.x)) for the box passed in. */

@@ -2,6 +2,9 @@
 """Summarise ncu output into small text files for profiles/.
   launch list : python tools/summarize_ncu.py launches <launches.csv>
   full capture: python tools/summarize_ncu.py full <file.ncu-rep>
+  roofline    : python tools/summarize_ncu.py roofline <file.ncu-rep> <bench.json> <out.json>
+                per-step totals (first captured step) of the counters bench.py's roofline
+                block needs: L1 data-pipe LSU wavefronts, L2 bytes, DRAM bytes, time.
 """
 import collections
 import csv
@@ -63,5 +66,58 @@ def full(path):
         print()
 
 
+def roofline(path, bench_json, out_path):
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+
+    def col(r, k, default=0.0):
+        if k not in h:
+            return default
+        v = r[h.index(k)].replace(",", "")
+        try:
+            x = float(v)
+        except ValueError:
+            return default
+        u = units[h.index(k)].strip()
+        return x * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1e-3, "ns": 1e-6, "s": 1e3,
+                    "ms": 1.0}.get(u, 1.0)
+
+    # launches in capture order; a step starts at every lowest-resolution pass
+    launches_ = [(r[h.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0], r)
+                 for r in rows[2:]]
+    starts = [i for i, (n, _) in enumerate(launches_) if n.startswith("k_score_top")]
+    lo = starts[0] if starts else 0
+    hi = starts[1] if len(starts) > 1 else len(launches_)
+    bench = json.loads(open(bench_json).read().strip().splitlines()[-1])
+    live = bench.get("roofline", {}).get("kernels", {})
+    res = {}
+    for name, r in launches_[lo:hi]:
+        e = res.setdefault(name, {"launches_per_step": 0, "time_ms": 0.0,
+                                  "l1_lsu_wavefronts_per_step": 0.0, "lts_bytes_per_step": 0.0,
+                                  "dram_bytes_per_step": 0.0, "_pct_w": 0.0})
+        t = col(r, "gpu__time_duration.sum")
+        e["launches_per_step"] += 1
+        e["time_ms"] += t
+        e["l1_lsu_wavefronts_per_step"] += col(r, "l1tex__data_pipe_lsu_wavefronts.sum")
+        e["lts_bytes_per_step"] += 32.0 * col(r, "lts__t_sectors.sum")
+        e["dram_bytes_per_step"] += col(r, "dram__bytes_read.sum") + col(r, "dram__bytes_write.sum")
+        e["_pct_w"] += t * col(r, "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed")
+    for name, e in res.items():
+        e["l1_lsu_pct"] = e.pop("_pct_w") / e["time_ms"] if e["time_ms"] else None
+        e["units_per_step"] = live.get(name, {}).get("candidates")
+        e["source"] = ("ncu --set full --clock-control none, first captured step of "
+                       "`python bench.py --steps 1 --warmup 1` (%s); units_per_step from the "
+                       "same session's bench line" % path.split("/")[-1])
+    json.dump(res, open(out_path, "w"), indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    cmd = sys.argv[1]
+    if cmd == "roofline":
+        roofline(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[cmd](sys.argv[2])
