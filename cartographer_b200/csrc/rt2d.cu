@@ -530,11 +530,17 @@ void PrepareJob(const RtHostJob& job, const RtGridDev& G, const RtParams& P, dou
   jd->x0 = jd->y0 = 0;
   if (rx1 < rx0 || ry1 < ry0) {       // the scan cannot reach the grid: any box will do
     plan->smem = true;
-  } else if (rx1 - rx0 + 1 <= G.bw && ry1 - ry0 + 1 <= G.bh) {
-    plan->smem = true;
-    jd->x0 = static_cast<int>(rx0);
-    jd->y0 = static_cast<int>(ry0);
+  } else {
+    // the box starts on a 16-byte boundary of its row (8 cells): TMA global addresses
+    const long long ax0 = rx0 & ~7LL;
+    if (rx1 - ax0 + 1 <= G.bw && ry1 - ry0 + 1 <= G.bh) {
+      plan->smem = true;
+      jd->x0 = static_cast<int>(ax0);
+      jd->y0 = static_cast<int>(ry0);
+    }
   }
+  static const bool origin0_only = getenv("CSM_RT_ORIGIN0") != nullptr;   // debug switch
+  if (origin0_only && (jd->x0 != 0 || jd->y0 != 0)) plan->smem = false;
 }
 
 int NumAngular(const RtHostJob& job, double resolution, double angular_window) {
