@@ -19,14 +19,13 @@ import numpy as np
 from benchmarks import synthetic
 
 
-def run(args, D, workload, sample_clocks):
+def run(args, D, workload, sample_clocks, rings=64, az=1024, base_sub=500, base_node=100):
     torch = D.torch
     from cartographer_b200 import scan_matching as sm
     rank, world = D.rank, D.world
     ctx = D.make_context(sm)
-    n_sub = max(world, int(round(500 * args.scale)))
-    n_node = max(2, int(round(100 * args.scale)))
-    rings, az = 64, 1024
+    n_sub = max(world, int(round(base_sub * args.scale)))
+    n_node = max(2, int(round(base_node * args.scale)))
     min_score = 0.55
     o3 = sm.FastCorrelativeScanMatcherOptions3D(min_rotational_score=0.45)
     distinct_sub = min(n_sub, 2)

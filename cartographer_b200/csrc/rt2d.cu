@@ -37,7 +37,10 @@ namespace csm {
 
 constexpr int kRtThreads = 256;
 constexpr int kRtWarps = kRtThreads / 32;
-constexpr int kRtAcc = 4;                    // candidates per lane and pass
+// candidates per lane and pass: 1 for windows of <= 32 offsets (the default +-0.1 m window
+// has 25), 4 for larger ones — a template parameter, so the common case carries no
+// predicated-off accumulator code (the first version executed all four and spent 67
+// instructions per warp and point instead of ~17; profiles/r2_ncu_full_k_rt_match_v1_acc4.txt)
 constexpr int kRtTileBytes = 100 * 1024;     // staged box (2 CTAs per SM)
 
 struct RtGridDev {
@@ -118,7 +121,7 @@ __device__ __forceinline__ void RotateZ(float w, float s, float vx, float vy, fl
 
 // kForm: 0 = ProbabilityGrid staged in shared memory by TMA, 1 = ProbabilityGrid through
 // read-only global gathers, 2 = TSDF2D (two global cell arrays).
-template <int kForm>
+template <int kForm, int kRtAcc>
 __global__ void __launch_bounds__(kRtThreads, 2)
 k_rt_match(const __grid_constant__ CUtensorMap tmap, const RtGridDev G, const RtParams P,
            const RtJobDev* __restrict__ jobs, int num_jobs, int total_items,
@@ -216,34 +219,38 @@ k_rt_match(const __grid_constant__ CUtensorMap tmap, const RtGridDev G, const Rt
 #pragma unroll
             for (int a = 0; a < kRtAcc; ++a) {
               if (a >= acc_n) continue;   // warp-uniform
+              // branch-free: an out-of-range candidate reads cell 0 of the staged box /
+              // the grid and discards it
               const int x = cx + xo[a], y = cy + yo[a];
               const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(G.nx) &&
                               static_cast<unsigned>(y) < static_cast<unsigned>(G.ny);
               if (kForm == 2) {
                 // TSDF (real_time...2d.cc:38-59): outside the limits tsd = min, weight = 0
-                float tsd = P.min_tsd, w = 0.f;
-                if (in) {
-                  const size_t flat = static_cast<size_t>(y) * G.pitch + x;
-                  const int tv = __ldg(G.cells + flat) & 0x7fff, wv = __ldg(G.wcells + flat) & 0x7fff;
-                  tsd = tv == 0 ? P.min_tsd
-                                : __fadd_rn(__fmul_rn(__int2float_rn(tv), P.tsd_scale), P.tsd_bias);
-                  w = wv == 0 ? 0.f : __fadd_rn(__fmul_rn(__int2float_rn(wv), P.w_scale), P.w_bias);
-                }
+                const size_t flat = in ? static_cast<size_t>(y) * G.pitch + x : 0;
+                const int tv = __ldg(G.cells + flat) & 0x7fff, wv = __ldg(G.wcells + flat) & 0x7fff;
+                const float tsd_in =
+                    tv == 0 ? P.min_tsd
+                            : __fadd_rn(__fmul_rn(__int2float_rn(tv), P.tsd_scale), P.tsd_bias);
+                const float w_in =
+                    wv == 0 ? 0.f : __fadd_rn(__fmul_rn(__int2float_rn(wv), P.w_scale), P.w_bias);
+                const float tsd = in ? tsd_in : P.min_tsd, w = in ? w_in : 0.f;
                 const float normalized = __fdiv_rn(__fsub_rn(P.truncation, fabsf(tsd)), P.truncation);
                 sum[a] = __fadd_rn(sum[a], __fmul_rn(normalized, w));
                 wsum[a] = __fadd_rn(wsum[a], w);
               } else {
                 // ProbabilityGrid::GetProbability (2d/probability_grid.cc:78-82)
-                float prob = P.min_probability;
-                if (in) {
-                  const int value =
-                      (kForm == 0 ? s_tile[(y - tile_y0) * G.bw + (x - tile_x0)]
-                                  : __ldg(G.cells + static_cast<size_t>(y) * G.pitch + x)) & 0x7fff;
-                  const float cost = value == 0 ? P.max_cost
-                                                : __fadd_rn(__fmul_rn(__int2float_rn(value), P.k_scale),
-                                                            P.cost_bias);
-                  prob = __fsub_rn(1.f, cost);
+                int value;
+                if (kForm == 0) {
+                  const int idx = in ? (y - tile_y0) * G.bw + (x - tile_x0) : 0;
+                  value = s_tile[idx] & 0x7fff;
+                } else {
+                  const size_t flat = in ? static_cast<size_t>(y) * G.pitch + x : 0;
+                  value = __ldg(G.cells + flat) & 0x7fff;
                 }
+                const float cost = value == 0 ? P.max_cost
+                                              : __fadd_rn(__fmul_rn(__int2float_rn(value), P.k_scale),
+                                                          P.cost_bias);
+                const float prob = in ? __fsub_rn(1.f, cost) : P.min_probability;
                 sum[a] = __fadd_rn(sum[a], prob);
               }
             }
@@ -649,24 +656,26 @@ csm_status RtRun(Ctx* ctx, const csm_rt_grid2d* grid, const RtHostJob* jobs, int
   const int form = grid->d_wcells ? 2 : ((all_smem && !no_tma) ? 0 : 1);
   const size_t smem = form == 0 ? static_cast<size_t>(G.bw) * G.bh * 2 : 0;
   int per_sm = 1;
-#define CSM_RT_LAUNCH(F)                                                                        \
+#define CSM_RT_LAUNCH(F, A)                                                                     \
   do {                                                                                          \
     if (smem > 48 * 1024)                                                                       \
-      CSM_CUDA(cudaFuncSetAttribute(k_rt_match<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      CSM_CUDA(cudaFuncSetAttribute(k_rt_match<F, A>,                                           \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,                \
                                     static_cast<int>(smem)));                                   \
-    CSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rt_match<F>, kRtThreads,  \
-                                                           smem));                              \
+    CSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rt_match<F, A>,           \
+                                                           kRtThreads, smem));                  \
     const int grid_dim = std::max(1, std::min((total_items + kRtWarps - 1) / kRtWarps,          \
                                               ctx->sm_count * std::max(1, per_sm)));            \
-    k_rt_match<F><<<grid_dim, kRtThreads, smem, s>>>(                                           \
+    k_rt_match<F, A><<<grid_dim, kRtThreads, smem, s>>>(                                        \
         grid->tmap, G, P, reinterpret_cast<const RtJobDev*>(d + off_jobs), num, total_items,    \
         reinterpret_cast<const float*>(d), reinterpret_cast<const float2*>(d + off_trig),       \
         reinterpret_cast<const double*>(d + off_w), d_best.as<unsigned long long>());           \
   } while (0)
   ProfBegin(ctx);
-  if (form == 0) CSM_RT_LAUNCH(0);
-  else if (form == 1) CSM_RT_LAUNCH(1);
-  else CSM_RT_LAUNCH(2);
+  const bool one_acc = P.per_scan <= 32;
+  if (form == 0) { if (one_acc) CSM_RT_LAUNCH(0, 1); else CSM_RT_LAUNCH(0, 4); }
+  else if (form == 1) { if (one_acc) CSM_RT_LAUNCH(1, 1); else CSM_RT_LAUNCH(1, 4); }
+  else { if (one_acc) CSM_RT_LAUNCH(2, 1); else CSM_RT_LAUNCH(2, 4); }
 #undef CSM_RT_LAUNCH
   CSM_LAUNCH_CHECK();
   ProfEnd(ctx, form == 0 ? "k_rt_match_tma" : (form == 1 ? "k_rt_match_gather" : "k_rt_match_tsdf"),

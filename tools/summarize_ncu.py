@@ -101,12 +101,19 @@ def roofline(path, bench_json, out_path):
         t = col(r, "gpu__time_duration.sum")
         e["launches_per_step"] += 1
         e["time_ms"] += t
-        e["l1_lsu_wavefronts_per_step"] += col(r, "l1tex__data_pipe_lsu_wavefronts.sum")
+        # one data-pipe wavefront per clock per SM is the peak, so
+        # wavefronts = pct / 100 * elapsed SM cycles * 148 (the raw .sum counter is not in --set full)
+        e["l1_lsu_wavefronts_per_step"] += (
+            col(r, "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed") / 100.0 *
+            col(r, "sm__cycles_elapsed.avg") * 148)
+        e["issue_pct_w"] = e.get("issue_pct_w", 0.0) + t * col(
+            r, "smsp__issue_active.avg.pct_of_peak_sustained_active")
         e["lts_bytes_per_step"] += 32.0 * col(r, "lts__t_sectors.sum")
         e["dram_bytes_per_step"] += col(r, "dram__bytes_read.sum") + col(r, "dram__bytes_write.sum")
         e["_pct_w"] += t * col(r, "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed")
     for name, e in res.items():
         e["l1_lsu_pct"] = e.pop("_pct_w") / e["time_ms"] if e["time_ms"] else None
+        e["issue_active_pct"] = e.pop("issue_pct_w", 0.0) / e["time_ms"] if e["time_ms"] else None
         e["units_per_step"] = live.get(name, {}).get("candidates")
         e["source"] = ("ncu --set full --clock-control none, first captured step of "
                        "`python bench.py --steps 1 --warmup 1` (%s); units_per_step from the "
