@@ -198,7 +198,9 @@ def roofline_block(kernels, bytes_per_unit, sm_mhz):
         out["hbm"] = {"achieved": dram / sec / 1e9, "peak": peak, "frac": dram / sec / 1e9 / peak}
     else:
         out["traffic"] = None
-    if static.get("l1_lsu_wavefronts_per_step") is not None:
+    lsu_pct = static.get("l1_lsu_pct") or 0.0
+    issue_pct = static.get("issue_active_pct") or 0.0
+    if static.get("l1_lsu_wavefronts_per_step") and lsu_pct >= issue_pct:
         wf = static["l1_lsu_wavefronts_per_step"] * scale
         peak_wf = 148 * clk_hz     # one data-pipe wavefront per clock per SM
         out["bound"] = "l1tex_lsu_wavefronts"
@@ -206,15 +208,24 @@ def roofline_block(kernels, bytes_per_unit, sm_mhz):
         out["peak_bound"] = peak_wf
         out["bound_unit"] = "wavefronts/s"
         out["frac"] = wf / sec / peak_wf
-        out["ncu_pct_of_peak"] = static.get("l1_lsu_pct")
-        if static.get("lts_bytes_per_step") is not None:
-            out["l2_GBps"] = static["lts_bytes_per_step"] * scale / sec / 1e9
-        out["source"] = static.get("source")
+        out["ncu_pct_of_peak"] = lsu_pct
+    elif static.get("inst_per_step"):
+        inst = static["inst_per_step"] * scale
+        peak_inst = 148 * 4 * clk_hz   # one warp instruction per clock per SM sub-partition
+        out["bound"] = "issue_slots"
+        out["achieved"] = inst / sec
+        out["peak_bound"] = peak_inst
+        out["bound_unit"] = "warp instructions/s"
+        out["frac"] = inst / sec / peak_inst
+        out["ncu_pct_of_peak"] = issue_pct
     else:
         # no capture committed for this kernel: the HBM reading is all there is
         out["bound"] = "hbm"
         out["achieved"] = out.get("hbm", {}).get("achieved")
         out["frac"] = out.get("hbm", {}).get("frac")
+    if static.get("lts_bytes_per_step") is not None:
+        out["l2_GBps"] = static["lts_bytes_per_step"] * scale / sec / 1e9
+    out["source"] = static.get("source")
     return out
 
 

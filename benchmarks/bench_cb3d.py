@@ -35,7 +35,10 @@ def run(args, D, workload, sample_clocks, rings=64, az=1024, base_sub=500, base_
     for s in range(distinct_sub):
         hi, lo, sub_hist, wd = synthetic.make_submap3d(40 + s, 40.0, rings, az, 20.0)
         rng = np.random.RandomState(500 + s)
-        nodes = [synthetic.make_node3d(wd, rng, rings, az, 20.0, seed=7000 + 100 * s + k)
+        # revisits close to the mapping poses: most same-building pairs are real matches (the
+        # expensive case: full descent + low-resolution gate), cross-building pairs are not
+        nodes = [synthetic.make_node3d(wd, rng, rings, az, 20.0, seed=7000 + 100 * s + k,
+                                       jitter=0.15)
                  for k in range(max(1, distinct_node // distinct_sub))]
         subs.append(dict(hi=hi, lo=lo, hist=sub_hist, nodes=nodes))
     gen_s = time.perf_counter() - t0

@@ -358,13 +358,14 @@ def make_submap3d(seed, size_m=40.0, rings=16, azimuths=2048, max_range=20.0, ma
 
 
 def make_node3d(world, rng, rings=16, azimuths=2048, max_range=20.0, seed=0, hist_size=120,
-                lo_res=0.45):
+                lo_res=0.45, jitter=0.7):
     """A node to match against a submap: one lidar scan taken near one of the poses
-    the submap was built from (a revisit, as in loop closure)."""
+    the submap was built from (a revisit, as in loop closure).  `jitter` (m) is how far
+    from that pose: smaller = more of the scan falls on mapped surfaces."""
     occ, cell, origin, map_poses = world
     for _ in range(200):
         base = map_poses[rng.randint(len(map_poses))]
-        pose = base + np.array([rng.uniform(-0.7, 0.7), rng.uniform(-0.7, 0.7), 0.0,
+        pose = base + np.array([rng.uniform(-jitter, jitter), rng.uniform(-jitter, jitter), 0.0,
                                 rng.uniform(-0.4, 0.4)])
         c = np.floor((pose[:3] - origin) / cell).astype(int)
         if not occ[max(0, c[2] - 2):c[2] + 3, c[1] - 2:c[1] + 3, c[0] - 2:c[0] + 3].any():

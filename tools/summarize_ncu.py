@@ -86,8 +86,14 @@ def roofline(path, bench_json, out_path):
                     "ms": 1.0}.get(u, 1.0)
 
     # launches in capture order; a step starts at every lowest-resolution pass
-    launches_ = [(r[h.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0], r)
-                 for r in rows[2:]]
+    def short(full_name):
+        n = full_name.split("(")[0].replace("void ", "")
+        base = n.split("<")[0]
+        if base == "k_rt_match" and "<" in n:   # the library profiles the three forms by name
+            form = n.split("<")[1].split(",")[0].strip()
+            base += {"0": "_tma", "1": "_gather", "2": "_tsdf"}.get(form, "")
+        return base
+    launches_ = [(short(r[h.index("Kernel Name")]), r) for r in rows[2:]]
     starts = [i for i, (n, _) in enumerate(launches_) if n.startswith("k_score_top")]
     lo = starts[0] if starts else 0
     hi = starts[1] if len(starts) > 1 else len(launches_)
@@ -108,6 +114,7 @@ def roofline(path, bench_json, out_path):
             col(r, "sm__cycles_elapsed.avg") * 148)
         e["issue_pct_w"] = e.get("issue_pct_w", 0.0) + t * col(
             r, "smsp__issue_active.avg.pct_of_peak_sustained_active")
+        e["inst_per_step"] = e.get("inst_per_step", 0.0) + col(r, "smsp__inst_executed.sum")
         e["lts_bytes_per_step"] += 32.0 * col(r, "lts__t_sectors.sum")
         e["dram_bytes_per_step"] += col(r, "dram__bytes_read.sum") + col(r, "dram__bytes_write.sum")
         e["_pct_w"] += t * col(r, "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed")
@@ -118,7 +125,12 @@ def roofline(path, bench_json, out_path):
         e["source"] = ("ncu --set full --clock-control none, first captured step of "
                        "`python bench.py --steps 1 --warmup 1` (%s); units_per_step from the "
                        "same session's bench line" % path.split("/")[-1])
-    json.dump(res, open(out_path, "w"), indent=1)
+    import os
+    merged = {}
+    if os.path.exists(out_path):   # several captures (one per workload) share the file
+        merged = json.load(open(out_path))
+    merged.update(res)
+    json.dump(merged, open(out_path, "w"), indent=1)
     print(json.dumps(res, indent=1))
 
 
