@@ -366,6 +366,17 @@ class Dist:
             self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
         return [float(v) for v in t]
 
+    def gather_stats(self, step_seconds):
+        """[[median ms, max ms] per rank] of a leg's timed steps (rank order)."""
+        v = [1e3 * float(np.median(step_seconds)), 1e3 * float(np.max(step_seconds))] \
+            if len(step_seconds) else [0.0, 0.0]
+        t = self.torch.tensor(v, dtype=self.torch.float64, device=self.dev)
+        if self.dist is None:
+            return [[round(x, 3) for x in v]]
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [[round(float(x), 3) for x in o] for o in out]
+
     def finish(self):
         if self.dist is not None:
             self.dist.barrier()
@@ -401,6 +412,11 @@ def bench_full_submap(args, D):
     jobs_all["cloud_index"] = np.arange(world * MATCHES_PER_STEP)
     jobs_all["full_submap"] = 1
     jobs_all["min_score"] = MIN_SCORE
+    no_collective = bool(os.environ.get("CSM_BENCH_NO_COLLECTIVE"))
+    jobs_local = np.zeros(MATCHES_PER_STEP, sm.JOB2D_DTYPE)
+    jobs_local["cloud_index"] = np.arange(MATCHES_PER_STEP)
+    jobs_local["full_submap"] = 1
+    jobs_local["min_score"] = MIN_SCORE
     pad_lo = [None] * (rank * MATCHES_PER_STEP)
     pad_hi = [None] * ((world - 1 - rank) * MATCHES_PER_STEP)
 
@@ -409,12 +425,17 @@ def bench_full_submap(args, D):
         (the others are never dereferenced here)."""
         own = (step_clouds if step_clouds is not None
                else clouds[step * MATCHES_PER_STEP:(step + 1) * MATCHES_PER_STEP])
+        if no_collective:   # diagnostic: the local searches alone
+            res, st = sm.match_batch([matcher], list(own), jobs_local, LIN, ANG)
+            full = np.zeros(world * MATCHES_PER_STEP, sm.RESULT2D_DTYPE)
+            full[rank * MATCHES_PER_STEP:(rank + 1) * MATCHES_PER_STEP] = res
+            return full, st
         return sm.match_batch_sharded(ctx, matchers_g, pad_lo + list(own) + pad_hi, jobs_all,
                                       LIN, ANG, owner)
 
     # ---- device-resident leg (value) -------------------------------------------
     launches0 = sm.kernel_launch_count()
-    step_s, cand, found, dev_ms, host_syncs = [], 0, 0, 0.0, 0
+    step_s, cand, found, dev_ms, host_syncs, coll_ms = [], 0, 0, 0.0, 0, 0.0
     mine = slice(rank * MATCHES_PER_STEP, (rank + 1) * MATCHES_PER_STEP)
     results_by_step = []
     for it in range(total_steps):
@@ -431,8 +452,11 @@ def bench_full_submap(args, D):
             cand += st["candidates_scored"]
             found += int(res[mine]["found"].sum())
             dev_ms += st["device_ms"]
+            coll_ms += st["collective_ms"]
             host_syncs = max(host_syncs, st["host_syncs"])
     launches = sm.kernel_launch_count() - launches0
+    # per-step diagnostics: every rank's median / max step and the library-side split
+    diag_v = D.gather_stats(step_s)
     elapsed = D.reduce([float(sum(step_s))], "MAX")[0]
     cand_all, found_all = D.reduce([float(cand), float(found)], "SUM")
     matches_all = world * args.steps * MATCHES_PER_STEP
@@ -453,6 +477,7 @@ def bench_full_submap(args, D):
         if it >= args.warmup:
             e2e_s.append(dt)
             e2e_c += st_e["candidates_scored"]
+    diag_e = D.gather_stats(e2e_s)
     e2e_elapsed = D.reduce([float(sum(e2e_s))], "MAX")[0]
     e2e_value = D.reduce([float(e2e_c)], "SUM")[0] / e2e_elapsed
     h2d = MATCHES_PER_STEP * 1081 * 12
@@ -525,11 +550,15 @@ def bench_full_submap(args, D):
                        "parallelism": "submap-sharded x%d" % world},
             "constraints_per_sec": matches_all / elapsed,
             "device_ms_per_step": dev_ms / max(1, args.steps),
+            "collective_ms_per_step": coll_ms / max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_elapsed / max(1, args.steps)},
             "gpu_launches": int(launches), "host_syncs_per_batch": host_syncs, "clocks": clocks,
             "parity_checked": parity_checked, "parity_failed": parity_failed,
+            "step_ms_per_rank": {"value": diag_v, "e2e": diag_e,
+                                 "rank0_value_steps": [round(1e3 * x, 2) for x in step_s],
+                                 "note": "[median, max] of each rank's timed steps"},
             "roofline": roofline, "cpu_baseline": cpu}))
     ctx.close()
 

@@ -23,7 +23,7 @@ class CsmStats(C.Structure):
                 ("num_scans", C.c_int32), ("best_scan_index", C.c_int32),
                 ("best_x_offset", C.c_int32), ("best_y_offset", C.c_int32),
                 ("host_tie_resolves", C.c_int32), ("host_syncs", C.c_int32),
-                ("device_ms", C.c_float), ("reserved_f", C.c_float)]
+                ("device_ms", C.c_float), ("collective_ms", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}

@@ -11,6 +11,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
+
 #include "engine2d.cuh"
 
 namespace csm {
@@ -223,8 +225,12 @@ csm_status csm_cb_batch2d_run(csm_ctx* ctx, const csm_stack2d* const* stacks, in
     else std::memset(&send[i].r, 0, sizeof(csm_result2d));
   }
   std::vector<Record> recv(static_cast<size_t>(max_per_rank) * W);
+  const auto t0 = std::chrono::steady_clock::now();
   CSM_TRY(csm_ctx_allgather(ctx, send.data(), static_cast<int64_t>(sizeof(Record)) * max_per_rank,
                             recv.data()));
+  if (stats)
+    stats->collective_ms +=
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   for (const Record& rec : recv)
     if (rec.job >= 0 && rec.job < num_jobs) results[rec.job] = rec.r;
   return CSM_OK;

@@ -64,7 +64,9 @@ struct DevBuf {
     if (p) CSM_CUDA(cudaFree(p));
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
+    // 50 % headroom: batches of a queue differ by tens of per cent in their scan counts, and
+    // every regrowth is a cudaFree + cudaMalloc pair (a device-wide synchronisation each)
+    size_t want = bytes + bytes / 2 + 256;
     CSM_CUDA(cudaMalloc(&p, want));
     cap = want;
     return CSM_OK;

@@ -59,7 +59,7 @@ typedef struct csm_stats {
   int32_t host_tie_resolves;            /* top-level std::sort replays */
   int32_t host_syncs;                   /* stream synchronisations inside the call (2D batch: 1 + ties) */
   float device_ms;                      /* CUDA-event time of the device work of this call */
-  float reserved_f;
+  float collective_ms;                  /* host wall time inside the ncclAllGather step (csm_cb_batch*_run) */
 } csm_stats;
 
 /* ---- device / context ---------------------------------------------------- */
