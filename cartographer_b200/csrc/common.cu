@@ -15,6 +15,16 @@ void SetError(const char* fmt, ...) {
 static std::mutex g_ctx_mu;
 static std::map<int, std::unique_ptr<Ctx>> g_ctx;
 
+// The stream-ordered pool keeps what the workspaces release (no trimming at synchronisation
+// points), so regrowths and the next call's allocations are served from the pool.
+static void KeepPoolMemory(int device) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+}
+
 csm_status GetCtx(int device, Ctx** out) {
   std::lock_guard<std::mutex> lock(g_ctx_mu);
   auto it = g_ctx.find(device);
@@ -26,6 +36,7 @@ csm_status GetCtx(int device, Ctx** out) {
   CSM_CUDA(cudaGetDeviceCount(&count));
   CSM_REQUIRE(device >= 0 && device < count, "device index out of range");
   CSM_CUDA(cudaSetDevice(device));
+  KeepPoolMemory(device);
   std::unique_ptr<Ctx> ctx(new Ctx);
   ctx->device = device;
   cudaDeviceProp prop;
@@ -40,6 +51,7 @@ csm_status GetCtx(int device, Ctx** out) {
 }
 
 static csm_status NewCtx(int device, std::unique_ptr<Ctx>* out) {
+  KeepPoolMemory(device);
   std::unique_ptr<Ctx> ctx(new Ctx);
   ctx->device = device;
   cudaDeviceProp prop;

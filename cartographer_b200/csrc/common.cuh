@@ -59,15 +59,25 @@ extern std::atomic<int64_t> g_launches;
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  cudaStream_t stream = nullptr;   // set by Ctx::D: the workspace lives on that lane's stream
   csm_status Reserve(size_t bytes) {
     if (bytes <= cap) return CSM_OK;
-    if (p) CSM_CUDA(cudaFree(p));
-    p = nullptr;
-    cap = 0;
-    // 50 % headroom: batches of a queue differ by tens of per cent in their scan counts, and
-    // every regrowth is a cudaFree + cudaMalloc pair (a device-wide synchronisation each)
-    size_t want = bytes + bytes / 2 + 256;
-    CSM_CUDA(cudaMalloc(&p, want));
+    // 50 % headroom: batches of a queue differ widely in their scan counts.  Workspaces of a
+    // lane are (re)allocated from the stream-ordered pool: a regrowth is then a pair of
+    // stream operations, not a cudaFree + cudaMalloc pair that synchronises the whole device
+    // (measured as 10 ms outlier steps at 8 GPUs, profiles/r2_bench_n8_diag.json).
+    const size_t want = bytes + bytes / 2 + 256;
+    if (stream) {
+      if (p) CSM_CUDA(cudaFreeAsync(p, stream));
+      p = nullptr;
+      cap = 0;
+      CSM_CUDA(cudaMallocAsync(&p, want, stream));
+    } else {
+      if (p) CSM_CUDA(cudaFree(p));
+      p = nullptr;
+      cap = 0;
+      CSM_CUDA(cudaMalloc(&p, want));
+    }
     cap = want;
     return CSM_OK;
   }
@@ -102,7 +112,11 @@ struct Ctx {
   std::mutex mu;
   std::map<std::string, DevBuf> dev;      // named workspaces
   std::map<std::string, PinnedBuf> pin;
-  DevBuf& D(const char* name) { return dev[name]; }
+  DevBuf& D(const char* name) {
+    DevBuf& b = dev[name];
+    b.stream = stream;
+    return b;
+  }
   PinnedBuf& P(const char* name) { return pin[name]; }
   // Recycled device buffers of destroyed point clouds (guarded by `mu`): node scans
   // come and go at sensor rate, and cudaMalloc / cudaFree serialise the whole device.
