@@ -44,7 +44,7 @@ from benchmarks import synthetic  # noqa: E402
 
 BYTES_PER_CANDIDATE = 1081 * (8 + 1) + 16   # N*(8+1)+16 @ N=1081
 BYTES_PER_CANDIDATE_RT = 1081 * (8 + 2) + 16
-MATCHES_PER_STEP = 32
+MATCHES_PER_STEP = 64
 MIN_SCORE = 0.6          # pose_graph.lua:28 global_localization_min_score
 DEPTH = 7                # pose_graph.lua:27
 LIN, ANG = 7.0, math.radians(30.0)

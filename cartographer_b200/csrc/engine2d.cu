@@ -2015,7 +2015,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
   // <= kChunk nodes from the end of its queue (k_level_begin), picks the kernel form on the
   // device and appends the survivors to the next queue; nothing is read back in between.
   // A queue below the top starts the sweep empty and receives <= 4 * kChunk children, so it
-  // cannot overflow.  Only if a level held more than one chunk (frontiers > 4 M nodes) does
+  // cannot overflow.  Only if a level held more than one chunk (frontiers > 8 M nodes) does
   // the host continue, deepest non-empty level first, with one read-back per extra chunk.
   int depth_max = 0;
   for (int j = 0; j < num_jobs; ++j)
@@ -2024,7 +2024,7 @@ static csm_status RunBatch2D(Ctx* ctx, const csm_stack2d* const* stacks, int num
     CSM_REQUIRE(stacks[jobs[j].stack_index]->h.depth == depth_max,
                 "internal: sub-batches are grouped by branch_and_bound_depth");
   const int hmax = depth_max - 1;
-  const int kChunk = 1 << 22;
+  const int kChunk = 1 << 23;
   const int kQueueCap = 4 * kChunk;
   const int kLeafCap = 1 << 22;
   const int kLatticeMin = 16384;  // smaller frontiers: the warp-per-parent kernel has a
