@@ -265,8 +265,10 @@ def run_reference(args):
         "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak" if args.config == 2 else "strong", "vs_baseline": None,
         "dtype": "u8/int32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "matches_per_step": per_step,
-                   "min_score": min_score, "oracle_stack_build_s": build_s},
+        "config": {"workload": WORKLOADS[args.config], "matches_per_step_per_gpu": per_step,
+                   "min_score": min_score, "l2": "n/a (host cores)",
+                   "parallelism": "%d host threads, one search per thread" % threads,
+                   "oracle_stack_build_s": build_s},
         "constraints_per_sec": tot_m / tot_s,
         "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": threads,
                          "kind": "port",

@@ -213,6 +213,7 @@ enum : int {
   kC3Leaf = 16,      // leaves recorded
   kC3Best = 17,      // optimal leaves after compaction
   kC3Scans = 18,     // scans that passed the rotational filter
+  kC3TopBest = 19,   // largest lowest-resolution sum of the match (dive selection)
   kC3Overflow = 20,
   kC3Start = 25,     // chunk of the current level: first node / count
   kC3Count = 26,
@@ -407,7 +408,8 @@ __device__ float LowResScore(const Job3& jb, int scan, int ox, int oy, int oz, f
 
 // Lowest-resolution pass: one CTA per candidate, generation order
 // scan-major, z outer, y, x inner (:315-327).
-__global__ void __launch_bounds__(kT3) k3_score_top(Job3 jb, int* __restrict__ top_sum) {
+__global__ void __launch_bounds__(kT3)
+k3_score_top(Job3 jb, int* __restrict__ top_sum, int* __restrict__ ctl) {
   __shared__ int s_red[kT3 / 32 * 8];
   const int per_scan = jb.nxc * jb.nxc * jb.nzc;
   const int c = blockIdx.x;
@@ -421,13 +423,16 @@ __global__ void __launch_bounds__(kT3) k3_score_top(Job3 jb, int* __restrict__ t
   int sums[8];
   ScoreOct(jb, scan, hmax, -jb.wxy + (kx << hmax), -jb.wxy + (ky << hmax), -jb.wz + (kz << hmax),
            0, 1u, sums, s_red);
-  if (threadIdx.x == 0) top_sum[c] = sums[0];
+  if (threadIdx.x == 0) {
+    top_sum[c] = sums[0];
+    atomicMax(&ctl[kC3TopBest], sums[0]);
+  }
 }
 
 // Greedy dive of one scan's best lowest-resolution candidate; a leaf only raises
 // the bound if it passes the low-resolution gate (:389-397).
 __global__ void __launch_bounds__(kT3)
-k3_dive(Job3 jb, const int* __restrict__ top_sum, unsigned* __restrict__ lb,
+k3_dive(Job3 jb, const int* __restrict__ top_sum, float dive_ratio, unsigned* __restrict__ lb,
         unsigned long long* __restrict__ counters) {
   __shared__ int s_red[kT3 / 32 * 8];
   __shared__ float s_buf[kT3];
@@ -448,6 +453,9 @@ k3_dive(Job3 jb, const int* __restrict__ top_sum, unsigned* __restrict__ lb,
   const int best = s_pick[0];
   int r = s_pick[1];
   if (!(ToScore3(best, jb.n_hi) > jb.min_score)) return;
+  // only scans whose best bound is close to the match's best are worth a dive (any subset
+  // keeps the bound valid; as in the 2D engine this keeps it tight at a fraction of the cost)
+  if (static_cast<float>(best) < dive_ratio * static_cast<float>(jb.ctl[kC3TopBest])) return;
   int h = jb.stack->depth - 1;
   const int kz = r / (jb.nxc * jb.nxc);
   r -= kz * jb.nxc * jb.nxc;
@@ -1192,11 +1200,12 @@ static csm_status Run3D(Ctx* ctx, const csm_matcher3d* m, const csm_node3d* node
   // ---- lowest-resolution pass + dives (grids sized for all angles; filtered-out scans exit) ----
   CSM_TRY(d_top.Reserve(sizeof(int) * max_top));
   ProfBegin(ctx);
-  k3_score_top<<<static_cast<int>(max_top), kT3, 0, s>>>(jb, d_top.as<int>());
+  k3_score_top<<<static_cast<int>(max_top), kT3, 0, s>>>(jb, d_top.as<int>(), ictr);
   CSM_LAUNCH_CHECK();
   ProfEnd(ctx, "k3_score_top", static_cast<double>(max_top));
   ProfBegin(ctx);
-  k3_dive<<<A, kT3, 0, s>>>(jb, d_top.as<int>(), lb, ctr);
+  static const float dive_ratio = getenv("CSM_DIVE_RATIO3") ? atof(getenv("CSM_DIVE_RATIO3")) : 0.97f;
+  k3_dive<<<A, kT3, 0, s>>>(jb, d_top.as<int>(), dive_ratio, lb, ctr);
   CSM_LAUNCH_CHECK();
   ProfEnd(ctx, "k3_dive", static_cast<double>(A) * 8 * hmax);
 
