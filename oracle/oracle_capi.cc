@@ -9,6 +9,7 @@
 
 #include "oracle_2d.h"
 #include "oracle_3d.h"
+#include "oracle_ceres2d.h"
 
 using namespace oracle;
 
@@ -513,6 +514,49 @@ void orc_rotational_match(const float* submap_hist, const float* hist, int n, fl
   const std::vector<float> r =
       RotationalMatch(a, b, initial_angle, std::vector<float>(angles, angles + m));
   std::memcpy(out, r.data(), sizeof(float) * m);
+}
+
+// ---- CeresScanMatcher2D restatement (oracle_ceres2d.h) ---------------------------
+// opts = {occupied_space_weight, translation_weight, rotation_weight,
+//         use_nonmonotonic_steps, max_num_iterations}
+static CeresScanMatcherOptions2D CeresOpts(const double* o) {
+  CeresScanMatcherOptions2D opt;
+  opt.occupied_space_weight = o[0];
+  opt.translation_weight = o[1];
+  opt.rotation_weight = o[2];
+  opt.use_nonmonotonic_steps = o[3] != 0.;
+  opt.max_num_iterations = static_cast<int>(o[4]);
+  return opt;
+}
+
+// residuals: n + 3; jacobian: (n + 3) x 3 row-major, or NULL for the plain-double path
+void orc_ceres2d_evaluate(const uint16_t* cells, int nx, int ny, double res, double max_x,
+                          double max_y, const float* xyz, int n, const double* opts,
+                          const double* target_xy, double target_angle, const double* pose,
+                          double* residuals, double* jacobian) {
+  const ProbabilityGrid grid =
+      MakeGrid(cells, nx, ny, res, max_x, max_y, kMinCorrespondenceCost, kMaxCorrespondenceCost);
+  std::vector<double> r, j;
+  EvaluateCeresResiduals2D(grid, MakeCloud(xyz, n), CeresOpts(opts), target_xy, target_angle,
+                           pose, &r, jacobian ? &j : nullptr);
+  std::memcpy(residuals, r.data(), sizeof(double) * r.size());
+  if (jacobian) std::memcpy(jacobian, j.data(), sizeof(double) * j.size());
+}
+
+// summary_out = {initial_cost, final_cost, iterations, num_successful_steps, termination}
+void orc_ceres2d_match(const uint16_t* cells, int nx, int ny, double res, double max_x,
+                       double max_y, const float* xyz, int n, const double* opts,
+                       const double* target_xy, const double* init_pose, double* pose_out,
+                       double* summary_out) {
+  const ProbabilityGrid grid =
+      MakeGrid(cells, nx, ny, res, max_x, max_y, kMinCorrespondenceCost, kMaxCorrespondenceCost);
+  CeresSummary2D sum;
+  CeresMatch2D(grid, MakeCloud(xyz, n), CeresOpts(opts), target_xy, init_pose, pose_out, &sum);
+  summary_out[0] = sum.initial_cost;
+  summary_out[1] = sum.final_cost;
+  summary_out[2] = sum.iterations;
+  summary_out[3] = sum.num_successful_steps;
+  summary_out[4] = sum.termination;
 }
 
 }  // extern "C"

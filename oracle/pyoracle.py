@@ -453,3 +453,54 @@ def rt3d_match(hybrid_grid, xyz, initial_pose, lin, ang, w_t, w_r):
                                  _p(stats, C.c_int64))
     return dict(score=np.float32(score), pose=pose, candidates_scored=int(stats[0]),
                 best_index=int(stats[1]))
+
+
+# ---- CeresScanMatcher2D restatement (oracle_ceres2d.h; parity unpinned against Ceres) ----
+CERES_TERMINATION = ("NO_CONVERGENCE", "FUNCTION_TOLERANCE", "GRADIENT_TOLERANCE",
+                     "PARAMETER_TOLERANCE", "MIN_TRUST_REGION_RADIUS", "INVALID_STEPS")
+
+
+def _ceres_opts(occupied_space_weight, translation_weight, rotation_weight,
+                use_nonmonotonic_steps, max_num_iterations):
+    return np.array([occupied_space_weight, translation_weight, rotation_weight,
+                     float(bool(use_nonmonotonic_steps)), float(max_num_iterations)], np.float64)
+
+
+def ceres2d_evaluate(grid, xyz, pose, target_xy, target_angle, occupied_space_weight=20.0,
+                     translation_weight=10.0, rotation_weight=1.0, jacobian=True):
+    """Residuals (n + 3) and Jacobian ((n + 3) x 3) of CeresScanMatcher2D's three blocks."""
+    xyz = _f32(xyz)
+    n = len(xyz)
+    o = _ceres_opts(occupied_space_weight, translation_weight, rotation_weight, True, 1)
+    p = np.ascontiguousarray(pose, np.float64)
+    t = np.ascontiguousarray(target_xy, np.float64)
+    res = np.zeros(n + 3, np.float64)
+    jac = np.zeros((n + 3, 3), np.float64) if jacobian else None
+    lib().orc_ceres2d_evaluate(_p(grid.cells, C.c_uint16), C.c_int(grid.num_x),
+                               C.c_int(grid.num_y), C.c_double(grid.resolution),
+                               C.c_double(grid.max_x), C.c_double(grid.max_y),
+                               _p(xyz, C.c_float), C.c_int(n), _p(o, C.c_double),
+                               _p(t, C.c_double), C.c_double(target_angle), _p(p, C.c_double),
+                               _p(res, C.c_double), _p(jac, C.c_double) if jacobian else None)
+    return res, jac
+
+
+def ceres2d_match(grid, xyz, target_xy, initial_pose, occupied_space_weight=20.0,
+                  translation_weight=10.0, rotation_weight=1.0, use_nonmonotonic_steps=True,
+                  max_num_iterations=10):
+    """CeresScanMatcher2D::Match -> dict(pose, initial_cost, final_cost, iterations, ...)."""
+    xyz = _f32(xyz)
+    o = _ceres_opts(occupied_space_weight, translation_weight, rotation_weight,
+                    use_nonmonotonic_steps, max_num_iterations)
+    t = np.ascontiguousarray(target_xy, np.float64)
+    ip = np.ascontiguousarray(initial_pose, np.float64)
+    pose = np.zeros(3, np.float64)
+    sm = np.zeros(5, np.float64)
+    lib().orc_ceres2d_match(_p(grid.cells, C.c_uint16), C.c_int(grid.num_x), C.c_int(grid.num_y),
+                            C.c_double(grid.resolution), C.c_double(grid.max_x),
+                            C.c_double(grid.max_y), _p(xyz, C.c_float), C.c_int(len(xyz)),
+                            _p(o, C.c_double), _p(t, C.c_double), _p(ip, C.c_double),
+                            _p(pose, C.c_double), _p(sm, C.c_double))
+    return dict(pose=pose, initial_cost=float(sm[0]), final_cost=float(sm[1]),
+                iterations=int(sm[2]), num_successful_steps=int(sm[3]),
+                termination=CERES_TERMINATION[int(sm[4])])
