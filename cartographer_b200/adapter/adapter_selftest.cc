@@ -239,6 +239,32 @@ int main() {
     }
     if (got[0].node_id.node_index != 0 || got[1].node_id.node_index != 2) return 1;
     builder.DeleteScanMatcher(sid);
+
+    // the same queue with the refinement of constraint_builder_2d.cc:245-249 on the device,
+    // and CeresScanMatcher2D::Match called directly (ceres_scan_matcher_2d.h:50-55)
+    ConstraintBuilder2D refining(bo, &pool);
+    refining.set_device_refinement(true);
+    refining.MaybeAddConstraint(sid, &submap, mapping::NodeId{0, 0}, &node, relative);
+    refining.MaybeAddGlobalConstraint(sid, &submap, mapping::NodeId{0, 2}, &node);
+    refining.NotifyEndOfNode();
+    ConstraintBuilder2D::Result got_refined;
+    refining.WhenDone([&](const ConstraintBuilder2D::Result& r) { got_refined = r; });
+    if (got_refined.size() != 2) return 1;
+    for (const auto& c : got_refined)
+      std::printf("RESULT cb2d_refined %d %.17g %.17g %.17g\n", c.node_id.node_index,
+                  c.pose.zbar_ij.translation().x(), c.pose.zbar_ij.translation().y(),
+                  2. * std::atan2(c.pose.zbar_ij.rotation().z(), c.pose.zbar_ij.rotation().w()));
+    refining.DeleteScanMatcher(sid);
+    mapping::scan_matching::CeresScanMatcher2D ceres(bo.ceres_scan_matcher_options());
+    const transform::Rigid2d start({0.03, -0.02}, 0.01);
+    transform::Rigid2d refined_pose;
+    mapping::scan_matching::CeresScanMatcher2D::Summary summary;
+    ceres.Match(start.translation(), start, cloud, grid, &refined_pose, &summary);
+    std::printf("RESULT ceres2d %.17g %.17g %.17g %.17g %.17g %d %d %d\n",
+                refined_pose.translation().x(), refined_pose.translation().y(),
+                refined_pose.rotation().angle(), summary.initial_cost, summary.final_cost,
+                summary.iterations, summary.num_successful_steps, summary.termination);
+    if (!(summary.final_cost <= summary.initial_cost)) return 1;
   }
   {
     using mapping::constraints::ConstraintBuilder3D;

@@ -234,6 +234,29 @@ class RealTimeCorrelativeScanMatcherOptions {
  private:
   double lin_ = 0., ang_ = 0., wt_ = 0., wr_ = 0.;
 };
+// proto/scan_matching/ceres_scan_matcher_options_2d.proto + common/proto/ceres_solver_options.proto
+// (defaults: configuration_files/pose_graph.lua:30-39)
+class CeresScanMatcherOptions2D {
+ public:
+  struct CeresSolverOptions {
+    bool use_nonmonotonic_steps_ = true;
+    int max_num_iterations_ = 10, num_threads_ = 1;
+    bool use_nonmonotonic_steps() const { return use_nonmonotonic_steps_; }
+    int max_num_iterations() const { return max_num_iterations_; }
+    int num_threads() const { return num_threads_; }
+  };
+  double occupied_space_weight() const { return occupied_; }
+  double translation_weight() const { return translation_; }
+  double rotation_weight() const { return rotation_; }
+  const CeresSolverOptions& ceres_solver_options() const { return solver_; }
+  CeresSolverOptions* mutable_ceres_solver_options() { return &solver_; }
+  void set_occupied_space_weight(double v) { occupied_ = v; }
+  void set_translation_weight(double v) { translation_ = v; }
+  void set_rotation_weight(double v) { rotation_ = v; }
+ private:
+  double occupied_ = 20., translation_ = 10., rotation_ = 1.;
+  CeresSolverOptions solver_;
+};
 // proto/scan_matching/fast_correlative_scan_matcher_options_3d.proto
 class FastCorrelativeScanMatcherOptions3D {
  public:
@@ -361,6 +384,10 @@ struct ConstraintBuilderOptions {
          loop_closure_rotation_weight_ = 1e5;
   scan_matching::proto::FastCorrelativeScanMatcherOptions2D fast2d_;
   scan_matching::proto::FastCorrelativeScanMatcherOptions3D fast3d_;
+  scan_matching::proto::CeresScanMatcherOptions2D ceres2d_;
+  const scan_matching::proto::CeresScanMatcherOptions2D& ceres_scan_matcher_options() const {
+    return ceres2d_;
+  }
   double sampling_ratio() const { return sampling_ratio_; }
   double max_constraint_distance() const { return max_constraint_distance_; }
   double min_score() const { return min_score_; }

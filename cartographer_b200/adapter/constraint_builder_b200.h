@@ -9,9 +9,12 @@
 // (RunWhenDoneCallback, :279-300).  Observable differences, all inside the contract of
 // the header comment ("After all computations are done the callback will be called"):
 //   * GetNumFinishedNodes() advances when the queue is drained, not pair by pair;
-//   * constraint poses are the fast matcher's estimates unless `set_refiner` installs
-//     the Ceres refinement (CeresScanMatcher2D/3D, :245-249 / 3d :261-275) — inside a
-//     checkout that is the reference's own ceres_scan_matcher_.Match call.
+//   * constraint poses are the fast matcher's estimates unless the refinement of :245-249
+//     is switched on: `set_device_refinement(true)` runs CeresScanMatcher2D::Match for all
+//     found matches of the queue in one launch (csm_ceres_match2d_batch, with
+//     options.ceres_scan_matcher_options()); `set_refiner` installs any other callable —
+//     inside a checkout that can be the reference's own ceres_scan_matcher_.Match (2D / 3D
+//     :261-275).
 #ifndef CSM_ADAPTER_CONSTRAINT_BUILDER_B200_H_
 #define CSM_ADAPTER_CONSTRAINT_BUILDER_B200_H_
 
@@ -74,6 +77,13 @@ class ConstraintBuilder2D {
   ConstraintBuilder2D& operator=(const ConstraintBuilder2D&) = delete;
 
   void set_refiner(const Refiner& refiner) { refiner_ = refiner; }
+  // constraint_builder_2d.cc:245-249 on the device.  Single-GPU builders only: with a
+  // multi_gpu context the results are exchanged inside csm_cb_batch2d_run, before a
+  // refinement could run on the owner.
+  void set_device_refinement(bool on) {
+    b200_internal::Require(!on || ctx_ == nullptr, "device refinement needs a single-GPU builder");
+    device_refinement_ = on;
+  }
 
   // constraint_builder_2d.cc:77-112
   void MaybeAddConstraint(const SubmapId& submap_id, const Submap2D* submap,
@@ -148,6 +158,7 @@ class ConstraintBuilder2D {
   struct SubmapStack {
     const Grid2D* grid = nullptr;
     csm_stack2d* stack = nullptr;
+    std::unique_ptr<scan_matching::DeviceGrid2D> device_grid;   // for the refinement
   };
 
   void Push(const SubmapId& submap_id, const Submap2D* submap, const NodeId& node_id,
@@ -244,11 +255,34 @@ class ConstraintBuilder2D {
         }
       }
       for (csm_cloud* c : clouds) csm_cloud_destroy(c);
+      // ceres_scan_matcher_.Match(pose_estimate.translation(), pose_estimate, cloud, grid,
+      // &pose_estimate, ...) for every found match (:245-249), one launch for the queue
+      std::vector<transform::Rigid2d> refined;
+      std::vector<size_t> refined_of(pending_.size(), 0);
+      if (device_refinement_) {
+        std::vector<scan_matching::CeresScanMatcher2D::Job> rjobs;
+        for (size_t i = 0; i < pending_.size(); ++i) {
+          if (!results[i].found) continue;
+          const Pending& p = pending_[i];
+          SubmapStack& entry = stacks_[p.submap_id];
+          if (entry.device_grid == nullptr)
+            entry.device_grid.reset(new scan_matching::DeviceGrid2D(*p.submap->grid(), device_));
+          refined_of[i] = rjobs.size();
+          rjobs.push_back(scan_matching::CeresScanMatcher2D::Job{
+              {results[i].pose_estimate[0], results[i].pose_estimate[1]},
+              transform::Rigid2d({results[i].pose_estimate[0], results[i].pose_estimate[1]},
+                                 results[i].pose_estimate[2]),
+              &p.constant_data->filtered_gravity_aligned_point_cloud, entry.device_grid.get()});
+        }
+        scan_matching::CeresScanMatcher2D(options_.ceres_scan_matcher_options(), device_)
+            .MatchBatch(rjobs, &refined, nullptr);
+      }
       for (size_t i = 0; i < pending_.size(); ++i) {
         if (!results[i].found) continue;  // below min_score: no constraint (:253-261)
         const Pending& p = pending_[i];
         transform::Rigid2d pose_estimate({results[i].pose_estimate[0], results[i].pose_estimate[1]},
                                          results[i].pose_estimate[2]);
+        if (device_refinement_) pose_estimate = refined[refined_of[i]];
         if (refiner_)
           pose_estimate = refiner_(pose_estimate,
                                    p.constant_data->filtered_gravity_aligned_point_cloud,
@@ -291,6 +325,7 @@ class ConstraintBuilder2D {
   std::map<SubmapId, SubmapStack> stacks_;
   std::map<SubmapId, common::FixedRatioSampler> per_submap_sampler_;
   Refiner refiner_;
+  bool device_refinement_ = false;
   csm_stats last_stats_{};
 };
 

@@ -26,6 +26,7 @@
 #include "cartographer/mapping/2d/grid_2d.h"
 #include "cartographer/mapping/internal/2d/scan_matching/correlative_scan_matcher_2d.h"
 #include "cartographer/mapping/internal/2d/tsdf_2d.h"
+#include "cartographer/mapping/proto/scan_matching/ceres_scan_matcher_options_2d.pb.h"
 #include "cartographer/mapping/proto/scan_matching/fast_correlative_scan_matcher_options_2d.pb.h"
 #include "cartographer/mapping/proto/scan_matching/real_time_correlative_scan_matcher_options.pb.h"
 #include "cartographer/sensor/point_cloud.h"
@@ -222,6 +223,112 @@ class RealTimeCorrelativeScanMatcher2D {
 
  private:
   const proto::RealTimeCorrelativeScanMatcherOptions options_;
+  int device_;
+};
+
+// A ProbabilityGrid kept on the device (csm_rt_grid2d): the form in which the batched
+// real-time matcher and the refinement below take the submap's grid.
+class DeviceGrid2D {
+ public:
+  explicit DeviceGrid2D(const Grid2D& grid, int device = 0) {
+    if (grid.GetGridType() != GridType::PROBABILITY_GRID) {
+      std::fprintf(stderr, "DeviceGrid2D (b200): only ProbabilityGrid is supported\n");
+      std::abort();
+    }
+    const MapLimits& l = grid.limits();
+    b200_internal::Check(csm_rt_grid2d_create(
+        grid.correspondence_cost_cells().data(), l.cell_limits().num_x_cells,
+        l.cell_limits().num_y_cells, l.resolution(), l.max().x(), l.max().y(), device, &grid_));
+  }
+  ~DeviceGrid2D() { csm_rt_grid2d_destroy(grid_); }
+  DeviceGrid2D(const DeviceGrid2D&) = delete;
+  DeviceGrid2D& operator=(const DeviceGrid2D&) = delete;
+  const csm_rt_grid2d* handle() const { return grid_; }
+
+ private:
+  csm_rt_grid2d* grid_ = nullptr;
+};
+
+// ceres_scan_matcher_2d.h:42-64.  Same constructor and Match signature, except that the
+// summary is this struct instead of ceres::Solver::Summary (Ceres is not linked; the
+// fields are the ones of the same name there).  MatchBatch is the form the constraint
+// builder uses: all found matches of a queue in one launch.
+class CeresScanMatcher2D {
+ public:
+  struct Summary {
+    double initial_cost = 0., final_cost = 0.;
+    int iterations = 0, num_successful_steps = 0;
+    int termination = 0;   // csm_ceres_result2d::termination
+  };
+  struct Job {
+    double target_translation[2];
+    transform::Rigid2d initial_pose_estimate;
+    const sensor::PointCloud* point_cloud;
+    const DeviceGrid2D* grid;
+  };
+
+  explicit CeresScanMatcher2D(const proto::CeresScanMatcherOptions2D& options, int device = 0)
+      : options_(options), device_(device) {}
+
+  template <typename Vector2>
+  void Match(const Vector2& target_translation, const transform::Rigid2d& initial_pose_estimate,
+             const sensor::PointCloud& point_cloud, const Grid2D& grid,
+             transform::Rigid2d* const pose_estimate, Summary* const summary) const {
+    const DeviceGrid2D device_grid(grid, device_);
+    std::vector<transform::Rigid2d> poses;
+    std::vector<Summary> summaries;
+    MatchBatch({Job{{target_translation.x(), target_translation.y()}, initial_pose_estimate,
+                    &point_cloud, &device_grid}},
+               &poses, &summaries);
+    *pose_estimate = poses[0];
+    if (summary != nullptr) *summary = summaries[0];
+  }
+
+  void MatchBatch(const std::vector<Job>& jobs, std::vector<transform::Rigid2d>* poses,
+                  std::vector<Summary>* summaries) const {
+    poses->clear();
+    if (summaries != nullptr) summaries->clear();
+    if (jobs.empty()) return;
+    std::vector<std::vector<float>> xyz(jobs.size());
+    std::vector<csm_ceres_job2d> cj(jobs.size());
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      xyz[i] = b200_internal::Flatten(*jobs[i].point_cloud);
+      cj[i] = csm_ceres_job2d{};
+      cj[i].grid = jobs[i].grid->handle();
+      cj[i].xyz = xyz[i].data();
+      cj[i].num_points = static_cast<int32_t>(jobs[i].point_cloud->size());
+      cj[i].target_translation[0] = jobs[i].target_translation[0];
+      cj[i].target_translation[1] = jobs[i].target_translation[1];
+      cj[i].initial_pose[0] = jobs[i].initial_pose_estimate.translation().x();
+      cj[i].initial_pose[1] = jobs[i].initial_pose_estimate.translation().y();
+      cj[i].initial_pose[2] = jobs[i].initial_pose_estimate.rotation().angle();
+    }
+    csm_ceres_options2d o;
+    o.occupied_space_weight = options_.occupied_space_weight();
+    o.translation_weight = options_.translation_weight();
+    o.rotation_weight = options_.rotation_weight();
+    o.use_nonmonotonic_steps = options_.ceres_solver_options().use_nonmonotonic_steps() ? 1 : 0;
+    o.max_num_iterations = options_.ceres_solver_options().max_num_iterations();
+    std::vector<csm_ceres_result2d> res(jobs.size());
+    b200_internal::Check(csm_ceres_match2d_batch(cj.data(), static_cast<int32_t>(cj.size()), &o,
+                                                 res.data(), nullptr));
+    for (const csm_ceres_result2d& r : res) {
+      poses->push_back(
+          transform::Rigid2d({r.pose_estimate[0], r.pose_estimate[1]}, r.pose_estimate[2]));
+      if (summaries != nullptr) {
+        Summary s;
+        s.initial_cost = r.initial_cost;
+        s.final_cost = r.final_cost;
+        s.iterations = r.iterations;
+        s.num_successful_steps = r.num_successful_steps;
+        s.termination = r.termination;
+        summaries->push_back(s);
+      }
+    }
+  }
+
+ private:
+  const proto::CeresScanMatcherOptions2D options_;
   int device_;
 };
 

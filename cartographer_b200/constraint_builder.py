@@ -12,10 +12,12 @@ With torch.distributed initialised the queue is sharded submap-major across rank
 only built on their owner) and the fixed-size constraint records are exchanged
 with a single all_gather; every rank then reports the same Result in queue order.
 
-Constraints are pinned PRE-Ceres: `pose` is ComputeSubmapPose(submap)^-1 *
-pose_estimate of the fast matcher (constraint_builder_2d.cc:251-258 without the
-CeresScanMatcher2D refinement at :245-249, which is third-party and out of scope,
-SURVEY.md §8c/§8f).
+By default constraints are the fast matcher's: `pose` is ComputeSubmapPose(submap)^-1 *
+pose_estimate (constraint_builder_2d.cc:251-258), which is what the bit-exact parity
+tests pin.  With ConstraintBuilderOptions.ceres_scan_matcher_options set, every found
+match is first refined as constraint_builder_2d.cc:245-249 does — all of a drain's
+matches in one csm_ceres_match2d_batch launch (scan_matching.CeresScanMatcher2D; Ceres
+itself is not linked).
 """
 import math
 from dataclasses import dataclass, field
@@ -42,6 +44,8 @@ class ConstraintBuilderOptions:
     linear_search_window: float = 7.0
     angular_search_window: float = math.radians(30.0)
     branch_and_bound_depth: int = 7
+    # scan_matching.CeresScanMatcherOptions2D, or None to leave matches unrefined
+    ceres_scan_matcher_options: object = None
 
 
 @dataclass
@@ -114,8 +118,10 @@ class CudaExecutor:
         self.options = options
         self.device = device
         self.matchers = {}
+        self.grids = {}     # submap id -> RealTimeGrid2D (only with the Ceres refinement on)
         self.clouds = {}
-        self.stats = {"candidates_scored": 0, "device_ms": 0.0, "searched": 0}
+        self.stats = {"candidates_scored": 0, "device_ms": 0.0, "searched": 0, "refined": 0,
+                      "refine_device_ms": 0.0}
 
     def ensure_matcher(self, submap_id, grid):
         if submap_id not in self.matchers:
@@ -129,6 +135,30 @@ class CudaExecutor:
         m = self.matchers.pop(submap_id, None)
         if m is not None:
             m.close()
+        g = self.grids.pop(submap_id, None)
+        if g is not None:
+            g.close()
+
+    def refine(self, jobs, submaps, clouds, out):
+        """constraint_builder_2d.cc:245-249 for every found match of the drain, one launch."""
+        sm = self.sm
+        idx = [i for i, r in enumerate(out) if r[0]]
+        if not idx:
+            return out
+        for i in idx:
+            sid = jobs[i].submap_id
+            if sid not in self.grids:
+                self.grids[sid] = sm.RealTimeGrid2D(submaps[sid].grid, device=self.device)
+        matcher = sm.CeresScanMatcher2D(self.options.ceres_scan_matcher_options)
+        poses, _ = matcher.MatchBatch([out[i][2][:2] for i in idx], [out[i][2] for i in idx],
+                                      [clouds[jobs[i].cloud_key] for i in idx],
+                                      [self.grids[jobs[i].submap_id] for i in idx])
+        self.stats["refined"] += len(idx)
+        self.stats["refine_device_ms"] += matcher.last_stats["device_ms"]
+        out = list(out)
+        for i, p in zip(idx, poses):
+            out[i] = (True, out[i][1], (float(p[0]), float(p[1]), float(p[2])))
+        return out
 
     def run(self, jobs, submaps, clouds):
         """-> list of (found, score, pose_estimate) in job order."""
@@ -158,7 +188,10 @@ class CudaExecutor:
         self.stats["candidates_scored"] += st["candidates_scored"]
         self.stats["device_ms"] += st["device_ms"]
         self.stats["searched"] += len(jobs)
-        return [(bool(r["found"]), float(r["score"]), tuple(r["pose_estimate"])) for r in res]
+        out = [(bool(r["found"]), float(r["score"]), tuple(r["pose_estimate"])) for r in res]
+        if self.options.ceres_scan_matcher_options is not None:
+            out = self.refine(jobs, submaps, clouds, out)
+        return out
 
     def release_clouds(self):
         for c in self.clouds.values():

@@ -32,6 +32,7 @@
 #include <thread>
 
 #include "engine2d.cuh"
+#include "rtgrid.cuh"
 
 namespace csm {
 
@@ -42,14 +43,6 @@ constexpr int kRtWarps = kRtThreads / 32;
 // predicated-off accumulator code (the first version executed all four and spent 67
 // instructions per warp and point instead of ~17; profiles/r2_ncu_full_k_rt_match_v1_acc4.txt)
 constexpr int kRtTileBytes = 100 * 1024;     // staged box (2 CTAs per SM)
-
-struct RtGridDev {
-  const uint16_t* cells;    // device copy, row pitch `pitch` cells
-  const uint16_t* wcells;   // TSDF weight cells (nullptr for a ProbabilityGrid)
-  int nx, ny, pitch;
-  int bw, bh;               // TMA box (cells)
-  double resolution, max_x, max_y;
-};
 
 struct RtParams {
   int lin, width, per_scan, npair;
@@ -322,20 +315,6 @@ using namespace csm;
 // A ProbabilityGrid (or TSDF2D) resident on the device, with the TMA descriptor of its
 // cell array.  LocalTrajectoryBuilder2D matches every scan against the active submap's
 // grid (local_trajectory_builder_2d.cc:77-82); the handle lets many scans share one copy.
-struct csm_rt_grid2d {
-  Ctx* ctx = nullptr;
-  RtGridDev g;
-  uint16_t* d_cells = nullptr;
-  uint16_t* d_wcells = nullptr;
-  CUtensorMap tmap;
-  bool has_tmap = false;
-  float truncation = 0.f, max_weight = 0.f;
-  ~csm_rt_grid2d() {
-    cudaFree(d_cells);
-    cudaFree(d_wcells);
-  }
-};
-
 namespace {
 
 struct HV3 { float x, y, z; };

@@ -739,3 +739,103 @@ class RealTimeCorrelativeScanMatcher3D:
             C.byref(stats)))
         self.last_stats = stats.as_dict()
         return np.float32(score.value), pose
+
+
+# ===========================================================================
+# CeresScanMatcher2D (mapping/internal/2d/scan_matching/ceres_scan_matcher_2d.{h,cc})
+# ===========================================================================
+class CsmCeresOptions2D(C.Structure):
+    _fields_ = [("occupied_space_weight", C.c_double), ("translation_weight", C.c_double),
+                ("rotation_weight", C.c_double), ("use_nonmonotonic_steps", C.c_int32),
+                ("max_num_iterations", C.c_int32)]
+
+
+class CsmCeresJob2D(C.Structure):
+    _fields_ = [("grid", C.c_void_p), ("xyz", C.POINTER(C.c_float)), ("num_points", C.c_int32),
+                ("reserved", C.c_int32), ("target_translation", C.c_double * 2),
+                ("initial_pose", C.c_double * 3)]
+
+
+class CsmCeresResult2D(C.Structure):
+    _fields_ = [("pose_estimate", C.c_double * 3), ("initial_cost", C.c_double),
+                ("final_cost", C.c_double), ("iterations", C.c_int32),
+                ("num_successful_steps", C.c_int32), ("termination", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+CERES_TERMINATION = ("NO_CONVERGENCE", "FUNCTION_TOLERANCE", "GRADIENT_TOLERANCE",
+                     "PARAMETER_TOLERANCE", "MIN_TRUST_REGION_RADIUS", "INVALID_STEPS")
+
+
+@dataclass
+class CeresScanMatcherOptions2D:
+    """proto/scan_matching/ceres_scan_matcher_options_2d.proto +
+    common/proto/ceres_solver_options.proto; defaults = the constraint builder's
+    (configuration_files/pose_graph.lua:30-39).  num_threads has no meaning here."""
+    occupied_space_weight: float = 20.0
+    translation_weight: float = 10.0
+    rotation_weight: float = 1.0
+    use_nonmonotonic_steps: bool = True
+    max_num_iterations: int = 10
+
+    def _c(self):
+        return CsmCeresOptions2D(self.occupied_space_weight, self.translation_weight,
+                                 self.rotation_weight, int(self.use_nonmonotonic_steps),
+                                 int(self.max_num_iterations))
+
+
+class CeresScanMatcher2D:
+    """ceres_scan_matcher_2d.h:42-64.  `grid` arguments are RealTimeGrid2D handles (the
+    submap's ProbabilityGrid resident on the device).  Match returns (pose_estimate, summary)
+    where the reference fills *pose_estimate and a ceres::Solver::Summary."""
+
+    def __init__(self, options=None):
+        self.options = options if options is not None else CeresScanMatcherOptions2D()
+
+    def Match(self, target_translation, initial_pose_estimate, point_cloud, grid):
+        poses, summaries = self.MatchBatch([target_translation], [initial_pose_estimate],
+                                           [point_cloud], [grid])
+        return poses[0], summaries[0]
+
+    def MatchBatch(self, target_translations, initial_pose_estimates, point_clouds, grids):
+        """Many Match calls in one launch (csm_ceres_match2d_batch); grids[j] may differ per
+        job (one per submap) but must live on one device."""
+        n = len(point_clouds)
+        clouds = [_f32(c) for c in point_clouds]
+        jobs = (CsmCeresJob2D * n)()
+        for j in range(n):
+            jobs[j].grid = grids[j]._h
+            jobs[j].xyz = ptr(clouds[j], C.c_float)
+            jobs[j].num_points = len(clouds[j])
+            jobs[j].target_translation[0] = float(target_translations[j][0])
+            jobs[j].target_translation[1] = float(target_translations[j][1])
+            for k in range(3):
+                jobs[j].initial_pose[k] = float(initial_pose_estimates[j][k])
+        res = (CsmCeresResult2D * n)()
+        stats = CsmStats()
+        opt = self.options._c()
+        check(lib().csm_ceres_match2d_batch(jobs, C.c_int32(n), C.byref(opt), res,
+                                            C.byref(stats)))
+        self.last_stats = stats.as_dict()
+        poses = np.array([[r.pose_estimate[0], r.pose_estimate[1], r.pose_estimate[2]]
+                          for r in res], np.float64)
+        summaries = [dict(initial_cost=r.initial_cost, final_cost=r.final_cost,
+                          iterations=r.iterations, num_successful_steps=r.num_successful_steps,
+                          termination=CERES_TERMINATION[r.termination]) for r in res]
+        return poses, summaries
+
+    def Evaluate(self, grid, point_cloud, pose, target_translation, target_angle, jacobian=True):
+        """Residuals (n + 3) and Jacobian ((n + 3) x 3) of the three residual blocks at
+        `pose` (csm_ceres_evaluate2d; what Problem::Evaluate would give)."""
+        xyz = _f32(point_cloud)
+        n = len(xyz)
+        res = np.zeros(n + 3, np.float64)
+        jac = np.zeros((n + 3, 3), np.float64) if jacobian else None
+        p = np.ascontiguousarray(pose, np.float64)
+        t = np.ascontiguousarray(target_translation, np.float64)
+        opt = self.options._c()
+        check(lib().csm_ceres_evaluate2d(
+            grid._h, ptr(xyz, C.c_float), C.c_int32(n), C.byref(opt), ptr(t, C.c_double),
+            C.c_double(target_angle), ptr(p, C.c_double), ptr(res, C.c_double),
+            ptr(jac, C.c_double) if jacobian else None))
+        return res, jac

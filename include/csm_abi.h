@@ -273,6 +273,62 @@ csm_status csm_rt_score_candidates2d(const uint16_t* cells, int32_t num_x_cells,
                                      double rotation_delta_cost_weight, int32_t device,
                                      float* scores);
 
+/* ---- post-match refinement: CeresScanMatcher2D ------------------------------- */
+/* ConstraintBuilder2D refines every found match with CeresScanMatcher2D::Match
+ * (internal/constraints/constraint_builder_2d.cc:245-249 ->
+ * internal/2d/scan_matching/ceres_scan_matcher_2d.cc:62-107): minimise over {x, y, theta}
+ * the occupied-space residuals of the scan in the submap's ProbabilityGrid
+ * (occupied_space_cost_function_2d.cc:42-69, bicubic interpolation of the correspondence
+ * costs) plus the translation / rotation priors (translation_delta_cost_functor_2d.h:41-45,
+ * rotation_delta_cost_functor_2d.h:40-43).  csm_ceres_match2d_batch solves many such
+ * problems in ONE launch (one CTA per match, the trust-region loop on the device).  Ceres
+ * itself is not linked: the solver follows Ceres' documented Levenberg-Marquardt
+ * trust-region algorithm with the Solver::Options the reference sets (DENSE_QR,
+ * use_nonmonotonic_steps, max_num_iterations; everything else default) — see DESIGN.md for
+ * what that restatement is pinned to.  Grids are csm_rt_grid2d handles (ProbabilityGrid
+ * only). */
+typedef struct csm_ceres_options2d {
+  double occupied_space_weight;   /* proto/scan_matching/ceres_scan_matcher_options_2d.proto */
+  double translation_weight;
+  double rotation_weight;
+  int32_t use_nonmonotonic_steps; /* common/proto/ceres_solver_options.proto */
+  int32_t max_num_iterations;
+} csm_ceres_options2d;
+
+typedef struct csm_ceres_job2d {
+  const csm_rt_grid2d* grid;      /* `grid` argument of Match */
+  const float* xyz;               /* point_cloud, num_points x {x, y, z} (host memory) */
+  int32_t num_points;
+  int32_t reserved;
+  double target_translation[2];
+  double initial_pose[3];         /* initial_pose_estimate {x, y, rotation().angle()} */
+} csm_ceres_job2d;
+
+/* termination: 0 max_num_iterations reached (NO_CONVERGENCE), 1 function tolerance,
+ * 2 gradient tolerance, 3 parameter tolerance, 4 minimum trust-region radius,
+ * 5 too many consecutive invalid steps (FAILURE).  Like Ceres, 1 and 3 stop BEFORE taking the
+ * step that triggered them, and the lowest-cost iterate visited is what is returned. */
+typedef struct csm_ceres_result2d {
+  double pose_estimate[3];
+  double initial_cost, final_cost; /* Solver::Summary::initial_cost / final_cost */
+  int32_t iterations;              /* trust-region iterations after the initial evaluation */
+  int32_t num_successful_steps;
+  int32_t termination;
+  int32_t reserved;
+} csm_ceres_result2d;
+
+csm_status csm_ceres_match2d_batch(const csm_ceres_job2d* jobs, int32_t num_jobs,
+                                   const csm_ceres_options2d* options,
+                                   csm_ceres_result2d* results,
+                                   csm_stats* stats /* may be NULL */);
+
+/* Test hook: the n + 3 residuals (and, if `jacobian` is not NULL, the (n + 3) x 3 row-major
+ * Jacobian) of the three residual blocks at `pose`; max_num_iterations etc. are ignored. */
+csm_status csm_ceres_evaluate2d(const csm_rt_grid2d* grid, const float* xyz, int32_t num_points,
+                                const csm_ceres_options2d* options,
+                                const double target_translation[2], double target_angle,
+                                const double pose[3], double* residuals, double* jacobian);
+
 /* ==== 3D: FastCorrelativeScanMatcher3D ====================================== */
 /* A HybridGrid crosses the ABI in the flat form of proto::HybridGrid
  * (mapping/proto/hybrid_grid.proto:19-28): voxel indices (n x {x,y,z} int32, origin

@@ -43,7 +43,15 @@ class OracleExecutor:
             m = self.matchers[j.submap_id]
             r = (m.match_full_submap(clouds[j.cloud_key], j.min_score) if j.full else
                  m.match(j.initial_pose, clouds[j.cloud_key], j.min_score))
-            out.append((r["found"], float(r["score"]), tuple(r["pose"])))
+            pose = tuple(r["pose"])
+            co = opt.ceres_scan_matcher_options
+            if r["found"] and co is not None:   # constraint_builder_2d.cc:245-249
+                og = self.matchers[j.submap_id].grid
+                pose = tuple(self.o.ceres2d_match(
+                    og, clouds[j.cloud_key], pose[:2], pose, co.occupied_space_weight,
+                    co.translation_weight, co.rotation_weight, co.use_nonmonotonic_steps,
+                    co.max_num_iterations)["pose"])
+            out.append((r["found"], float(r["score"]), pose))
         return out
 
     def delete_matcher(self, submap_id):
@@ -187,3 +195,27 @@ def test_sharded_queue_world2_gloo():
     # submap-major sharding: disjoint owners, stacks only built where owned
     assert set(ret[0][1]).isdisjoint(ret[1][1])
     assert sorted(ret[0][1] + ret[1][1]) == sorted(submaps.keys())
+
+
+def test_ceres_refinement_changes_only_the_poses():
+    """With ceres_scan_matcher_options set the queue yields the same constraints (ids,
+    scores, order) with refined poses (constraint_builder_2d.cc:245-258); host logic only —
+    the executor is the CPU oracle."""
+    from cartographer_b200 import scan_matching as sm
+    opts, submaps, clouds, poses = _small_queue()
+    plain = cb.ConstraintBuilder2D(opts, executor=OracleExecutor(opts))
+    _fill(plain, submaps, clouds, poses)
+    want = plain.WhenDone(lambda r: None)
+    opts2, _, _, _ = _small_queue()
+    opts2.ceres_scan_matcher_options = sm.CeresScanMatcherOptions2D()
+    refined = cb.ConstraintBuilder2D(opts2, executor=OracleExecutor(opts2))
+    _fill(refined, submaps, clouds, poses)
+    got = refined.WhenDone(lambda r: None)
+    assert len(got) == len(want) > 0
+    moved = 0
+    for a, b in zip(got, want):
+        assert a.submap_id == b.submap_id and a.node_id == b.node_id and a.score == b.score
+        d = np.abs(np.array(a.zbar_ij) - np.array(b.zbar_ij))
+        assert d[:2].max() < 0.2 and d[2] < 0.1        # a refinement, not a new search
+        moved += int(d.max() > 0)
+    assert moved > 0

@@ -101,6 +101,20 @@ def test_adapter_selftest_runs_on_device(oracle):
         z = compose(inverse(sp), tuple(want["pose"]))
         np.testing.assert_allclose([float(v) for v in got[1:3]], z[:2], rtol=0, atol=1e-12)
         assert abs(float(got[3]) - z[2]) < 1e-12   # yaw went through a quaternion (Embed3D)
+    # the same queue with the device refinement (constraint_builder_2d.cc:245-249), and
+    # CeresScanMatcher2D::Match through the C++ class; doubles, tolerance as in
+    # tests/test_gpu_ceres2d.py
+    for got, want in zip(res["cb2d_refined"], (w_local, w_global)):
+        r = oracle.ceres2d_match(ogrt, cloud, want["pose"][:2], want["pose"])
+        z = compose(inverse(sp), tuple(r["pose"]))
+        np.testing.assert_allclose([float(v) for v in got[1:4]], z, rtol=0, atol=1e-7)
+    got = res["ceres2d"][0]
+    want = oracle.ceres2d_match(ogrt, cloud, [0.03, -0.02], [0.03, -0.02, 0.01])
+    np.testing.assert_allclose([float(v) for v in got[0:3]], want["pose"], rtol=0, atol=1e-7)
+    assert float(got[3]) == pytest.approx(want["initial_cost"], rel=1e-12)
+    assert float(got[4]) == pytest.approx(want["final_cost"], rel=1e-9)
+    assert [int(got[5]), int(got[6])] == [want["iterations"], want["num_successful_steps"]]
+    assert oracle.CERES_TERMINATION[int(got[7])] == want["termination"]
     # FastCorrelativeScanMatcher3D::Match
     idx, val, cloud3 = [], [], []
     tx, ty, tz = np.float32(0.2), np.float32(-0.15), np.float32(0.1)
