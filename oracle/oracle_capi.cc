@@ -10,6 +10,7 @@
 #include "oracle_2d.h"
 #include "oracle_3d.h"
 #include "oracle_ceres2d.h"
+#include "oracle_ceres3d.h"
 
 using namespace oracle;
 
@@ -552,6 +553,62 @@ void orc_ceres2d_match(const uint16_t* cells, int nx, int ny, double res, double
       MakeGrid(cells, nx, ny, res, max_x, max_y, kMinCorrespondenceCost, kMaxCorrespondenceCost);
   CeresSummary2D sum;
   CeresMatch2D(grid, MakeCloud(xyz, n), CeresOpts(opts), target_xy, init_pose, pose_out, &sum);
+  summary_out[0] = sum.initial_cost;
+  summary_out[1] = sum.final_cost;
+  summary_out[2] = sum.iterations;
+  summary_out[3] = sum.num_successful_steps;
+  summary_out[4] = sum.termination;
+}
+
+// ---- CeresScanMatcher3D restatement (oracle_ceres3d.h) ---------------------------
+// opts = {translation_weight, rotation_weight, use_nonmonotonic_steps, max_num_iterations,
+//         occupied_space_weight_0, occupied_space_weight_1, ...}
+static CeresScanMatcherOptions3D CeresOpts3(const double* o, int num_clouds) {
+  CeresScanMatcherOptions3D opt;
+  opt.translation_weight = o[0];
+  opt.rotation_weight = o[1];
+  opt.use_nonmonotonic_steps = o[2] != 0.;
+  opt.max_num_iterations = static_cast<int>(o[3]);
+  opt.occupied_space_weight.assign(o + 4, o + 4 + num_clouds);
+  return opt;
+}
+
+double orc_interpolated_probability(void* hybrid, double x, double y, double z, double* gradient) {
+  return InterpolatedProbability(*static_cast<HybridGrid*>(hybrid), x, y, z, gradient);
+}
+
+namespace {
+struct Clouds3 {
+  std::vector<PointCloud> clouds;
+  std::vector<PointCloudAndHybridGrid> pairs;
+  Clouds3(void** hybrids, const float* const* xyz, const int32_t* n, int num) {
+    clouds.reserve(num);
+    for (int b = 0; b < num; ++b) clouds.push_back(MakeCloud(xyz[b], n[b]));
+    for (int b = 0; b < num; ++b)
+      pairs.push_back(PointCloudAndHybridGrid{&clouds[b], static_cast<HybridGrid*>(hybrids[b])});
+  }
+};
+}  // namespace
+
+// residuals: sum(n) + 6; jacobian: rows x 6 (tangent space) or NULL
+void orc_ceres3d_evaluate(void** hybrids, const float* const* xyz, const int32_t* n,
+                          int num_clouds, const double* opts, const double* target_t,
+                          const double* target_q, const double* pose, double* residuals,
+                          double* jacobian) {
+  const Clouds3 c(hybrids, xyz, n, num_clouds);
+  std::vector<double> r, j;
+  EvaluateCeresResiduals3D(c.pairs, CeresOpts3(opts, num_clouds), target_t, target_q, pose, &r,
+                           jacobian ? &j : nullptr);
+  std::memcpy(residuals, r.data(), sizeof(double) * r.size());
+  if (jacobian) std::memcpy(jacobian, j.data(), sizeof(double) * j.size());
+}
+
+void orc_ceres3d_match(void** hybrids, const float* const* xyz, const int32_t* n, int num_clouds,
+                       const double* opts, const double* target_t, const double* init_pose,
+                       double* pose_out, double* summary_out) {
+  const Clouds3 c(hybrids, xyz, n, num_clouds);
+  CeresSummary2D sum;
+  CeresMatch3D(c.pairs, CeresOpts3(opts, num_clouds), target_t, init_pose, pose_out, &sum);
   summary_out[0] = sum.initial_cost;
   summary_out[1] = sum.final_cost;
   summary_out[2] = sum.iterations;

@@ -504,3 +504,63 @@ def ceres2d_match(grid, xyz, target_xy, initial_pose, occupied_space_weight=20.0
     return dict(pose=pose, initial_cost=float(sm[0]), final_cost=float(sm[1]),
                 iterations=int(sm[2]), num_successful_steps=int(sm[3]),
                 termination=CERES_TERMINATION[int(sm[4])])
+
+
+# ---- CeresScanMatcher3D restatement (oracle_ceres3d.h; parity unpinned against Ceres) ----
+def interpolated_probability(hybrid_grid, x, y, z, gradient=False):
+    """InterpolatedGrid<HybridGrid>::GetInterpolatedValue (+ d/d(x, y, z) on dual numbers)."""
+    lib().orc_interpolated_probability.restype = C.c_double
+    g = np.zeros(3, np.float64)
+    f = lib().orc_interpolated_probability(hybrid_grid._h, C.c_double(x), C.c_double(y),
+                                           C.c_double(z), _p(g, C.c_double) if gradient else None)
+    return (float(f), g) if gradient else float(f)
+
+
+def _ceres3d_args(clouds_and_grids, occupied_space_weights, translation_weight, rotation_weight,
+                  use_nonmonotonic_steps, max_num_iterations):
+    num = len(clouds_and_grids)
+    clouds = [_f32(c) for c, _ in clouds_and_grids]
+    hy = (C.c_void_p * num)(*[g._h for _, g in clouds_and_grids])
+    xs = (C.POINTER(C.c_float) * num)(*[_p(c, C.c_float) for c in clouds])
+    ns = np.array([len(c) for c in clouds], np.int32)
+    o = np.array([translation_weight, rotation_weight, float(bool(use_nonmonotonic_steps)),
+                  float(max_num_iterations)] + list(occupied_space_weights)[:num], np.float64)
+    return num, clouds, hy, xs, ns, o
+
+
+def ceres3d_evaluate(clouds_and_grids, pose, target_translation, target_rotation,
+                     occupied_space_weights=(5.0, 30.0), translation_weight=10.0,
+                     rotation_weight=1.0, jacobian=True):
+    """clouds_and_grids = [(xyz, HybridGrid), ...]; pose = {t xyz, q wxyz}.  Residuals
+    (sum n + 6) and the tangent-space Jacobian (rows x 6)."""
+    num, clouds, hy, xs, ns, o = _ceres3d_args(clouds_and_grids, occupied_space_weights,
+                                               translation_weight, rotation_weight, False, 1)
+    rows = int(ns.sum()) + 6
+    res = np.zeros(rows, np.float64)
+    jac = np.zeros((rows, 6), np.float64) if jacobian else None
+    p = np.ascontiguousarray(pose, np.float64)
+    tt = np.ascontiguousarray(target_translation, np.float64)
+    tq = np.ascontiguousarray(target_rotation, np.float64)
+    lib().orc_ceres3d_evaluate(hy, xs, _p(ns, C.c_int32), C.c_int(num), _p(o, C.c_double),
+                               _p(tt, C.c_double), _p(tq, C.c_double), _p(p, C.c_double),
+                               _p(res, C.c_double), _p(jac, C.c_double) if jacobian else None)
+    return res, jac
+
+
+def ceres3d_match(clouds_and_grids, target_translation, initial_pose,
+                  occupied_space_weights=(5.0, 30.0), translation_weight=10.0,
+                  rotation_weight=1.0, use_nonmonotonic_steps=False, max_num_iterations=10):
+    """CeresScanMatcher3D::Match (no intensity grids, only_optimize_yaw = false)."""
+    num, clouds, hy, xs, ns, o = _ceres3d_args(clouds_and_grids, occupied_space_weights,
+                                               translation_weight, rotation_weight,
+                                               use_nonmonotonic_steps, max_num_iterations)
+    tt = np.ascontiguousarray(target_translation, np.float64)
+    ip = np.ascontiguousarray(initial_pose, np.float64)
+    pose = np.zeros(7, np.float64)
+    sm = np.zeros(5, np.float64)
+    lib().orc_ceres3d_match(hy, xs, _p(ns, C.c_int32), C.c_int(num), _p(o, C.c_double),
+                            _p(tt, C.c_double), _p(ip, C.c_double), _p(pose, C.c_double),
+                            _p(sm, C.c_double))
+    return dict(pose=pose, initial_cost=float(sm[0]), final_cost=float(sm[1]),
+                iterations=int(sm[2]), num_successful_steps=int(sm[3]),
+                termination=CERES_TERMINATION[int(sm[4])])
