@@ -20,15 +20,9 @@
 #include <map>
 
 #include "common.cuh"
+#include "grid3d.cuh"
 
 namespace csm {
-
-struct Grid3Dev {
-  const uint16_t* p;   // dense box of HybridGrid values (0 outside / unallocated)
-  int lo[3];
-  int n[3];
-  float resolution, k_scale, bias, min_probability;
-};
 
 struct Rt3Params {
   int n;          // points
@@ -120,13 +114,6 @@ k_rt3_match(const Grid3Dev G, const Rt3Params P, const float* __restrict__ xyz,
 }  // namespace csm
 
 using namespace csm;
-
-struct csm_grid3d {
-  Ctx* ctx = nullptr;
-  Grid3Dev g;
-  uint16_t* d_vol = nullptr;
-  ~csm_grid3d() { cudaFree(d_vol); }
-};
 
 namespace {
 

@@ -461,6 +461,54 @@ csm_status csm_rt_match3d(const csm_grid3d* grid, const float* xyz, int32_t num_
                           double rotation_delta_cost_weight, float* score,
                           double pose_estimate[7], csm_stats* stats /* may be NULL */);
 
+/* ---- post-match refinement in 3D: CeresScanMatcher3D --------------------------- */
+/* ConstraintBuilder3D refines every found match with CeresScanMatcher3D::Match
+ * (internal/constraints/constraint_builder_3d.cc:265-275 ->
+ * internal/3d/scan_matching/ceres_scan_matcher_3d.cc:95-157): occupied-space residuals of
+ * up to two (point cloud, HybridGrid) pairs — high and low resolution — through the
+ * smoothstep-interpolated grid (occupied_space_cost_function_3d.h:68-78,
+ * interpolated_grid.h:49-96), a translation prior and a rotation prior
+ * (translation_delta_cost_functor_3d.h, rotation_delta_cost_functor_3d.h:42-53), minimised over
+ * {translation[3], rotation[4]} with ceres::QuaternionParameterization.  No intensity grids
+ * (the constraint builder passes none) and only_optimize_yaw must be 0.  Same solver notes as
+ * csm_ceres_match2d_batch; grids are csm_grid3d handles.  Poses are {t xyz, q wxyz}. */
+typedef struct csm_ceres_options3d {
+  double occupied_space_weight[2]; /* occupied_space_weight_0 / _1 */
+  double translation_weight;
+  double rotation_weight;
+  int32_t only_optimize_yaw;       /* must be 0 */
+  int32_t use_nonmonotonic_steps;
+  int32_t max_num_iterations;
+  int32_t reserved;
+} csm_ceres_options3d;
+
+typedef struct csm_ceres_job3d {
+  const csm_grid3d* grid[2];       /* PointCloudAndHybridGridsPointers::hybrid_grid */
+  const float* xyz[2];             /* ::point_cloud, num_points x {x, y, z} (host memory) */
+  int32_t num_points[2];
+  int32_t num_clouds;              /* 1 or 2 */
+  int32_t reserved;
+  double target_translation[3];
+  double initial_pose[7];          /* initial_pose_estimate; its rotation is the rotation prior's target */
+} csm_ceres_job3d;
+
+typedef struct csm_ceres_result3d {
+  double pose_estimate[7];
+  double initial_cost, final_cost;
+  int32_t iterations, num_successful_steps, termination, reserved;  /* as csm_ceres_result2d */
+} csm_ceres_result3d;
+
+csm_status csm_ceres_match3d_batch(const csm_ceres_job3d* jobs, int32_t num_jobs,
+                                   const csm_ceres_options3d* options,
+                                   csm_ceres_result3d* results,
+                                   csm_stats* stats /* may be NULL */);
+
+/* Test hook: all residuals (clouds in order, 3 translation, 3 rotation) at `pose` and, if
+ * `jacobian` is not NULL, the row-major (rows x 6) Jacobian by the tangent-space parameters
+ * {dt[3], dq[3]}; the rotation prior's target is job->initial_pose's rotation. */
+csm_status csm_ceres_evaluate3d(const csm_ceres_job3d* job, const csm_ceres_options3d* options,
+                                const double pose[7], double* residuals, double* jacobian);
+
 /* ==== multi-GPU: one process per GPU, the sharded ConstraintBuilder queue ==== */
 /* Every (submap, node) search only depends on its submap's matcher
  * (constraints/constraint_builder_2d.cc:102-111), so the queue shards by submap with no
