@@ -293,6 +293,38 @@ int main() {
         std::fabs(got[0].pose.zbar_ij.translation().z() - tz) > 0.051)
       return 1;
     builder.DeleteScanMatcher(sid);
+
+    // the local pair again with the refinement of constraint_builder_3d.cc:265-275 on the
+    // device, and CeresScanMatcher3D::Match called directly
+    ConstraintBuilder3D refining(bo, &pool);
+    refining.set_device_refinement(true);
+    refining.MaybeAddConstraint(sid, &submap, mapping::NodeId{0, 0}, &data, transform::Rigid3d(),
+                                transform::Rigid3d());
+    refining.NotifyEndOfNode();
+    ConstraintBuilder3D::Result got_refined;
+    refining.WhenDone([&](const ConstraintBuilder3D::Result& r) { got_refined = r; });
+    if (got_refined.size() != 1) return 1;
+    {
+      const transform::Rigid3d& z = got_refined[0].pose.zbar_ij;
+      std::printf("RESULT cb3d_refined %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n",
+                  z.translation().x(), z.translation().y(), z.translation().z(), z.rotation().w(),
+                  z.rotation().x(), z.rotation().y(), z.rotation().z());
+    }
+    refining.DeleteScanMatcher(sid);
+    const mapping::scan_matching::DeviceHybridGrid device_grid(hybrid);
+    mapping::scan_matching::CeresScanMatcher3D ceres3(bo.ceres_scan_matcher_options_3d());
+    const transform::Rigid3d start({{0.22, -0.13, 0.08}}, transform::Quaterniond{1., 0., 0., 0.});
+    transform::Rigid3d refined_pose;
+    mapping::scan_matching::CeresScanMatcher3D::Summary summary3;
+    ceres3.Match(start.translation(), start, {{&data.high_resolution_point_cloud, &device_grid}},
+                 &refined_pose, &summary3);
+    std::printf("RESULT ceres3d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %d %d %d\n",
+                refined_pose.translation().x(), refined_pose.translation().y(),
+                refined_pose.translation().z(), refined_pose.rotation().w(),
+                refined_pose.rotation().x(), refined_pose.rotation().y(),
+                refined_pose.rotation().z(), summary3.initial_cost, summary3.final_cost,
+                summary3.iterations, summary3.num_successful_steps, summary3.termination);
+    if (!(summary3.final_cost <= summary3.initial_cost)) return 1;
   }
   return 0;
 }

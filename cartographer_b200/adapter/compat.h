@@ -257,6 +257,29 @@ class CeresScanMatcherOptions2D {
   double occupied_ = 20., translation_ = 10., rotation_ = 1.;
   CeresSolverOptions solver_;
 };
+// proto/scan_matching/ceres_scan_matcher_options_3d.proto (defaults: pose_graph.lua:49-60)
+class CeresScanMatcherOptions3D {
+ public:
+  int occupied_space_weight_size() const { return 2; }
+  double occupied_space_weight(int i) const { return occupied_[i]; }
+  double translation_weight() const { return translation_; }
+  double rotation_weight() const { return rotation_; }
+  bool only_optimize_yaw() const { return only_optimize_yaw_; }
+  const CeresScanMatcherOptions2D::CeresSolverOptions& ceres_solver_options() const {
+    return solver_;
+  }
+  CeresScanMatcherOptions2D::CeresSolverOptions* mutable_ceres_solver_options() {
+    return &solver_;
+  }
+  void set_occupied_space_weight(int i, double v) { occupied_[i] = v; }
+  void set_translation_weight(double v) { translation_ = v; }
+  void set_rotation_weight(double v) { rotation_ = v; }
+ private:
+  double occupied_[2] = {5., 30.};
+  double translation_ = 10., rotation_ = 1.;
+  bool only_optimize_yaw_ = false;
+  CeresScanMatcherOptions2D::CeresSolverOptions solver_{false, 10, 1};
+};
 // proto/scan_matching/fast_correlative_scan_matcher_options_3d.proto
 class FastCorrelativeScanMatcherOptions3D {
  public:
@@ -385,6 +408,10 @@ struct ConstraintBuilderOptions {
   scan_matching::proto::FastCorrelativeScanMatcherOptions2D fast2d_;
   scan_matching::proto::FastCorrelativeScanMatcherOptions3D fast3d_;
   scan_matching::proto::CeresScanMatcherOptions2D ceres2d_;
+  scan_matching::proto::CeresScanMatcherOptions3D ceres3d_;
+  const scan_matching::proto::CeresScanMatcherOptions3D& ceres_scan_matcher_options_3d() const {
+    return ceres3d_;
+  }
   const scan_matching::proto::CeresScanMatcherOptions2D& ceres_scan_matcher_options() const {
     return ceres2d_;
   }

@@ -349,6 +349,10 @@ class ConstraintBuilder3D {
   ConstraintBuilder3D(const ConstraintBuilder3D&) = delete;
   ConstraintBuilder3D& operator=(const ConstraintBuilder3D&) = delete;
 
+  // constraint_builder_3d.cc:265-275 on the device: every found match of a drained queue is
+  // refined by CeresScanMatcher3D (options.ceres_scan_matcher_options_3d()) in one launch.
+  void set_device_refinement(bool on) { device_refinement_ = on; }
+
   // constraint_builder_3d.cc:79-114
   void MaybeAddConstraint(const SubmapId& submap_id, const Submap3D* submap,
                           const NodeId& node_id, const TrajectoryNodeData* constant_data,
@@ -411,6 +415,7 @@ class ConstraintBuilder3D {
       csm_matcher3d_destroy(it->second);
       matchers_.erase(it);
     }
+    device_grids_.erase(submap_id);
     per_submap_sampler_.erase(submap_id);
   }
 
@@ -523,18 +528,56 @@ class ConstraintBuilder3D {
             static_cast<int32_t>(nodes.size()), jobs.data(), static_cast<int32_t>(jobs.size()),
             0, results.data(), nullptr));
       }
+      // ceres_scan_matcher_.Match(pose_estimate.translation(), pose_estimate, {{high cloud,
+      // high grid}, {low cloud, low grid}}, &constraint_transform, ...) for every found
+      // match (constraint_builder_3d.cc:265-275), one launch for the queue
+      std::vector<transform::Rigid3d> refined;
+      std::vector<size_t> refined_of(pending_.size(), 0);
+      if (device_refinement_) {
+        std::vector<scan_matching::CeresScanMatcher3D::Job> rjobs;
+        for (size_t i = 0; i < pending_.size(); ++i) {
+          if (!results[i].found) continue;
+          const Pending& p = pending_[i];
+          auto& grids = device_grids_[p.submap_id];
+          if (grids.first == nullptr) {
+            grids.first.reset(new scan_matching::DeviceHybridGrid(
+                p.submap->high_resolution_hybrid_grid(), device_));
+            grids.second.reset(new scan_matching::DeviceHybridGrid(
+                p.submap->low_resolution_hybrid_grid(), device_));
+          }
+          const csm_result3d& r = results[i];
+          scan_matching::CeresScanMatcher3D::Job job;
+          for (int k = 0; k < 3; ++k) job.target_translation[k] = r.pose_estimate[k];
+          job.initial_pose_estimate = transform::Rigid3d(
+              {{r.pose_estimate[0], r.pose_estimate[1], r.pose_estimate[2]}},
+              transform::Quaterniond{r.pose_estimate[3], r.pose_estimate[4], r.pose_estimate[5],
+                                     r.pose_estimate[6]});
+          job.point_clouds_and_hybrid_grids = {
+              {&p.constant_data->high_resolution_point_cloud, grids.first.get()},
+              {&p.constant_data->low_resolution_point_cloud, grids.second.get()}};
+          refined_of[i] = rjobs.size();
+          rjobs.push_back(job);
+        }
+        scan_matching::CeresScanMatcher3D(options_.ceres_scan_matcher_options_3d())
+            .MatchBatch(rjobs, &refined, nullptr);
+      }
       for (size_t i = 0; i < pending_.size(); ++i) {
         const csm_result3d& r = results[i];
         if (!r.found) continue;
-        // constraint_transform = the matcher's pose_estimate (Ceres-refined in a checkout,
-        // constraint_builder_3d.cc:261-275)
+        // constraint_transform = the matcher's pose_estimate, refined when
+        // set_device_refinement(true) (constraint_builder_3d.cc:261-275)
+        const transform::Rigid3d pose_estimate =
+            device_refinement_
+                ? refined[refined_of[i]]
+                : transform::Rigid3d(
+                      {{r.pose_estimate[0], r.pose_estimate[1], r.pose_estimate[2]}},
+                      transform::Quaterniond{r.pose_estimate[3], r.pose_estimate[4],
+                                             r.pose_estimate[5], r.pose_estimate[6]});
         result.push_back(Constraint{
             pending_[i].submap_id,
             pending_[i].node_id,
-            {transform::Rigid3d({{r.pose_estimate[0], r.pose_estimate[1], r.pose_estimate[2]}},
-                                transform::Quaterniond{r.pose_estimate[3], r.pose_estimate[4],
-                                                       r.pose_estimate[5], r.pose_estimate[6]}),
-             options_.loop_closure_translation_weight(), options_.loop_closure_rotation_weight()},
+            {pose_estimate, options_.loop_closure_translation_weight(),
+             options_.loop_closure_rotation_weight()},
             Constraint::INTER_SUBMAP});
       }
       pending_.clear();
@@ -554,6 +597,10 @@ class ConstraintBuilder3D {
   int num_finished_nodes_ = 0;
   std::deque<Pending> pending_;
   std::map<SubmapId, csm_matcher3d*> matchers_;
+  std::map<SubmapId, std::pair<std::unique_ptr<scan_matching::DeviceHybridGrid>,
+                               std::unique_ptr<scan_matching::DeviceHybridGrid>>>
+      device_grids_;   // high / low resolution grids for the refinement
+  bool device_refinement_ = false;
   std::map<SubmapId, common::FixedRatioSampler> per_submap_sampler_;
 };
 #endif  // !CSM_ADAPTER_REAL_CARTOGRAPHER

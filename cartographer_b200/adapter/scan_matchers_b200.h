@@ -507,6 +507,100 @@ class RealTimeCorrelativeScanMatcher3D {
  private:
   const proto::RealTimeCorrelativeScanMatcherOptions options_;
 };
+
+// ceres_scan_matcher_3d.h:44-66 without the intensity grid (the constraint builder passes
+// none, constraint_builder_3d.cc:265-275); grids are device-resident handles.  Summary: see
+// CeresScanMatcher2D::Summary.
+class CeresScanMatcher3D {
+ public:
+  using Summary = CeresScanMatcher2D::Summary;
+  struct PointCloudAndDeviceGrid {
+    const sensor::PointCloud* point_cloud;
+    const DeviceHybridGrid* hybrid_grid;
+  };
+  struct Job {
+    double target_translation[3];
+    transform::Rigid3d initial_pose_estimate;
+    std::vector<PointCloudAndDeviceGrid> point_clouds_and_hybrid_grids;   // 1 or 2
+  };
+
+  explicit CeresScanMatcher3D(const proto::CeresScanMatcherOptions3D& options)
+      : options_(options) {}
+
+  template <typename Vector3>
+  void Match(const Vector3& target_translation, const transform::Rigid3d& initial_pose_estimate,
+             const std::vector<PointCloudAndDeviceGrid>& point_clouds_and_hybrid_grids,
+             transform::Rigid3d* const pose_estimate, Summary* const summary) const {
+    std::vector<transform::Rigid3d> poses;
+    std::vector<Summary> summaries;
+    MatchBatch({Job{{target_translation.x(), target_translation.y(), target_translation.z()},
+                    initial_pose_estimate, point_clouds_and_hybrid_grids}},
+               &poses, &summaries);
+    *pose_estimate = poses[0];
+    if (summary != nullptr) *summary = summaries[0];
+  }
+
+  void MatchBatch(const std::vector<Job>& jobs, std::vector<transform::Rigid3d>* poses,
+                  std::vector<Summary>* summaries) const {
+    poses->clear();
+    if (summaries != nullptr) summaries->clear();
+    if (jobs.empty()) return;
+    std::vector<std::vector<float>> xyz;
+    xyz.reserve(2 * jobs.size());
+    std::vector<csm_ceres_job3d> cj(jobs.size());
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      const Job& job = jobs[i];
+      if (job.point_clouds_and_hybrid_grids.empty() ||
+          job.point_clouds_and_hybrid_grids.size() > 2)
+        std::abort();  // CHECK_EQ(occupied_space_weight_size(), size) (:111-112)
+      cj[i] = csm_ceres_job3d{};
+      cj[i].num_clouds = static_cast<int32_t>(job.point_clouds_and_hybrid_grids.size());
+      for (int b = 0; b < cj[i].num_clouds; ++b) {
+        xyz.push_back(b200_internal::Flatten(*job.point_clouds_and_hybrid_grids[b].point_cloud));
+        cj[i].grid[b] = job.point_clouds_and_hybrid_grids[b].hybrid_grid->handle();
+        cj[i].xyz[b] = xyz.back().data();
+        cj[i].num_points[b] =
+            static_cast<int32_t>(job.point_clouds_and_hybrid_grids[b].point_cloud->size());
+      }
+      for (int k = 0; k < 3; ++k) cj[i].target_translation[k] = job.target_translation[k];
+      const transform::Rigid3d& p = job.initial_pose_estimate;
+      const double init[7] = {p.translation().x(), p.translation().y(), p.translation().z(),
+                              p.rotation().w(), p.rotation().x(), p.rotation().y(),
+                              p.rotation().z()};
+      for (int k = 0; k < 7; ++k) cj[i].initial_pose[k] = init[k];
+    }
+    csm_ceres_options3d o{};
+    o.occupied_space_weight[0] = options_.occupied_space_weight(0);
+    o.occupied_space_weight[1] =
+        options_.occupied_space_weight_size() > 1 ? options_.occupied_space_weight(1) : 1.;
+    o.translation_weight = options_.translation_weight();
+    o.rotation_weight = options_.rotation_weight();
+    o.only_optimize_yaw = options_.only_optimize_yaw() ? 1 : 0;
+    o.use_nonmonotonic_steps = options_.ceres_solver_options().use_nonmonotonic_steps() ? 1 : 0;
+    o.max_num_iterations = options_.ceres_solver_options().max_num_iterations();
+    std::vector<csm_ceres_result3d> res(jobs.size());
+    b200_internal::Check(csm_ceres_match3d_batch(cj.data(), static_cast<int32_t>(cj.size()), &o,
+                                                 res.data(), nullptr));
+    for (const csm_ceres_result3d& r : res) {
+      poses->push_back(transform::Rigid3d(
+          {{r.pose_estimate[0], r.pose_estimate[1], r.pose_estimate[2]}},
+          transform::Quaterniond{r.pose_estimate[3], r.pose_estimate[4], r.pose_estimate[5],
+                                 r.pose_estimate[6]}));
+      if (summaries != nullptr) {
+        Summary s;
+        s.initial_cost = r.initial_cost;
+        s.final_cost = r.final_cost;
+        s.iterations = r.iterations;
+        s.num_successful_steps = r.num_successful_steps;
+        s.termination = r.termination;
+        summaries->push_back(s);
+      }
+    }
+  }
+
+ private:
+  const proto::CeresScanMatcherOptions3D options_;
+};
 #endif  // !CSM_ADAPTER_REAL_CARTOGRAPHER
 
 }  // namespace scan_matching

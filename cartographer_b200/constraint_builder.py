@@ -385,6 +385,8 @@ class ConstraintBuilderOptions3D:
     linear_xy_search_window: float = 5.0
     linear_z_search_window: float = 1.0
     angular_search_window: float = math.radians(15.0)
+    # scan_matching.CeresScanMatcherOptions3D, or None to leave matches unrefined
+    ceres_scan_matcher_options_3d: object = None
 
 
 @dataclass
@@ -419,12 +421,43 @@ class CudaExecutor3D:
         self.device = device
         self.threads = threads
         self.matchers = {}
-        self.stats = {"candidates_scored": 0, "device_ms": 0.0, "searched": 0}
+        self.grids = {}    # submap id -> (high, low) DeviceHybridGrid, for the refinement
+        self.stats = {"candidates_scored": 0, "device_ms": 0.0, "searched": 0, "refined": 0,
+                      "refine_device_ms": 0.0}
 
     def delete_matcher(self, submap_id):
         m = self.matchers.pop(submap_id, None)
         if m is not None:
             m.close()
+        for g in self.grids.pop(submap_id, ()):
+            g.close()
+
+    def refine(self, jobs, submaps, nodes, out):
+        """constraint_builder_3d.cc:265-275 for every found match of the drain, one launch."""
+        sm = self.sm
+        idx = [i for i, r in enumerate(out) if r is not None]
+        if not idx:
+            return out
+        pairs = []
+        for i in idx:
+            sid = jobs[i].submap_id
+            if sid not in self.grids:
+                sub = submaps[sid]
+                self.grids[sid] = (sm.DeviceHybridGrid(sub.high_resolution_hybrid_grid, self.device),
+                                   sm.DeviceHybridGrid(sub.low_resolution_hybrid_grid, self.device))
+            node = nodes[jobs[i].node_key]
+            hi, lo = self.grids[sid]
+            pairs.append([(node.high_resolution_point_cloud, hi),
+                          (node.low_resolution_point_cloud, lo)])
+        matcher = sm.CeresScanMatcher3D(self.options.ceres_scan_matcher_options_3d)
+        poses, _ = matcher.MatchBatch([out[i]["pose_estimate"][:3] for i in idx],
+                                      [out[i]["pose_estimate"] for i in idx], pairs)
+        self.stats["refined"] += len(idx)
+        self.stats["refine_device_ms"] += matcher.last_stats["device_ms"]
+        out = list(out)
+        for i, p in zip(idx, poses):
+            out[i] = dict(out[i], pose_estimate=np.array(p, np.float64))
+        return out
 
     def run(self, jobs, submaps, nodes):
         """Matchers are built first (one per submap, like the reference's creation
@@ -458,13 +491,17 @@ class CudaExecutor3D:
         self.stats["candidates_scored"] += st["candidates_scored"]
         self.stats["device_ms"] += st["device_ms"]
         self.stats["searched"] += len(jobs)
+        if self.options.ceres_scan_matcher_options_3d is not None:
+            out = self.refine(jobs, submaps, nodes, out)
         return out
 
 
 class ConstraintBuilder3D:
     """constraint_builder_3d.h:59-114 over the 3D engine; same sharding / single
     all_gather scheme as ConstraintBuilder2D.  Constraint poses are the fast
-    matcher's pose_estimate (submap <- node), i.e. pre-Ceres (:265-275)."""
+    matcher's pose_estimate (submap <- node); with
+    ConstraintBuilderOptions3D.ceres_scan_matcher_options_3d set they are first refined as
+    constraint_builder_3d.cc:265-275 does (one csm_ceres_match3d_batch launch per drain)."""
 
     def __init__(self, options, executor=None, process_group=None, device=0):
         self.options = options

@@ -839,3 +839,116 @@ class CeresScanMatcher2D:
             C.c_double(target_angle), ptr(p, C.c_double), ptr(res, C.c_double),
             ptr(jac, C.c_double) if jacobian else None))
         return res, jac
+
+
+# ===========================================================================
+# CeresScanMatcher3D (mapping/internal/3d/scan_matching/ceres_scan_matcher_3d.{h,cc})
+# ===========================================================================
+class CsmCeresOptions3D(C.Structure):
+    _fields_ = [("occupied_space_weight", C.c_double * 2), ("translation_weight", C.c_double),
+                ("rotation_weight", C.c_double), ("only_optimize_yaw", C.c_int32),
+                ("use_nonmonotonic_steps", C.c_int32), ("max_num_iterations", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class CsmCeresJob3D(C.Structure):
+    _fields_ = [("grid", C.c_void_p * 2), ("xyz", C.POINTER(C.c_float) * 2),
+                ("num_points", C.c_int32 * 2), ("num_clouds", C.c_int32),
+                ("reserved", C.c_int32), ("target_translation", C.c_double * 3),
+                ("initial_pose", C.c_double * 7)]
+
+
+class CsmCeresResult3D(C.Structure):
+    _fields_ = [("pose_estimate", C.c_double * 7), ("initial_cost", C.c_double),
+                ("final_cost", C.c_double), ("iterations", C.c_int32),
+                ("num_successful_steps", C.c_int32), ("termination", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+@dataclass
+class CeresScanMatcherOptions3D:
+    """proto/scan_matching/ceres_scan_matcher_options_3d.proto; defaults = the constraint
+    builder's (configuration_files/pose_graph.lua:49-60).  only_optimize_yaw = true and
+    intensity cost functions are not supported."""
+    occupied_space_weight_0: float = 5.0
+    occupied_space_weight_1: float = 30.0
+    translation_weight: float = 10.0
+    rotation_weight: float = 1.0
+    only_optimize_yaw: bool = False
+    use_nonmonotonic_steps: bool = False
+    max_num_iterations: int = 10
+
+    def _c(self):
+        o = CsmCeresOptions3D()
+        o.occupied_space_weight[0] = self.occupied_space_weight_0
+        o.occupied_space_weight[1] = self.occupied_space_weight_1
+        o.translation_weight = self.translation_weight
+        o.rotation_weight = self.rotation_weight
+        o.only_optimize_yaw = int(self.only_optimize_yaw)
+        o.use_nonmonotonic_steps = int(self.use_nonmonotonic_steps)
+        o.max_num_iterations = int(self.max_num_iterations)
+        return o
+
+
+class CeresScanMatcher3D:
+    """ceres_scan_matcher_3d.h:44-66.  `point_clouds_and_hybrid_grids` is a list of
+    (point_cloud, DeviceHybridGrid) pairs — one or two, high resolution first — as
+    PointCloudAndHybridGridsPointers without the intensity grid.  Poses are
+    {tx, ty, tz, qw, qx, qy, qz}."""
+
+    def __init__(self, options=None):
+        self.options = options if options is not None else CeresScanMatcherOptions3D()
+
+    def _job(self, job, target_translation, initial_pose_estimate, pairs, keep):
+        job.num_clouds = len(pairs)
+        for b, (cloud, grid) in enumerate(pairs):
+            xyz = _f32(cloud)
+            keep.append(xyz)
+            job.grid[b] = grid._h
+            job.xyz[b] = ptr(xyz, C.c_float)
+            job.num_points[b] = len(xyz)
+        for k in range(3):
+            job.target_translation[k] = float(target_translation[k])
+        for k in range(7):
+            job.initial_pose[k] = float(initial_pose_estimate[k])
+
+    def Match(self, target_translation, initial_pose_estimate, point_clouds_and_hybrid_grids):
+        poses, summaries = self.MatchBatch([target_translation], [initial_pose_estimate],
+                                           [point_clouds_and_hybrid_grids])
+        return poses[0], summaries[0]
+
+    def MatchBatch(self, target_translations, initial_pose_estimates, pairs_per_job):
+        """Many Match calls in one launch (csm_ceres_match3d_batch)."""
+        n = len(pairs_per_job)
+        jobs = (CsmCeresJob3D * n)()
+        keep = []
+        for j in range(n):
+            self._job(jobs[j], target_translations[j], initial_pose_estimates[j],
+                      pairs_per_job[j], keep)
+        res = (CsmCeresResult3D * n)()
+        stats = CsmStats()
+        opt = self.options._c()
+        check(lib().csm_ceres_match3d_batch(jobs, C.c_int32(n), C.byref(opt), res,
+                                            C.byref(stats)))
+        self.last_stats = stats.as_dict()
+        poses = np.array([[r.pose_estimate[k] for k in range(7)] for r in res], np.float64)
+        summaries = [dict(initial_cost=r.initial_cost, final_cost=r.final_cost,
+                          iterations=r.iterations, num_successful_steps=r.num_successful_steps,
+                          termination=CERES_TERMINATION[r.termination]) for r in res]
+        return poses, summaries
+
+    def Evaluate(self, pairs, pose, target_translation, target_rotation, jacobian=True):
+        """All residuals (clouds in order, 3 translation, 3 rotation) and the (rows x 6)
+        tangent-space Jacobian at `pose` (csm_ceres_evaluate3d)."""
+        job = CsmCeresJob3D()
+        keep = []
+        self._job(job, target_translation, [0.0, 0.0, 0.0] + list(target_rotation), pairs, keep)
+        rows = sum(len(k) for k in keep) + 6
+        res = np.zeros(rows, np.float64)
+        jac = np.zeros((rows, 6), np.float64) if jacobian else None
+        p = np.ascontiguousarray(pose, np.float64)
+        opt = self.options._c()
+        check(lib().csm_ceres_evaluate3d(C.byref(job), C.byref(opt), ptr(p, C.c_double),
+                                         ptr(res, C.c_double),
+                                         ptr(jac, C.c_double) if jacobian else None))
+        return res, jac

@@ -39,6 +39,21 @@ def test_struct_layouts(csm):
     assert C.sizeof(csm.CsmJob2D) == 48
     assert C.sizeof(csm.CsmResult2D) == 48
     assert csm.JOB2D_DTYPE.itemsize == 48 and csm.RESULT2D_DTYPE.itemsize == 48
+    # the refinement's records against the C compiler's view of include/csm_abi.h
+    import subprocess
+    import tempfile
+    from cartographer_b200 import scan_matching as sm
+    names = ["csm_ceres_options2d", "csm_ceres_job2d", "csm_ceres_result2d",
+             "csm_ceres_options3d", "csm_ceres_job3d", "csm_ceres_result3d"]
+    src = '#include <stdio.h>\n#include "include/csm_abi.h"\nint main(){printf("' + \
+        " ".join(["%zu"] * len(names)) + '\\n",' + ",".join("sizeof(%s)" % n for n in names) + ");}"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "sz.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", ROOT, os.path.join(d, "sz.c"), "-o", os.path.join(d, "sz")])
+        sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "sz")]).split()]
+    py = [sm.CsmCeresOptions2D, sm.CsmCeresJob2D, sm.CsmCeresResult2D, sm.CsmCeresOptions3D,
+          sm.CsmCeresJob3D, sm.CsmCeresResult3D]
+    assert sizes == [C.sizeof(t) for t in py]
 
 
 def test_invalid_arguments_return_status(csm):

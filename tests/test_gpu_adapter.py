@@ -146,6 +146,19 @@ def test_adapter_selftest_runs_on_device(oracle):
     assert _f(got[0]) == want["score"]
     np.testing.assert_array_equal([float(v) for v in got[1:8]], want["pose"])
     assert _f(got[8]) == want["rotational_score"] and _f(got[9]) == want["low_resolution_score"]
+    # ConstraintBuilder3D with the device refinement (constraint_builder_3d.cc:265-275) and
+    # CeresScanMatcher3D::Match through the C++ class (doubles, 1e-7)
+    refined = oracle.ceres3d_match([(cloud3, ohi), (cloud3, olo)], want["pose"][:3], want["pose"])
+    got = res["cb3d_refined"][0]
+    np.testing.assert_allclose([float(v) for v in got[0:7]], refined["pose"], rtol=0, atol=1e-7)
+    start = [0.22, -0.13, 0.08, 1, 0, 0, 0]
+    direct = oracle.ceres3d_match([(cloud3, ohi)], start[:3], start, occupied_space_weights=[5.0])
+    got = res["ceres3d"][0]
+    np.testing.assert_allclose([float(v) for v in got[0:7]], direct["pose"], rtol=0, atol=1e-7)
+    assert float(got[7]) == pytest.approx(direct["initial_cost"], rel=1e-12)
+    assert float(got[8]) == pytest.approx(direct["final_cost"], rel=1e-9)
+    assert [int(got[9]), int(got[10])] == [direct["iterations"], direct["num_successful_steps"]]
+    assert oracle.CERES_TERMINATION[int(got[11])] == direct["termination"]
     # RealTimeCorrelativeScanMatcher3D::Match
     want = oracle.rt3d_match(ohi, cloud3, [0.25, -0.1, 0.05, 1, 0, 0, 0], 0.1, 0.01, 0.1, 1.0)
     got = res["rt3d"][0]

@@ -112,6 +112,9 @@ def _config3d(sm, oracle, rings, az, n_nodes, seed):
     ident = [0, 0, 0, 1, 0, 0, 0]
     rng = np.random.RandomState(9)
     n_found = 0
+    # the post-match refinement at the same size (constraint_builder_3d.cc:265-275)
+    dhi, dlo = sm.DeviceHybridGrid(hi), sm.DeviceHybridGrid(lo)
+    ceres = sm.CeresScanMatcher3D()
     for n in nodes:
         init = n["pose"].copy()
         init[:3] += rng.uniform(-1, 1, 3) * [2.0, 2.0, 0.3]
@@ -129,6 +132,17 @@ def _config3d(sm, oracle, rings, az, n_nodes, seed):
             np.testing.assert_array_equal(got["pose_estimate"], want["pose"])
             assert got["rotational_score"] == want["rotational_score"]
             assert got["low_resolution_score"] == want["low_resolution_score"]
+            est = got["pose_estimate"]
+            rp, rs = ceres.Match(est[:3], est, [(n["cloud"], dhi), (n["low"], dlo)])
+            rw = oracle.ceres3d_match([(n["cloud"], ohi), (n["low"], olo)], est[:3], est)
+            assert np.allclose(rp, rw["pose"], rtol=0, atol=1e-7), (rp, rw["pose"])
+            assert rs["iterations"] == rw["iterations"]
+            assert rs["num_successful_steps"] == rw["num_successful_steps"]
+            assert rs["termination"] == rw["termination"]
+            assert rs["final_cost"] == pytest.approx(rw["final_cost"], rel=1e-9)
+            assert rs["final_cost"] <= rs["initial_cost"]
+    dhi.close()
+    dlo.close()
     m.close()
     return n_found, len(nodes[0]["cloud"])
 
