@@ -47,22 +47,15 @@ using std::isfinite;
 
 #include "../../cartographer_b200/csrc/refine3d.cu"
 
-extern "C" {
-
-// Dense boxes as csm_grid3d_create builds them: vol[b] has n[b][0..2] cells from lo[b][0..2].
-// opts = {translation_weight, rotation_weight, use_nonmonotonic_steps, max_num_iterations,
-//         occupied_space_weight_0, occupied_space_weight_1}
-// out = {pose[7], initial_cost, final_cost, iterations, num_successful_steps, termination}
-void emu_ceres_match3d(int num_clouds, const uint16_t* const* vol, const int32_t* lo,
-                       const int32_t* n, const float* resolution, const float* const* xyz,
-                       const int32_t* npts, const double* opts, const double* target_t,
-                       const double* init_pose, double* out) {
-  csm::Ref3JobDev job;
-  std::memset(&job, 0, sizeof(job));
-  job.num_clouds = num_clouds;
-  std::vector<float> cloud;
+namespace {
+void FillEmuJob(int num_clouds, const uint16_t* const* vol, const int32_t* lo, const int32_t* n,
+                const float* resolution, const float* const* xyz, const int32_t* npts,
+                const double* target_t, const double* init_pose, csm::Ref3JobDev* job,
+                std::vector<float>* cloud) {
+  std::memset(job, 0, sizeof(*job));
+  job->num_clouds = num_clouds;
   for (int b = 0; b < num_clouds; ++b) {
-    csm::Ref3Cloud& c = job.c[b];
+    csm::Ref3Cloud& c = job->c[b];
     c.vol = vol[b];
     for (int a = 0; a < 3; ++a) {
       c.lo[a] = lo[3 * b + a];
@@ -75,11 +68,55 @@ void emu_ceres_match3d(int num_clouds, const uint16_t* const* vol, const int32_t
     c.bias = kMinProbability - c.k_scale;
     c.min_probability = kMinProbability;
     c.npts = npts[b];
-    c.xyz_off = static_cast<long long>(cloud.size());
-    cloud.insert(cloud.end(), xyz[b], xyz[b] + 3 * static_cast<size_t>(npts[b]));
+    c.xyz_off = static_cast<long long>(cloud->size());
+    cloud->insert(cloud->end(), xyz[b], xyz[b] + 3 * static_cast<size_t>(npts[b]));
   }
-  for (int k = 0; k < 3; ++k) job.target_t[k] = target_t[k];
-  for (int k = 0; k < 7; ++k) job.init[k] = init_pose[k];
+  for (int k = 0; k < 3; ++k) job->target_t[k] = target_t[k];
+  for (int k = 0; k < 7; ++k) job->init[k] = init_pose[k];
+}
+}  // namespace
+
+extern "C" {
+
+// k_ceres_evaluate3d, one emulated thread after the other (the kernel has no barriers).
+// opts = {translation_weight, rotation_weight, occupied_space_weight_0, _1}
+void emu_ceres_evaluate3d(int num_clouds, const uint16_t* const* vol, const int32_t* lo,
+                          const int32_t* n, const float* resolution, const float* const* xyz,
+                          const int32_t* npts, const double* opts, const double* target_t,
+                          const double* target_q, const double* pose, int with_jacobian,
+                          double* residuals, double* jacobian) {
+  csm::Ref3JobDev job;
+  std::vector<float> cloud;
+  const double init[7] = {0., 0., 0., target_q[0], target_q[1], target_q[2], target_q[3]};
+  FillEmuJob(num_clouds, vol, lo, n, resolution, xyz, npts, target_t, init, &job, &cloud);
+  csm::Ref3Opts P;
+  std::memset(&P, 0, sizeof(P));
+  P.translation_weight = opts[0];
+  P.rotation_weight = opts[1];
+  P.occupied_space_weight[0] = opts[2];
+  P.occupied_space_weight[1] = opts[3];
+  int rows = 6;
+  for (int b = 0; b < num_clouds; ++b) rows += npts[b];
+  blockDim.x = 256;
+  for (int blk = 0; blk < (rows + 255) / 256; ++blk)
+    for (int t = 0; t < 256; ++t) {
+      blockIdx.x = blk;
+      threadIdx.x = t;
+      csm::k_ceres_evaluate3d(&job, P, cloud.data(), pose, with_jacobian, residuals, jacobian);
+    }
+}
+
+// Dense boxes as csm_grid3d_create builds them: vol[b] has n[b][0..2] cells from lo[b][0..2].
+// opts = {translation_weight, rotation_weight, use_nonmonotonic_steps, max_num_iterations,
+//         occupied_space_weight_0, occupied_space_weight_1}
+// out = {pose[7], initial_cost, final_cost, iterations, num_successful_steps, termination}
+void emu_ceres_match3d(int num_clouds, const uint16_t* const* vol, const int32_t* lo,
+                       const int32_t* n, const float* resolution, const float* const* xyz,
+                       const int32_t* npts, const double* opts, const double* target_t,
+                       const double* init_pose, double* out) {
+  csm::Ref3JobDev job;
+  std::vector<float> cloud;
+  FillEmuJob(num_clouds, vol, lo, n, resolution, xyz, npts, target_t, init_pose, &job, &cloud);
   csm::Ref3Opts P;
   P.translation_weight = opts[0];
   P.rotation_weight = opts[1];

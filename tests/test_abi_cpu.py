@@ -54,6 +54,23 @@ def test_struct_layouts(csm):
     py = [sm.CsmCeresOptions2D, sm.CsmCeresJob2D, sm.CsmCeresResult2D, sm.CsmCeresOptions3D,
           sm.CsmCeresJob3D, sm.CsmCeresResult3D]
     assert sizes == [C.sizeof(t) for t in py]
+    # ... and every field offset
+    fields = [(n, t, f[0]) for n, t in zip(names, py) for f in t._fields_]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "include/csm_abi.h"\nint main(){' + \
+        "".join('printf("%%zu\\n", offsetof(%s, %s));' % (n, f) for n, _, f in fields) + "}"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "off.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", ROOT, os.path.join(d, "off.c"), "-o", os.path.join(d, "off")])
+        offsets = [int(v) for v in subprocess.check_output([os.path.join(d, "off")]).split()]
+    assert offsets == [getattr(t, f).offset for _, t, f in fields]
+    # arrays of handles / pointers marshal element-wise
+    job = sm.CsmCeresJob3D()
+    cloud = np.zeros((4, 3), np.float32)
+    job.grid[1] = C.c_void_p(0x1234)
+    job.xyz[1] = cloud.ctypes.data_as(C.POINTER(C.c_float))
+    raw = bytes(job)
+    assert int.from_bytes(raw[8:16], "little") == 0x1234
+    assert int.from_bytes(raw[24:32], "little") == cloud.ctypes.data
 
 
 def test_invalid_arguments_return_status(csm):

@@ -104,3 +104,48 @@ def test_emulated_kernel_two_clouds_with_rotation(oracle, emu, nonmonotonic):
         [(cloud, grid), (POINTS, grid2)], init[:3], init, occupied_space_weights=[5.0, 30.0],
         translation_weight=10.0, rotation_weight=1.0,
         use_nonmonotonic_steps=bool(nonmonotonic), max_num_iterations=12))
+
+
+def test_emulated_evaluate_kernel_rows(oracle, emu):
+    """k_ceres_evaluate3d (the GPU tests' residual / Jacobian hook): row indexing over two
+    clouds and the six prior rows, against the oracle — values must be identical."""
+    spec, grid = hybrid(oracle, 1.0, POINTS + np.array([-1, 0, 0], np.float32))
+    spec2, grid2 = hybrid(oracle, 2.0, POINTS + np.array([-1, 0, 0], np.float32))
+    rng = np.random.RandomState(3)
+    cloud = (POINTS[rng.randint(0, 7, 270)] + rng.uniform(-0.4, 0.4, (270, 3))).astype(np.float32)
+    a = 0.07
+    q = np.array([math.cos(a), math.sin(a) * 0.2, -math.sin(a) * 0.3, math.sin(a) * 0.933])
+    pose = np.concatenate([[-0.95, 0.04, 0.06], q / np.linalg.norm(q)])
+    tq = np.array([math.cos(0.02), 0.0, 0.0, math.sin(0.02)])
+    pairs = [(cloud, spec), (POINTS, spec2)]
+    num = 2
+    vols, los, ns, res, xs, npts = [], [], [], [], [], []
+    for xyz, (r, idx, val) in pairs:
+        v, lo, n = dense_box(idx, val)
+        vols.append(v)
+        los += list(lo)
+        ns += list(n)
+        res.append(r)
+        xs.append(np.ascontiguousarray(xyz, np.float32))
+        npts.append(len(xyz))
+
+    def p(arr, ty):
+        return arr.ctypes.data_as(C.POINTER(ty))
+    volp = (C.POINTER(C.c_uint16) * num)(*[p(v, C.c_uint16) for v in vols])
+    xp = (C.POINTER(C.c_float) * num)(*[p(x, C.c_float) for x in xs])
+    lo, n = np.array(los, np.int32), np.array(ns, np.int32)
+    rs, npt = np.array(res, np.float32), np.array(npts, np.int32)
+    rows = sum(npts) + 6
+    op = np.array([10.0, 1.0, 5.0, 30.0])
+    tt = np.array([-1.0, 0.0, 0.0])
+    for with_jac in (1, 0):
+        got_r, got_j = np.zeros(rows), np.zeros((rows, 6))
+        emu.emu_ceres_evaluate3d(C.c_int(num), volp, p(lo, C.c_int32), p(n, C.c_int32),
+                                 p(rs, C.c_float), xp, p(npt, C.c_int32), p(op, C.c_double),
+                                 p(tt, C.c_double), p(tq, C.c_double), p(pose, C.c_double),
+                                 C.c_int(with_jac), p(got_r, C.c_double), p(got_j, C.c_double))
+        want_r, want_j = oracle.ceres3d_evaluate([(cloud, grid), (POINTS, grid2)], pose, tt, tq,
+                                                 jacobian=bool(with_jac))
+        assert np.array_equal(got_r, want_r)
+        if with_jac:
+            assert np.array_equal(got_j, want_j)
