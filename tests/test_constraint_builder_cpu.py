@@ -155,11 +155,14 @@ def _fill(builder, submaps, clouds, poses):
         builder.NotifyEndOfNode()
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, refine=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     opts, submaps, clouds, poses = _small_queue()
+    if refine:
+        from cartographer_b200 import scan_matching as sm
+        opts.ceres_scan_matcher_options = sm.CeresScanMatcherOptions2D()
     ex = OracleExecutor(opts)
     b = cb.ConstraintBuilder2D(opts, executor=ex, process_group=dist.group.WORLD)
     _fill(b, submaps, clouds, poses)
@@ -169,8 +172,14 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_sharded_queue_world2_gloo():
+@pytest.mark.parametrize("refine", [False, True])
+def test_sharded_queue_world2_gloo(refine):
+    """refine=True: the owner of a submap refines its found matches BEFORE the single
+    all-gather, so every rank still ends with the single-process Result."""
     opts, submaps, clouds, poses = _small_queue()
+    if refine:
+        from cartographer_b200 import scan_matching as sm
+        opts.ceres_scan_matcher_options = sm.CeresScanMatcherOptions2D()
     single = cb.ConstraintBuilder2D(opts, executor=OracleExecutor(opts))
     _fill(single, submaps, clouds, poses)
     want = single.WhenDone(lambda r: None)
@@ -183,7 +192,7 @@ def test_sharded_queue_world2_gloo():
     s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, refine)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
