@@ -76,3 +76,21 @@ def test_emulated_kernel_on_a_smooth_field(oracle, emu, nonmonotonic):
     out = _run(emu, grid, cloud, init[:2], init, [20.0, 10.0, 1.0, nonmonotonic, 15])
     _check(oracle, out, oracle.ceres2d_match(grid, cloud, init[:2], init, 20.0, 10.0, 1.0,
                                              bool(nonmonotonic), 15))
+
+
+@pytest.mark.parametrize("prior_weight,termination", [(1e3, "FUNCTION_TOLERANCE"),
+                                                      (1e5, "PARAMETER_TOLERANCE")])
+def test_emulated_kernel_tolerance_exits(oracle, emu, prior_weight, termination):
+    """Stiff priors make the first trial step tiny: the function / parameter tolerance exits
+    (which stop BEFORE taking the step) are reached in the kernel as in the oracle."""
+    rng = np.random.RandomState(8)
+    grid = smooth_grid(oracle)
+    ang = rng.uniform(0, 2 * np.pi, 200)
+    rad = rng.uniform(0.02, 0.3, 200)
+    cloud = np.stack([rad * np.cos(ang), rad * np.sin(ang), np.zeros(200)], 1).astype(np.float32)
+    init = np.array([0.525 + 0.05, -0.125 - 0.04, 0.3])
+    want = oracle.ceres2d_match(grid, cloud, init[:2], init, 20.0, prior_weight, prior_weight,
+                                True, 50)
+    assert want["termination"] == termination
+    out = _run(emu, grid, cloud, init[:2], init, [20.0, prior_weight, prior_weight, 1, 50])
+    _check(oracle, out, want)

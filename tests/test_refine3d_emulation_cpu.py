@@ -149,3 +149,20 @@ def test_emulated_evaluate_kernel_rows(oracle, emu):
         assert np.array_equal(got_r, want_r)
         if with_jac:
             assert np.array_equal(got_j, want_j)
+
+
+@pytest.mark.parametrize("prior_weight,termination", [(1e2, "FUNCTION_TOLERANCE"),
+                                                      (1e4, "PARAMETER_TOLERANCE"),
+                                                      (1e6, "PARAMETER_TOLERANCE")])
+def test_emulated_kernel_tolerance_exits(oracle, emu, prior_weight, termination):
+    """Stiff priors: the tolerance exits (before the step is taken) in the kernel as in the
+    oracle, including a successful step followed by a parameter-tolerance stop."""
+    spec, grid = hybrid(oracle, 1.0, POINTS + np.array([-1, 0, 0], np.float32))
+    init = [-0.9, -0.2, 0.2, 1.0, 0.0, 0.0, 0.0]
+    want = oracle.ceres3d_match([(POINTS, grid)], init[:3], init, occupied_space_weights=[1.0],
+                                translation_weight=prior_weight, rotation_weight=prior_weight,
+                                use_nonmonotonic_steps=False, max_num_iterations=30)
+    assert want["termination"] == termination
+    out = run_emulation(emu, [(POINTS, spec)], init[:3], init,
+                        [prior_weight, prior_weight, 0, 30, 1.0, 1.0])
+    _check(oracle, out, want)
